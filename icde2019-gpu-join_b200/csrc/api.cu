@@ -1,0 +1,858 @@
+// api.cu -- host side of libgpujoin.so: the C ABI declared in include/gpujoin.h.
+//
+// Shape follows the reference's in-GPU operator outOfGPU_Join1_payload
+// (/root/reference/src/hash_join_clustered_probe.cu:802-994): allocate device scratch, run
+// partition(R), partition(S), join, read back the aggregate -- but allocation happens once in
+// gj_create, all work is enqueued on one stream without host round trips, timing uses CUDA
+// events, and errors are returned instead of exit()ed (common.h:132-141).
+#include "../../include/gpujoin.h"
+#include "kernels.cuh"
+
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+using namespace gj;
+
+// ------------------------------------------------------------------------------------------
+// errors, launch accounting
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(GJ_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,            \
+                        cudaGetErrorString(e_));                                              \
+    } while (0)
+#define LAUNCHED()                                                                            \
+    do {                                                                                      \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+        ++ctx->launches;                                                                      \
+        CK(cudaGetLastError());                                                               \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// kernel variant tables
+// ------------------------------------------------------------------------------------------
+typedef void (*scatter_fn)(ScatterArgs);
+struct ScatterCfg { int threads, ipt, mode; scatter_fn col, packed; };
+#define GJ_SC(T, I, M) { T, I, M, scatter_kernel<T, I, M, true>, scatter_kernel<T, I, M, false> }
+static const ScatterCfg kScatter[] = {
+    GJ_SC(256, 16, 0), GJ_SC(512, 16, 0), GJ_SC(256, 16, 1), GJ_SC(512, 16, 1),
+    GJ_SC(512, 8, 0),  GJ_SC(1024, 8, 0), GJ_SC(1024, 8, 1), GJ_SC(512, 8, 1),
+    GJ_SC(256, 8, 0),  GJ_SC(256, 8, 1),
+};
+static const int kNumScatter = (int)(sizeof(kScatter) / sizeof(kScatter[0]));
+
+typedef void (*join_fn)(JoinArgs);
+struct JoinCfg { int threads, cap; join_fn agg, mat; };
+#define GJ_JC(T, C) { T, C, join_kernel<T, C, false>, join_kernel<T, C, true> }
+static const JoinCfg kJoin[] = {
+    GJ_JC(512, 8192), GJ_JC(256, 8192), GJ_JC(256, 4096), GJ_JC(512, 4096), GJ_JC(1024, 8192),
+    GJ_JC(128, 4096), GJ_JC(128, 2048), GJ_JC(256, 2048),
+};
+static const int kNumJoin = (int)(sizeof(kJoin) / sizeof(kJoin[0]));
+
+static size_t join_smem(const JoinCfg& c, bool mat) {
+    return (size_t)c.cap * (sizeof(tup_t) + 4 + 2) + (mat ? (size_t)JOIN_STAGE * 8 : 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct RelMeta {
+    uint32_t* ghist;             // 2^15 (zeroed per call)
+    unsigned long long* desc;    // scan descriptors (zeroed per call)
+    uint32_t* ticket;            // scan ticket (zeroed per call)
+    uint32_t* off;               // 2^15 + 1
+    uint32_t* cur1;              // 256
+    uint32_t* cur2;              // 2^15
+    uint32_t* tile_prefix;       // 257
+};
+
+constexpr uint32_t FINE_MAX = 1u << MAX_RADIX_BITS;
+constexpr uint32_t SCAN_TILES_MAX = FINE_MAX / SCAN_TILE;
+constexpr int N_EVENTS = 64;
+
+struct gj_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    uint64_t maxR = 0, maxS = 0;
+    tup_t* out[2] = {nullptr, nullptr};   // partitioned tuples of R (slot 0) / S (slot 1)
+    tup_t* scratch = nullptr;             // first-pass output, max(maxR, maxS) tuples
+    unsigned char* zero_block = nullptr;
+    size_t zero_bytes = 0;
+    unsigned char* meta_block = nullptr;
+    RelMeta meta[2];
+    uint4* units = nullptr;
+    uint64_t units_cap = 0;
+    uint32_t* num_units = nullptr;
+    uint32_t* unit_ticket = nullptr;
+    unsigned long long* result = nullptr;
+    unsigned long long* h_result = nullptr;   // pinned
+    tup_t** d_dst_bases = nullptr;            // 256 pointers (shuffle)
+    cudaEvent_t ev[5] = {};
+    cudaEvent_t pev[2][3] = {};   // per scatter launch: [role][before p1, after p1, after p2]
+    cudaEvent_t cev[N_EVENTS] = {};
+    int32_t* d_in[4] = {nullptr, nullptr, nullptr, nullptr};   // host-entry staging Rk,Rp,Sk,Sp
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    uint32_t launches = 0;
+    // options
+    int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 0, opt_scatter_cfg2 = 0,
+            opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20;
+    bool attrs_set = false;
+};
+
+struct Rel {   // one input relation as handed to the pipeline
+    const int32_t* keys = nullptr;
+    const int32_t* pays = nullptr;
+    const tup_t* tup = nullptr;     // packed alternative
+    uint64_t n = 0;
+    int slot = 0;                   // 0 = user's R, 1 = user's S
+};
+
+static int set_func_attrs(gj_ctx* ctx) {
+    if (ctx->attrs_set) return GJ_OK;
+    CK(cudaFuncSetAttribute(hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << MAX_RADIX_BITS));
+    CK(cudaFuncSetAttribute(hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << MAX_RADIX_BITS));
+    for (int i = 0; i < kNumScatter; ++i) {
+        const int bytes = kScatter[i].threads * kScatter[i].ipt * (int)sizeof(tup_t);
+        CK(cudaFuncSetAttribute(kScatter[i].col, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        CK(cudaFuncSetAttribute(kScatter[i].packed, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    }
+    for (int i = 0; i < kNumJoin; ++i) {
+        CK(cudaFuncSetAttribute(kJoin[i].agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem(kJoin[i], false)));
+        CK(cudaFuncSetAttribute(kJoin[i].mat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem(kJoin[i], true)));
+    }
+    ctx->attrs_set = true;
+    return GJ_OK;
+}
+
+extern "C" const char* gj_last_error(void) { return g_err; }
+extern "C" int gj_version(void) { return GJ_VERSION; }
+extern "C" uint64_t gj_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" void gj_destroy(gj_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->out[0]); cudaFree(ctx->out[1]); cudaFree(ctx->scratch);
+    cudaFree(ctx->zero_block); cudaFree(ctx->meta_block); cudaFree(ctx->units);
+    cudaFree(ctx->d_dst_bases); cudaFree(ctx->flush_buf);
+    for (int i = 0; i < 4; ++i) cudaFree(ctx->d_in[i]);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& r : ctx->pev) for (auto& e : r) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->cev) if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) {
+    const uint64_t LIM = 0xFFFFFFFFull - (1ull << 20);
+    if (max_R > LIM || max_S > LIM) return fail(GJ_ERR_ARG, "relations are limited to %llu tuples", (unsigned long long)LIM);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(GJ_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(GJ_ERR_CUDA, "device %d is sm_%d%d; libgpujoin is built for sm_100a only", device, prop.major, prop.minor);
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->maxR = std::max<uint64_t>(max_R, 1);
+    ctx->maxS = std::max<uint64_t>(max_S, 1);
+    CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
+    for (auto& r : ctx->pev) for (auto& e : r) CK(cudaEventCreate(&e));
+    for (auto& e : ctx->cev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+    const uint64_t mx = std::max(ctx->maxR, ctx->maxS);
+    if (cudaMalloc(&ctx->out[0], ctx->maxR * sizeof(tup_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->out[1], ctx->maxS * sizeof(tup_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->scratch, mx * sizeof(tup_t)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GJ_ERR_NOMEM, "cudaMalloc of %.2f GB partition buffers failed", (ctx->maxR + ctx->maxS + mx) * 8e-9);
+    }
+    // zeroed-per-call block: ghist x2 | desc x2 | tickets + counters | result
+    size_t zb = 0;
+    const size_t o_hist = zb;   zb += 2 * FINE_MAX * sizeof(uint32_t);
+    const size_t o_desc = zb;   zb += 2 * SCAN_TILES_MAX * sizeof(unsigned long long);
+    const size_t o_cnt = zb;    zb += 16 * sizeof(uint32_t);
+    const size_t o_res = zb;    zb += 4 * sizeof(unsigned long long);
+    ctx->zero_bytes = zb;
+    CK(cudaMalloc(&ctx->zero_block, zb));
+    // persistent metadata block
+    size_t mb = 0;
+    const size_t o_off = mb;    mb += 2 * (FINE_MAX + 4) * sizeof(uint32_t);
+    const size_t o_cur1 = mb;   mb += 2 * NB_MAX * sizeof(uint32_t);
+    const size_t o_cur2 = mb;   mb += 2 * FINE_MAX * sizeof(uint32_t);
+    const size_t o_tp = mb;     mb += 2 * (NB_MAX + 4) * sizeof(uint32_t);
+    CK(cudaMalloc(&ctx->meta_block, mb));
+    for (int r = 0; r < 2; ++r) {
+        RelMeta& m = ctx->meta[r];
+        m.ghist = reinterpret_cast<uint32_t*>(ctx->zero_block + o_hist) + (size_t)r * FINE_MAX;
+        m.desc = reinterpret_cast<unsigned long long*>(ctx->zero_block + o_desc) + (size_t)r * SCAN_TILES_MAX;
+        m.ticket = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + r;
+        m.off = reinterpret_cast<uint32_t*>(ctx->meta_block + o_off) + (size_t)r * (FINE_MAX + 4);
+        m.cur1 = reinterpret_cast<uint32_t*>(ctx->meta_block + o_cur1) + (size_t)r * NB_MAX;
+        m.cur2 = reinterpret_cast<uint32_t*>(ctx->meta_block + o_cur2) + (size_t)r * FINE_MAX;
+        m.tile_prefix = reinterpret_cast<uint32_t*>(ctx->meta_block + o_tp) + (size_t)r * (NB_MAX + 4);
+    }
+    ctx->unit_ticket = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + 4;
+    ctx->num_units = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + 5;
+    ctx->result = reinterpret_cast<unsigned long long*>(ctx->zero_block + o_res);
+    // unit list: probe side cut every >= 1024 tuples, plus one per partition
+    ctx->units_cap = mx / 1024 + FINE_MAX + 16;
+    CK(cudaMalloc(&ctx->units, ctx->units_cap * sizeof(uint4)));
+    CK(cudaMalloc(&ctx->d_dst_bases, NB_MAX * sizeof(tup_t*)));
+    CK(cudaHostAlloc(&ctx->h_result, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    return set_func_attrs(ctx);
+}
+
+extern "C" int gj_create(gj_ctx** out, int device, uint64_t max_R, uint64_t max_S) {
+    if (!out) return fail(GJ_ERR_ARG, "gj_create: out is NULL");
+    *out = nullptr;
+    gj_ctx* ctx = new (std::nothrow) gj_ctx();
+    if (!ctx) return fail(GJ_ERR_NOMEM, "host allocation failed");
+    const int rc = create_impl(ctx, device, max_R, max_S);
+    if (rc != GJ_OK) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        gj_destroy(ctx);
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    *out = ctx;
+    return GJ_OK;
+}
+
+extern "C" int gj_set_stream(gj_ctx* ctx, void* s) {
+    if (!ctx) return fail(GJ_ERR_ARG, "ctx is NULL");
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return GJ_OK;
+}
+
+static int64_t* option_slot(gj_ctx* ctx, const char* name) {
+    struct { const char* n; int64_t* p; } tab[] = {
+        {"radix_bits", &ctx->opt_radix_bits}, {"pass1_bits", &ctx->opt_pass1_bits},
+        {"scatter_cfg1", &ctx->opt_scatter_cfg1}, {"scatter_cfg2", &ctx->opt_scatter_cfg2},
+        {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
+        {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
+        {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
+    };
+    for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
+    return nullptr;
+}
+
+extern "C" int gj_set_option(gj_ctx* ctx, const char* name, int64_t v) {
+    if (!ctx || !name) return fail(GJ_ERR_ARG, "gj_set_option: NULL argument");
+    if (!strcmp(name, "scatter_cfg")) {
+        if (v < 0 || v >= kNumScatter) return fail(GJ_ERR_ARG, "scatter_cfg %lld out of range [0,%d)", (long long)v, kNumScatter);
+        ctx->opt_scatter_cfg1 = ctx->opt_scatter_cfg2 = v;
+        return GJ_OK;
+    }
+    int64_t* p = option_slot(ctx, name);
+    if (!p) return fail(GJ_ERR_ARG, "unknown option '%s'", name);
+    if (v < 0) return fail(GJ_ERR_ARG, "option '%s' must be >= 0", name);
+    if ((p == &ctx->opt_scatter_cfg1 || p == &ctx->opt_scatter_cfg2) && v >= kNumScatter)
+        return fail(GJ_ERR_ARG, "%s %lld out of range [0,%d)", name, (long long)v, kNumScatter);
+    if (p == &ctx->opt_join_cfg && v >= kNumJoin) return fail(GJ_ERR_ARG, "join_cfg out of range [0,%d)", kNumJoin);
+    if (p == &ctx->opt_radix_bits && v > MAX_RADIX_BITS) return fail(GJ_ERR_ARG, "radix_bits <= %d", MAX_RADIX_BITS);
+    if (p == &ctx->opt_pass1_bits && v > MAX_PASS_BITS) return fail(GJ_ERR_ARG, "pass1_bits <= %d", MAX_PASS_BITS);
+    if (p == &ctx->opt_unit && v && v < 1024) return fail(GJ_ERR_ARG, "unit_tuples >= 1024");
+    if (p == &ctx->opt_gpu_bits && v > 8) return fail(GJ_ERR_ARG, "gpu_bits <= 8");
+    if (p == &ctx->opt_part_target && v < 32) return fail(GJ_ERR_ARG, "part_target >= 32");
+    if (p == &ctx->opt_h2d_chunk && v < 4096) return fail(GJ_ERR_ARG, "h2d_chunk >= 4096");
+    *p = v;
+    return GJ_OK;
+}
+
+extern "C" int gj_get_option(gj_ctx* ctx, const char* name, int64_t* v) {
+    if (!ctx || !name || !v) return fail(GJ_ERR_ARG, "gj_get_option: NULL argument");
+    if (!strcmp(name, "scatter_cfg")) { *v = ctx->opt_scatter_cfg1; return GJ_OK; }
+    if (!strcmp(name, "num_scatter_cfgs")) { *v = kNumScatter; return GJ_OK; }
+    if (!strcmp(name, "num_join_cfgs")) { *v = kNumJoin; return GJ_OK; }
+    if (!strcmp(name, "sm_count")) { *v = ctx->sm_count; return GJ_OK; }
+    int64_t* p = option_slot(ctx, name);
+    if (!p) return fail(GJ_ERR_ARG, "unknown option '%s'", name);
+    *v = *p;
+    return GJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// planning: how many radix bits, how they split over passes
+// (the reference freezes log_parts1 = 8, log_parts2 = 5 at compile time, common.h:51-52)
+// ------------------------------------------------------------------------------------------
+struct Plan { uint32_t B, b1, b2; };
+
+static Plan choose_plan(const gj_ctx* ctx, uint64_t n_build, uint32_t forced_bits) {
+    Plan p;
+    uint32_t B = forced_bits ? forced_bits : (uint32_t)ctx->opt_radix_bits;
+    if (!B) {
+        const uint64_t target = (uint64_t)ctx->opt_part_target;
+        while (B < (uint32_t)MAX_RADIX_BITS && (n_build >> B) > target) ++B;
+    }
+    B = std::min<uint32_t>(B, MAX_RADIX_BITS);
+    if (B <= (uint32_t)MAX_PASS_BITS) { p.b1 = B; p.b2 = 0; }
+    else {
+        p.b1 = ctx->opt_pass1_bits ? (uint32_t)ctx->opt_pass1_bits : (B + 1) / 2;
+        p.b1 = std::min<uint32_t>(std::max<uint32_t>(p.b1, B - MAX_PASS_BITS), MAX_PASS_BITS);
+        p.b2 = B - p.b1;
+    }
+    p.B = B;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// enqueue helpers (no host synchronisation inside)
+// ------------------------------------------------------------------------------------------
+static int enqueue_hist(gj_ctx* ctx, cudaStream_t s, const void* in, bool packed, uint64_t n,
+                        uint32_t shift, uint32_t bits, uint32_t* ghist) {
+    if (!n) return GJ_OK;
+    const uint64_t per_cta = 1024ull * 16;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count, (n + per_cta - 1) / per_cta));
+    const size_t smem = (size_t)4 << bits;
+    if (packed) hist_kernel<true><<<grid, 1024, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+    else hist_kernel<false><<<grid, 1024, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+    LAUNCHED();
+    return GJ_OK;
+}
+
+static int enqueue_scan(gj_ctx* ctx, cudaStream_t s, uint32_t nrel, uint32_t nb) {
+    ScanArgs a;
+    for (uint32_t r = 0; r < 2; ++r) {
+        const RelMeta& m = ctx->meta[r < nrel ? r : 0];
+        a.rel[r].in = m.ghist; a.rel[r].out = m.off; a.rel[r].desc = m.desc; a.rel[r].ticket = m.ticket;
+    }
+    a.nb = nb;
+    dim3 grid((nb + SCAN_TILE - 1) / SCAN_TILE, nrel);
+    scan_lookback_kernel<<<grid, SCAN_THREADS, 0, s>>>(a);
+    LAUNCHED();
+    return GJ_OK;
+}
+
+static uint32_t unit_tuples(const gj_ctx* ctx) { return ctx->opt_unit ? (uint32_t)ctx->opt_unit : 16384u; }
+
+static int enqueue_plan(gj_ctx* ctx, cudaStream_t s, uint32_t nrel, const Plan& pl) {
+    PlanArgs a;
+    for (uint32_t r = 0; r < 2; ++r) {
+        const RelMeta& m = ctx->meta[r < nrel ? r : 0];
+        a.rel[r].off = m.off; a.rel[r].cur1 = m.cur1; a.rel[r].cur2 = m.cur2; a.rel[r].tile_prefix = m.tile_prefix;
+    }
+    a.nrel = nrel; a.b1 = pl.b1; a.b2 = pl.b2;
+    const ScatterCfg& c2 = kScatter[ctx->opt_scatter_cfg2];
+    a.tile = (uint32_t)(c2.threads * c2.ipt);
+    a.unit = unit_tuples(ctx);
+    a.units = ctx->units; a.num_units = ctx->num_units;
+    plan_kernel<<<1, PLAN_THREADS, 0, s>>>(a);
+    LAUNCHED();
+    return GJ_OK;
+}
+
+// all scatter passes of one relation; role indexes ctx->meta, dst is the final buffer
+static int enqueue_scatter(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role, const Plan& pl, tup_t* dst) {
+    if (!rel.n) return GJ_OK;
+    const RelMeta& m = ctx->meta[role];
+    const ScatterCfg& c1 = kScatter[ctx->opt_scatter_cfg1];
+    const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
+    ScatterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in_keys = rel.keys; a.in_pays = rel.pays; a.in_tup = rel.tup;
+    a.n = (uint32_t)rel.n;
+    a.out = pl.b2 ? ctx->scratch : dst;
+    a.shift = pl.b2; a.bits = pl.b1;
+    a.cursors = pl.b2 ? m.cur1 : m.cur2;
+    const uint32_t grid1 = (uint32_t)((rel.n + T1 - 1) / T1);
+    CK(cudaEventRecord(ctx->pev[role][0], s));
+    (rel.tup ? c1.packed : c1.col)<<<grid1, c1.threads, (size_t)T1 * sizeof(tup_t), s>>>(a);
+    LAUNCHED();
+    CK(cudaEventRecord(ctx->pev[role][1], s));
+    if (pl.b2) {
+        const ScatterCfg& c2 = kScatter[ctx->opt_scatter_cfg2];
+        const uint32_t T2 = (uint32_t)(c2.threads * c2.ipt);
+        ScatterArgs b;
+        memset(&b, 0, sizeof(b));
+        b.in_tup = ctx->scratch; b.out = dst; b.n = (uint32_t)rel.n;
+        b.shift = 0; b.bits = pl.b2;
+        b.cursors = m.cur2; b.tile_prefix = m.tile_prefix; b.parent_off = m.off; b.nparent_bits = pl.b1;
+        const uint32_t grid2 = (uint32_t)(rel.n / T2) + (1u << pl.b1);   // upper bound on tiles
+        c2.packed<<<grid2, c2.threads, (size_t)T2 * sizeof(tup_t), s>>>(b);
+        LAUNCHED();
+        CK(cudaEventRecord(ctx->pev[role][2], s));
+    }
+    return GJ_OK;
+}
+
+static int fill_pass_times(gj_ctx* ctx, gj_timings* t, const Plan& pl, int nroles, int first_role) {
+    if (!t) return GJ_OK;
+    for (int k = 0; k < nroles; ++k) {
+        const int role = first_role + k;
+        CK(cudaEventElapsedTime(&t->pass_ms[2 * k], ctx->pev[role][0], ctx->pev[role][1]));
+        if (pl.b2) CK(cudaEventElapsedTime(&t->pass_ms[2 * k + 1], ctx->pev[role][1], ctx->pev[role][2]));
+    }
+    return GJ_OK;
+}
+
+static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup_t* prb, const Plan& pl,
+                        uint64_t n_prb, bool mat, int32_t* out_b, int32_t* out_p, uint64_t cap) {
+    const JoinCfg& jc = kJoin[ctx->opt_join_cfg];
+    JoinArgs a;
+    a.bld = bld; a.off_bld = ctx->meta[0].off; a.prb = prb; a.off_prb = ctx->meta[1].off;
+    a.units = ctx->units; a.num_units = ctx->num_units; a.ticket = ctx->unit_ticket;
+    a.hash_shift = pl.B + (uint32_t)ctx->opt_gpu_bits;
+    a.result = ctx->result;
+    a.out_bld_pay = out_b; a.out_prb_pay = out_p; a.cap = cap;
+    const size_t smem = join_smem(jc, mat);
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mat ? jc.mat : jc.agg, jc.threads, smem));
+    occ = std::max(occ, 1);
+    uint64_t grid = (uint64_t)ctx->sm_count * occ;
+    if (ctx->opt_join_grid) grid = (uint64_t)ctx->opt_join_grid;
+    const uint64_t max_units = n_prb / unit_tuples(ctx) + (1ull << pl.B);
+    grid = std::max<uint64_t>(1, std::min(grid, max_units));
+    (mat ? jc.mat : jc.agg)<<<(uint32_t)grid, jc.threads, smem, s>>>(a);
+    LAUNCHED();
+    return GJ_OK;
+}
+
+static void fill_plan(gj_timings* t, const Plan& pl) {
+    if (!t) return;
+    t->radix_bits = pl.B; t->pass1_bits = pl.b1; t->pass2_bits = pl.b2;
+}
+
+// ------------------------------------------------------------------------------------------
+// the join pipeline
+// ------------------------------------------------------------------------------------------
+static int check_caps(gj_ctx* ctx, uint64_t nR, uint64_t nS) {
+    if (!ctx) return fail(GJ_ERR_ARG, "ctx is NULL");
+    if (nR > ctx->maxR || nS > ctx->maxS)
+        return fail(GJ_ERR_ARG, "relation sizes (%llu, %llu) exceed the context capacity (%llu, %llu)",
+                    (unsigned long long)nR, (unsigned long long)nS, (unsigned long long)ctx->maxR, (unsigned long long)ctx->maxS);
+    return GJ_OK;
+}
+
+static int run_join(gj_ctx* ctx, Rel R, Rel S, bool mat, int32_t* out_Rp, int32_t* out_Sp, uint64_t cap,
+                    uint64_t* matches, uint64_t* checksum, uint64_t* n_pairs, gj_timings* t) {
+    const auto w0 = std::chrono::steady_clock::now();
+    if (t) memset(t, 0, sizeof(*t));
+    if (matches) *matches = 0;
+    if (checksum) *checksum = 0;
+    if (n_pairs) *n_pairs = 0;
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    if (R.n == 0 || S.n == 0) return GJ_OK;
+    cudaStream_t s = ctx->stream;
+    const bool swap = R.n > S.n;   // build on the smaller relation
+    const Rel& bld = swap ? S : R;
+    const Rel& prb = swap ? R : S;
+    const Plan pl = choose_plan(ctx, bld.n, 0);
+    fill_plan(t, pl);
+
+    CK(cudaMemsetAsync(ctx->zero_block, 0, ctx->zero_bytes, s));
+    CK(cudaEventRecord(ctx->ev[0], s));
+    int rc;
+    if ((rc = enqueue_hist(ctx, s, bld.tup ? (const void*)bld.tup : (const void*)bld.keys, bld.tup != nullptr, bld.n, 0, pl.B, ctx->meta[0].ghist))) return rc;
+    if ((rc = enqueue_hist(ctx, s, prb.tup ? (const void*)prb.tup : (const void*)prb.keys, prb.tup != nullptr, prb.n, 0, pl.B, ctx->meta[1].ghist))) return rc;
+    if ((rc = enqueue_scan(ctx, s, 2, 1u << pl.B))) return rc;
+    if ((rc = enqueue_plan(ctx, s, 2, pl))) return rc;
+    CK(cudaEventRecord(ctx->ev[1], s));
+    if ((rc = enqueue_scatter(ctx, s, bld, 0, pl, ctx->out[bld.slot]))) return rc;
+    if ((rc = enqueue_scatter(ctx, s, prb, 1, pl, ctx->out[prb.slot]))) return rc;
+    CK(cudaEventRecord(ctx->ev[2], s));
+    if ((rc = enqueue_join(ctx, s, ctx->out[bld.slot], ctx->out[prb.slot], pl, prb.n, mat,
+                           swap ? out_Sp : out_Rp, swap ? out_Rp : out_Sp, cap))) return rc;
+    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (matches) *matches = ctx->h_result[0];
+    if (checksum) *checksum = ctx->h_result[1];
+    if (n_pairs) *n_pairs = ctx->h_result[2];
+    if (t) {
+        CK(cudaEventElapsedTime(&t->hist_ms, ctx->ev[0], ctx->ev[1]));
+        CK(cudaEventElapsedTime(&t->part_ms, ctx->ev[1], ctx->ev[2]));
+        CK(cudaEventElapsedTime(&t->join_ms, ctx->ev[2], ctx->ev[3]));
+        CK(cudaEventElapsedTime(&t->total_ms, ctx->ev[0], ctx->ev[3]));
+        if ((rc = fill_pass_times(ctx, t, pl, 2, 0))) return rc;
+        t->kernel_launches = ctx->launches;
+        t->wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    }
+    return GJ_OK;
+}
+
+extern "C" int gj_join_aggregate(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
+                                 const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS,
+                                 uint64_t* matches, uint64_t* checksum, gj_timings* t) {
+    int rc = check_caps(ctx, nR, nS);
+    if (rc) return rc;
+    if ((nR && (!d_Rk || !d_Rp)) || (nS && (!d_Sk || !d_Sp))) return fail(GJ_ERR_ARG, "NULL input column");
+    Rel R, S;
+    R.keys = d_Rk; R.pays = d_Rp; R.n = nR; R.slot = 0;
+    S.keys = d_Sk; S.pays = d_Sp; S.n = nS; S.slot = 1;
+    return run_join(ctx, R, S, false, nullptr, nullptr, 0, matches, checksum, nullptr, t);
+}
+
+extern "C" int gj_join_aggregate_tuples(gj_ctx* ctx, const void* d_Rtup, uint64_t nR, const void* d_Stup,
+                                        uint64_t nS, uint64_t* matches, uint64_t* checksum, gj_timings* t) {
+    int rc = check_caps(ctx, nR, nS);
+    if (rc) return rc;
+    if ((nR && !d_Rtup) || (nS && !d_Stup)) return fail(GJ_ERR_ARG, "NULL input");
+    if (((size_t)d_Rtup | (size_t)d_Stup) & 7u) return fail(GJ_ERR_ARG, "packed tuples must be 8-byte aligned");
+    Rel R, S;
+    R.tup = (const tup_t*)d_Rtup; R.n = nR; R.slot = 0;
+    S.tup = (const tup_t*)d_Stup; S.n = nS; S.slot = 1;
+    return run_join(ctx, R, S, false, nullptr, nullptr, 0, matches, checksum, nullptr, t);
+}
+
+extern "C" int gj_join_materialize(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
+                                   const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS, int32_t* d_out_Rp,
+                                   int32_t* d_out_Sp, uint64_t cap, uint64_t* n_pairs, uint64_t* checksum,
+                                   gj_timings* t) {
+    int rc = check_caps(ctx, nR, nS);
+    if (rc) return rc;
+    if ((nR && (!d_Rk || !d_Rp)) || (nS && (!d_Sk || !d_Sp))) return fail(GJ_ERR_ARG, "NULL input column");
+    if (cap && (!d_out_Rp || !d_out_Sp)) return fail(GJ_ERR_ARG, "NULL output column with cap > 0");
+    Rel R, S;
+    R.keys = d_Rk; R.pays = d_Rp; R.n = nR; R.slot = 0;
+    S.keys = d_Sk; S.pays = d_Sp; S.n = nS; S.slot = 1;
+    uint64_t m = 0;
+    rc = run_join(ctx, R, S, true, d_out_Rp, d_out_Sp, cap, &m, checksum, n_pairs, t);
+    if (rc == GJ_OK && n_pairs && *n_pairs != m)
+        return fail(GJ_ERR_STATE, "internal: pairs reserved (%llu) != matches (%llu)", (unsigned long long)*n_pairs, (unsigned long long)m);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// end-to-end host entry: H2D copies chunked on a copy stream, histograms chase the key chunks
+// ------------------------------------------------------------------------------------------
+static int ensure_host_staging(gj_ctx* ctx) {
+    if (ctx->d_in[0]) return GJ_OK;
+    const uint64_t caps[4] = {ctx->maxR, ctx->maxR, ctx->maxS, ctx->maxS};
+    for (int i = 0; i < 4; ++i)
+        if (cudaMalloc(&ctx->d_in[i], caps[i] * sizeof(int32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(GJ_ERR_NOMEM, "cudaMalloc of the host-entry staging columns failed");
+        }
+    return GJ_OK;
+}
+
+extern "C" int gj_join_aggregate_host(gj_ctx* ctx, const int32_t* h_Rk, const int32_t* h_Rp, uint64_t nR,
+                                      const int32_t* h_Sk, const int32_t* h_Sp, uint64_t nS,
+                                      uint64_t* matches, uint64_t* checksum, gj_timings* t) {
+    const auto w0 = std::chrono::steady_clock::now();
+    int rc = check_caps(ctx, nR, nS);
+    if (rc) return rc;
+    if ((nR && (!h_Rk || !h_Rp)) || (nS && (!h_Sk || !h_Sp))) return fail(GJ_ERR_ARG, "NULL input column");
+    if (t) memset(t, 0, sizeof(*t));
+    if (matches) *matches = 0;
+    if (checksum) *checksum = 0;
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    if (!nR || !nS) return GJ_OK;
+    if ((rc = ensure_host_staging(ctx))) return rc;
+    cudaStream_t s = ctx->stream, c = ctx->copy_stream;
+    const bool swap = nR > nS;
+    // role 0 = build, role 1 = probe
+    const int32_t* hk[2] = {swap ? h_Sk : h_Rk, swap ? h_Rk : h_Sk};
+    const int32_t* hp[2] = {swap ? h_Sp : h_Rp, swap ? h_Rp : h_Sp};
+    int32_t* dk[2] = {ctx->d_in[swap ? 2 : 0], ctx->d_in[swap ? 0 : 2]};
+    int32_t* dp[2] = {ctx->d_in[swap ? 3 : 1], ctx->d_in[swap ? 1 : 3]};
+    const uint64_t nn[2] = {swap ? nS : nR, swap ? nR : nS};
+    const int slot[2] = {swap ? 1 : 0, swap ? 0 : 1};
+    const Plan pl = choose_plan(ctx, nn[0], 0);
+    fill_plan(t, pl);
+
+    CK(cudaMemsetAsync(ctx->zero_block, 0, ctx->zero_bytes, s));
+    CK(cudaEventRecord(ctx->ev[0], s));
+    CK(cudaStreamWaitEvent(c, ctx->ev[0], 0));   // copies start with the timed window
+    int evi = 0;
+    const uint64_t chunk = (uint64_t)ctx->opt_h2d_chunk;
+    for (int r = 0; r < 2; ++r) {
+        for (uint64_t o = 0; o < nn[r]; o += chunk) {
+            const uint64_t m = std::min(chunk, nn[r] - o);
+            CK(cudaMemcpyAsync(dk[r] + o, hk[r] + o, m * sizeof(int32_t), cudaMemcpyHostToDevice, c));
+            cudaEvent_t e = ctx->cev[evi++ % N_EVENTS];
+            CK(cudaEventRecord(e, c));
+            CK(cudaStreamWaitEvent(s, e, 0));
+            if ((rc = enqueue_hist(ctx, s, dk[r] + o, false, m, 0, pl.B, ctx->meta[r].ghist))) return rc;
+        }
+    }
+    cudaEvent_t pay_ev[2];
+    for (int r = 0; r < 2; ++r) {
+        CK(cudaMemcpyAsync(dp[r], hp[r], nn[r] * sizeof(int32_t), cudaMemcpyHostToDevice, c));
+        pay_ev[r] = ctx->cev[evi++ % N_EVENTS];
+        CK(cudaEventRecord(pay_ev[r], c));
+    }
+    CK(cudaEventRecord(ctx->ev[4], c));   // end of all H2D traffic
+    if ((rc = enqueue_scan(ctx, s, 2, 1u << pl.B))) return rc;
+    if ((rc = enqueue_plan(ctx, s, 2, pl))) return rc;
+    CK(cudaEventRecord(ctx->ev[1], s));
+    for (int r = 0; r < 2; ++r) {
+        Rel rel;
+        rel.keys = dk[r]; rel.pays = dp[r]; rel.n = nn[r]; rel.slot = slot[r];
+        CK(cudaStreamWaitEvent(s, pay_ev[r], 0));
+        if ((rc = enqueue_scatter(ctx, s, rel, r, pl, ctx->out[slot[r]]))) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev[2], s));
+    if ((rc = enqueue_join(ctx, s, ctx->out[slot[0]], ctx->out[slot[1]], pl, nn[1], false, nullptr, nullptr, 0))) return rc;
+    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(c));
+    if (matches) *matches = ctx->h_result[0];
+    if (checksum) *checksum = ctx->h_result[1];
+    if (t) {
+        CK(cudaEventElapsedTime(&t->hist_ms, ctx->ev[0], ctx->ev[1]));
+        CK(cudaEventElapsedTime(&t->part_ms, ctx->ev[1], ctx->ev[2]));
+        CK(cudaEventElapsedTime(&t->join_ms, ctx->ev[2], ctx->ev[3]));
+        CK(cudaEventElapsedTime(&t->total_ms, ctx->ev[0], ctx->ev[3]));
+        CK(cudaEventElapsedTime(&t->h2d_ms, ctx->ev[0], ctx->ev[4]));
+        if ((rc = fill_pass_times(ctx, t, pl, 2, 0))) return rc;
+        t->kernel_launches = ctx->launches;
+        t->wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    }
+    return GJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the partitioner on its own
+// ------------------------------------------------------------------------------------------
+extern "C" int gj_partition(gj_ctx* ctx, int slot, const int32_t* d_keys, const int32_t* d_pays, uint64_t n,
+                            uint32_t radix_bits, const void** d_tuples, const uint32_t** d_offsets,
+                            uint32_t* radix_bits_used, gj_timings* t) {
+    const auto w0 = std::chrono::steady_clock::now();
+    if (!ctx) return fail(GJ_ERR_ARG, "ctx is NULL");
+    if (slot != 0 && slot != 1) return fail(GJ_ERR_ARG, "slot must be 0 or 1");
+    if (n > (slot ? ctx->maxS : ctx->maxR)) return fail(GJ_ERR_ARG, "n exceeds the capacity of slot %d", slot);
+    if (n && (!d_keys || !d_pays)) return fail(GJ_ERR_ARG, "NULL input column");
+    if (radix_bits > (uint32_t)MAX_RADIX_BITS) return fail(GJ_ERR_ARG, "radix_bits <= %d", MAX_RADIX_BITS);
+    if (t) memset(t, 0, sizeof(*t));
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    cudaStream_t s = ctx->stream;
+    const Plan pl = choose_plan(ctx, n, radix_bits);
+    fill_plan(t, pl);
+    Rel rel;
+    rel.keys = d_keys; rel.pays = d_pays; rel.n = n; rel.slot = slot;
+    // the standalone partitioner uses role `slot` of the metadata so two calls (R then S) coexist
+    CK(cudaMemsetAsync(ctx->zero_block, 0, ctx->zero_bytes, s));
+    CK(cudaEventRecord(ctx->ev[0], s));
+    int rc;
+    if ((rc = enqueue_hist(ctx, s, d_keys, false, n, 0, pl.B, ctx->meta[slot].ghist))) return rc;
+    {   // scan + plan of this one relation only (role = slot)
+        ScanArgs a;
+        const RelMeta& m = ctx->meta[slot];
+        for (int r = 0; r < 2; ++r) { a.rel[r].in = m.ghist; a.rel[r].out = m.off; a.rel[r].desc = m.desc; a.rel[r].ticket = m.ticket; }
+        a.nb = 1u << pl.B;
+        dim3 grid((a.nb + SCAN_TILE - 1) / SCAN_TILE, 1);
+        scan_lookback_kernel<<<grid, SCAN_THREADS, 0, s>>>(a);
+        LAUNCHED();
+        PlanArgs p;
+        for (int r = 0; r < 2; ++r) { p.rel[r].off = m.off; p.rel[r].cur1 = m.cur1; p.rel[r].cur2 = m.cur2; p.rel[r].tile_prefix = m.tile_prefix; }
+        p.nrel = 1; p.b1 = pl.b1; p.b2 = pl.b2;
+        const ScatterCfg& c2 = kScatter[ctx->opt_scatter_cfg2];
+        p.tile = (uint32_t)(c2.threads * c2.ipt);
+        p.unit = unit_tuples(ctx); p.units = ctx->units; p.num_units = ctx->num_units;
+        plan_kernel<<<1, PLAN_THREADS, 0, s>>>(p);
+        LAUNCHED();
+    }
+    CK(cudaEventRecord(ctx->ev[1], s));
+    if ((rc = enqueue_scatter(ctx, s, rel, slot, pl, ctx->out[slot]))) return rc;
+    CK(cudaEventRecord(ctx->ev[2], s));
+    CK(cudaStreamSynchronize(s));
+    if (d_tuples) *d_tuples = ctx->out[slot];
+    if (d_offsets) *d_offsets = ctx->meta[slot].off;
+    if (radix_bits_used) *radix_bits_used = pl.B;
+    if (t) {
+        CK(cudaEventElapsedTime(&t->hist_ms, ctx->ev[0], ctx->ev[1]));
+        CK(cudaEventElapsedTime(&t->part_ms, ctx->ev[1], ctx->ev[2]));
+        CK(cudaEventElapsedTime(&t->total_ms, ctx->ev[0], ctx->ev[2]));
+        if (n && (rc = fill_pass_times(ctx, t, pl, 1, slot))) return rc;
+        t->kernel_launches = ctx->launches;
+        t->wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    }
+    return GJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU shuffle step
+// ------------------------------------------------------------------------------------------
+static int shuffle_args_ok(gj_ctx* ctx, uint64_t n, uint32_t n_gpus, uint32_t gpu_shift, uint32_t* bits) {
+    if (!ctx) return fail(GJ_ERR_ARG, "ctx is NULL");
+    if (n_gpus == 0 || n_gpus > (uint32_t)NB_MAX || (n_gpus & (n_gpus - 1))) return fail(GJ_ERR_ARG, "n_gpus must be a power of two <= %d", NB_MAX);
+    if (gpu_shift > 31) return fail(GJ_ERR_ARG, "gpu_shift <= 31");
+    if (n > std::max(ctx->maxR, ctx->maxS)) return fail(GJ_ERR_ARG, "n exceeds the context capacity");
+    uint32_t b = 0;
+    while ((1u << b) < n_gpus) ++b;
+    *bits = b;
+    return GJ_OK;
+}
+
+extern "C" int gj_shuffle_count(gj_ctx* ctx, const int32_t* d_keys, uint64_t n, uint32_t n_gpus,
+                                uint32_t gpu_shift, uint64_t* h_counts) {
+    uint32_t bits = 0;
+    int rc = shuffle_args_ok(ctx, n, n_gpus, gpu_shift, &bits);
+    if (rc) return rc;
+    if (!h_counts || (n && !d_keys)) return fail(GJ_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->zero_block, 0, ctx->zero_bytes, s));
+    if ((rc = enqueue_hist(ctx, s, d_keys, false, n, gpu_shift, bits, ctx->meta[0].ghist))) return rc;
+    uint32_t tmp[NB_MAX];
+    CK(cudaMemcpyAsync(tmp, ctx->meta[0].ghist, n_gpus * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint32_t g = 0; g < n_gpus; ++g) h_counts[g] = tmp[g];
+    return GJ_OK;
+}
+
+extern "C" int gj_shuffle_split(gj_ctx* ctx, const int32_t* d_keys, const int32_t* d_pays, uint64_t n,
+                                uint32_t n_gpus, uint32_t gpu_shift, void* d_out_tuples, uint64_t* h_counts) {
+    uint32_t bits = 0;
+    int rc = shuffle_args_ok(ctx, n, n_gpus, gpu_shift, &bits);
+    if (rc) return rc;
+    if (!h_counts || (n && (!d_keys || !d_pays || !d_out_tuples))) return fail(GJ_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->zero_block, 0, ctx->zero_bytes, s));
+    if ((rc = enqueue_hist(ctx, s, d_keys, false, n, gpu_shift, bits, ctx->meta[0].ghist))) return rc;
+    Plan pl; pl.B = bits; pl.b1 = bits; pl.b2 = 0;
+    if ((rc = enqueue_scan(ctx, s, 1, n_gpus))) return rc;
+    if ((rc = enqueue_plan(ctx, s, 1, pl))) return rc;
+    if (n) {
+        const ScatterCfg& c1 = kScatter[ctx->opt_scatter_cfg1];
+        const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
+        ScatterArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = (tup_t*)d_out_tuples;
+        a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2;
+        c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, (size_t)T1 * sizeof(tup_t), s>>>(a);
+        LAUNCHED();
+    }
+    uint32_t tmp[NB_MAX];
+    CK(cudaMemcpyAsync(tmp, ctx->meta[0].ghist, n_gpus * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint32_t g = 0; g < n_gpus; ++g) h_counts[g] = tmp[g];
+    return GJ_OK;
+}
+
+extern "C" int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, const int32_t* d_pays, uint64_t n,
+                                        uint32_t n_gpus, uint32_t gpu_shift, void* const* d_peer_bases,
+                                        const uint64_t* h_peer_offsets) {
+    uint32_t bits = 0;
+    int rc = shuffle_args_ok(ctx, n, n_gpus, gpu_shift, &bits);
+    if (rc) return rc;
+    if (!d_peer_bases || !h_peer_offsets || (n && (!d_keys || !d_pays))) return fail(GJ_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    cudaStream_t s = ctx->stream;
+    uint32_t cur[NB_MAX];
+    for (uint32_t g = 0; g < n_gpus; ++g) {
+        if (h_peer_offsets[g] > 0xFFFFFFFFull) return fail(GJ_ERR_ARG, "peer offset exceeds 2^32 tuples");
+        cur[g] = (uint32_t)h_peer_offsets[g];
+    }
+    CK(cudaMemcpyAsync(ctx->meta[0].cur2, cur, n_gpus * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_dst_bases, d_peer_bases, n_gpus * sizeof(void*), cudaMemcpyHostToDevice, s));
+    if (n) {
+        const ScatterCfg& c1 = kScatter[ctx->opt_scatter_cfg1];
+        const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
+        ScatterArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = nullptr;
+        a.dst_bases = ctx->d_dst_bases;
+        a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2;
+        c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, (size_t)T1 * sizeof(tup_t), s>>>(a);
+        LAUNCHED();
+    }
+    CK(cudaStreamSynchronize(s));
+    return GJ_OK;
+}
+
+extern "C" int gj_ipc_export(void* d_ptr, char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!d_ptr || !handle) return fail(GJ_ERR_ARG, "NULL argument");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return GJ_OK;
+}
+extern "C" int gj_ipc_open(const char handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return fail(GJ_ERR_ARG, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GJ_OK;
+}
+extern "C" int gj_ipc_close(void* d_ptr) { CK(cudaIpcCloseMemHandle(d_ptr)); return GJ_OK; }
+
+// ------------------------------------------------------------------------------------------
+// synthetic data, memory helpers
+// ------------------------------------------------------------------------------------------
+extern "C" int gj_generate_unique(gj_ctx* ctx, int32_t* d_keys, int32_t* d_pays, uint64_t row_begin,
+                                  uint64_t n_rows, uint64_t n_total, uint32_t seed, uint32_t pay_seed) {
+    if (!ctx) return fail(GJ_ERR_ARG, "ctx is NULL");
+    if (n_total == 0 || n_total > (1ull << 32) || row_begin + n_rows > n_total) return fail(GJ_ERR_ARG, "rows out of range");
+    if (n_rows && (!d_keys || !d_pays)) return fail(GJ_ERR_ARG, "NULL output column");
+    if (!n_rows) return GJ_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int grid = (int)std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    generate_unique_kernel<<<grid, 256, 0, ctx->stream>>>(d_keys, d_pays, row_begin, n_rows, n_total, seed, pay_seed);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GJ_OK;
+}
+
+extern "C" uint32_t gj_bijection(uint64_t row, uint64_t n_total, uint32_t seed) { return bijection(row, n_total, seed); }
+extern "C" int32_t gj_payload_of_key(uint32_t key, uint32_t pay_seed) { return payload_of_key(key, pay_seed); }
+
+extern "C" int gj_device_count(int* n) {
+    if (!n) return fail(GJ_ERR_ARG, "NULL argument");
+    CK(cudaGetDeviceCount(n));
+    return GJ_OK;
+}
+extern "C" int gj_malloc_device(void** p, uint64_t bytes) {
+    if (!p) return fail(GJ_ERR_ARG, "NULL argument");
+    if (cudaMalloc(p, std::max<uint64_t>(bytes, 1)) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "cudaMalloc(%llu) failed", (unsigned long long)bytes); }
+    return GJ_OK;
+}
+extern "C" int gj_free_device(void* p) { CK(cudaFree(p)); return GJ_OK; }
+extern "C" int gj_malloc_pinned(void** p, uint64_t bytes) {
+    if (!p) return fail(GJ_ERR_ARG, "NULL argument");
+    if (cudaHostAlloc(p, std::max<uint64_t>(bytes, 1), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "cudaHostAlloc(%llu) failed", (unsigned long long)bytes); }
+    return GJ_OK;
+}
+extern "C" int gj_free_pinned(void* p) { CK(cudaFreeHost(p)); return GJ_OK; }
+extern "C" int gj_memcpy_h2d(void* d, const void* h, uint64_t bytes) { CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); return GJ_OK; }
+extern "C" int gj_memcpy_d2h(void* h, const void* d, uint64_t bytes) { CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); return GJ_OK; }
+extern "C" int gj_device_synchronize(void) { CK(cudaDeviceSynchronize()); return GJ_OK; }
+
+extern "C" int gj_flush_l2(gj_ctx* ctx) {
+    if (!ctx) return fail(GJ_ERR_ARG, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = 256ull << 20;   // 2x the 126 MB L2
+        if (cudaMalloc(&ctx->flush_buf, ctx->flush_bytes) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "flush buffer"); }
+    }
+    static uint32_t v = 0;
+    flush_kernel<<<ctx->sm_count * 4, 512, 0, ctx->stream>>>((uint4*)ctx->flush_buf, ctx->flush_bytes / 16, ++v);
+    CK(cudaGetLastError());
+    return GJ_OK;
+}

@@ -1,0 +1,233 @@
+"""Multi-GPU radix join: one process per GPU, torch.distributed for the plumbing.
+
+No reference counterpart exists (the reference only ever calls
+cudaSetDevice(1), hash_join_clustered_probe.cu:1001,1685).  Design:
+
+  radix field = [ gpu bits | local bits ]:  destination GPU d = (key >> B) & (G-1) where B is
+  the number of radix bits of the LOCAL partitioner, i.e. the top bits of the field pick the
+  GPU and co-partitions of R and S meet on one GPU.  Steps per join:
+    1. count      per-destination histogram of R and S           (gj_shuffle_count / _split)
+    2. exchange   G x G count matrix                              (all_gather, tiny)
+    3. shuffle    mode "nccl": split into destination groups, then all_to_all_single
+                  mode "p2p" : ONE kernel partitions and stores each tuple run straight into
+                               the destination GPU's receive buffer over NVLink (peer memory
+                               mapped with CUDA IPC) -- no send buffer, no separate collective
+    4. local      partition + build + probe on the received tuples (gj_join_aggregate_tuples)
+    5. reduce     all_reduce(SUM) of {matches, checksum} (int64 wrap-around == mod 2^64)
+
+`ops` abstracts the three device steps so the host logic (counts, offsets, split sizes,
+collectives, reduction) is testable on CPU with the gloo backend and a stand-in `ops`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+def choose_radix_bits(n_build_local: int, part_target: int = 4096, max_bits: int = 15) -> int:
+    """Mirror of choose_plan() in csrc/api.cu: smallest B with n >> B <= part_target."""
+    b = 0
+    while b < max_bits and (n_build_local >> b) > part_target:
+        b += 1
+    return max(b, 1)
+
+
+def receive_layout(counts: np.ndarray, rank: int):
+    """counts[s][d] = tuples rank s sends to rank d.  Returns (recv_counts[s], recv_offsets[s],
+    my_write_offset_at[d]) -- source s writes its tuples for d at sum_{s' < s} counts[s'][d]."""
+    counts = np.asarray(counts, dtype=np.int64)
+    recv_counts = counts[:, rank].copy()
+    recv_offsets = np.concatenate(([0], np.cumsum(recv_counts)[:-1]))
+    write_at = np.array([counts[:rank, d].sum() for d in range(counts.shape[1])], dtype=np.int64)
+    return recv_counts, recv_offsets, write_at
+
+
+@dataclass
+class ShardedResult:
+    matches: int
+    checksum: int
+    local_R: int
+    local_S: int
+    phases_ms: dict = field(default_factory=dict)
+
+
+class GpuOps:
+    """Device steps backed by libgpujoin.so (the product path)."""
+
+    def __init__(self, max_R: int, max_S: int, device: int, slack: float = 1.3):
+        import torch
+        from .engine import JoinEngine
+        self.torch = torch
+        self.device = device
+        self.cap_R = int(max_R * slack) + 4096
+        self.cap_S = int(max_S * slack) + 4096
+        self.engine = JoinEngine(self.cap_R, self.cap_S, device)
+        self.stream = torch.cuda.Stream(device)
+        self.engine.use_torch_stream(self.stream)
+        dev = torch.device("cuda", device)
+        self.send = [torch.empty(self.cap_R, dtype=torch.int64, device=dev),
+                     torch.empty(self.cap_S, dtype=torch.int64, device=dev)]
+        self.recv = [torch.empty(self.cap_R, dtype=torch.int64, device=dev),
+                     torch.empty(self.cap_S, dtype=torch.int64, device=dev)]
+
+    def configure(self, radix_bits: int, gpu_bits: int):
+        self.engine.set_option("radix_bits", radix_bits)
+        self.engine.set_option("gpu_bits", gpu_bits)
+
+    def count(self, keys, G, shift):
+        return self.engine.shuffle_count(keys, G, shift)
+
+    def split(self, which, keys, pays, G, shift):
+        return self.engine.shuffle_split(keys, pays, G, shift, self.send[which])
+
+    def scatter_peers(self, keys, pays, G, shift, peer_ptrs, offsets):
+        self.engine.shuffle_scatter_peers(keys, pays, G, shift, peer_ptrs, offsets)
+
+    def local_join(self, nR, nS):
+        res = self.engine.join_aggregate_tuples(self.recv[0], nR, self.recv[1], nS)
+        return res.matches, res.checksum, res.timings.as_dict()
+
+    def local_join_ptrs(self, ptr_R, nR, ptr_S, nS):
+        res = self.engine.join_aggregate_ptrs(ptr_R, nR, ptr_S, nS)
+        return res.matches, res.checksum, res.timings.as_dict()
+
+    def result_tensor(self, matches, checksum):
+        # int64 two's complement add == addition mod 2^64
+        to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v  # noqa: E731
+        return self.torch.tensor([to_i64(matches), to_i64(checksum)], dtype=self.torch.int64,
+                                 device=self.torch.device("cuda", self.device))
+
+
+class ShardedJoin:
+    """R and S are sharded row-wise over the ranks of `group`; every rank calls join_aggregate
+    with its local shard (device int32 columns) and all ranks get the global result."""
+
+    def __init__(self, max_local_R: int, max_local_S: int, device: int | None = None, group=None,
+                 mode: str = "nccl", ops=None, part_target: int = 4096):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world & (self.world - 1):
+            raise ValueError("world size must be a power of two (GPU id = radix bits)")
+        self.gpu_bits = int(math.log2(self.world))
+        self.mode = mode
+        self.part_target = part_target
+        self.ops = ops if ops is not None else GpuOps(max_local_R, max_local_S, device)
+        self.max_local = (max_local_R, max_local_S)
+        self._peers = None
+        if mode == "p2p":
+            self._setup_peers()
+        elif mode != "nccl":
+            raise ValueError("mode must be 'nccl' or 'p2p'")
+
+    # -- CUDA IPC mapping of every rank's receive buffers (p2p mode) -------------------------
+    def _setup_peers(self):
+        from .engine import lib, _check
+        L = lib()
+        L.gj_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+        L.gj_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.gj_ipc_close.argtypes = [C.c_void_p]
+        ops = self.ops
+        # receive buffers must be plain cudaMalloc allocations to be exportable
+        self._own = []
+        handles = []
+        for which, cap in enumerate((ops.cap_R, ops.cap_S)):
+            p = C.c_void_p()
+            _check(L.gj_malloc_device(C.byref(p), cap * 8))
+            h = C.create_string_buffer(64)
+            _check(L.gj_ipc_export(p, h))
+            self._own.append(p.value)
+            handles.append(h.raw)
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, handles, group=self.group)
+        self._peers = [[0] * self.world, [0] * self.world]
+        self._opened = []
+        for r in range(self.world):
+            for which in range(2):
+                if r == self.rank:
+                    self._peers[which][r] = self._own[which]
+                else:
+                    q = C.c_void_p()
+                    _check(L.gj_ipc_open(gathered[r][which], C.byref(q)))
+                    self._peers[which][r] = q.value
+                    self._opened.append(q.value)
+        self._L = L
+
+    def close(self):
+        if self._peers is not None:
+            for q in self._opened:
+                self._L.gj_ipc_close(C.c_void_p(q))
+            self.dist.barrier(group=self.group)
+            for p in self._own:
+                self._L.gj_free_device(C.c_void_p(p))
+            self._peers = None
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _all_gather_counts(self, mine: np.ndarray) -> np.ndarray:
+        out = [None] * self.world
+        self.dist.all_gather_object(out, [int(x) for x in mine], group=self.group)
+        return np.array(out, dtype=np.int64)
+
+    def plan_bits(self, n_build_global: int) -> int:
+        return choose_radix_bits(max(1, n_build_global // self.world), self.part_target)
+
+    # -- the join ------------------------------------------------------------------------------
+    def join_aggregate(self, Rk, Rp, Sk, Sp, n_R_global: int, n_S_global: int) -> ShardedResult:
+        G, rank, ops, dist = self.world, self.rank, self.ops, self.dist
+        B = self.plan_bits(min(n_R_global, n_S_global))
+        ops.configure(B, self.gpu_bits)
+        shift = B
+        rels = ((Rk, Rp), (Sk, Sp))
+        local_n = [0, 0]
+        if self.mode == "nccl":
+            import torch
+            for which, (k, p) in enumerate(rels):
+                cnt = ops.split(which, k, p, G, shift)
+                counts = self._all_gather_counts(cnt)
+                recv_counts, _, _ = receive_layout(counts, rank)
+                n_in = int(recv_counts.sum())
+                if n_in > ops.recv[which].numel():
+                    raise RuntimeError(f"rank {rank}: receives {n_in} tuples, capacity {ops.recv[which].numel()}")
+                n_out = int(cnt.sum())
+                with torch.cuda.stream(ops.stream) if hasattr(ops, "stream") else _null():
+                    dist.all_to_all_single(ops.recv[which][:n_in], ops.send[which][:n_out],
+                                           output_split_sizes=[int(x) for x in recv_counts],
+                                           input_split_sizes=[int(x) for x in cnt], group=self.group)
+                local_n[which] = n_in
+            if hasattr(ops, "stream"):
+                ops.stream.synchronize()
+        else:
+            all_counts = []
+            for which, (k, p) in enumerate(rels):
+                all_counts.append(self._all_gather_counts(ops.count(k, G, shift)))
+            dist.barrier(group=self.group)   # peers are done reading their receive buffers
+            for which, (k, p) in enumerate(rels):
+                recv_counts, _, write_at = receive_layout(all_counts[which], rank)
+                n_in = int(recv_counts.sum())
+                cap = ops.cap_R if which == 0 else ops.cap_S
+                if n_in > cap:
+                    raise RuntimeError(f"rank {rank}: receives {n_in} tuples, capacity {cap}")
+                ops.scatter_peers(k, p, G, shift, self._peers[which], write_at)
+                local_n[which] = n_in
+            dist.barrier(group=self.group)   # every rank's stores have landed
+        if self.mode == "p2p":
+            m, c, tm = ops.local_join_ptrs(self._own[0], local_n[0], self._own[1], local_n[1])
+        else:
+            m, c, tm = ops.local_join(local_n[0], local_n[1])
+        res = ops.result_tensor(m, c)
+        dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
+        vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
+        return ShardedResult(vals[0], vals[1], local_n[0], local_n[1], tm)
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -1,0 +1,300 @@
+"""ctypes binding of the C ABI in include/gpujoin.h (libgpujoin.so).
+
+`JoinEngine` mirrors the reference operator outOfGPU_Join1_payload
+(/root/reference/src/hash_join_clustered_probe.cu:802-994): relations are (keys, payloads)
+int32 column pairs; `join_aggregate` returns what the reference prints as "%d results"
+(widened to 64 bit) plus the exact match count.  Device inputs are torch CUDA tensors (their
+data_ptr() crosses the ABI as a plain pointer); host inputs are numpy arrays / CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# every symbol include/gpujoin.h declares (tests check that the library exports all of them)
+C_ABI_SYMBOLS = [
+    "gj_create", "gj_destroy", "gj_last_error", "gj_version", "gj_set_stream", "gj_set_option",
+    "gj_get_option", "gj_join_aggregate", "gj_join_aggregate_tuples", "gj_join_aggregate_host",
+    "gj_join_materialize", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
+    "gj_shuffle_count", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
+    "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
+    "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_device_synchronize", "gj_flush_l2",
+    "gj_kernel_launch_count",
+]
+
+
+class GJError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libgpujoin error {code}: {msg}")
+        self.code = code
+
+
+class Timings(C.Structure):
+    _fields_ = [("hist_ms", C.c_float), ("part_ms", C.c_float), ("join_ms", C.c_float),
+                ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("wall_ms", C.c_float),
+                ("pass_ms", C.c_float * 4),
+                ("radix_bits", C.c_uint32), ("pass1_bits", C.c_uint32), ("pass2_bits", C.c_uint32),
+                ("kernel_launches", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: (list(getattr(self, k)) if k == "pass_ms" else getattr(self, k)) for k, _ in self._fields_}
+
+
+@dataclass
+class JoinResult:
+    matches: int
+    checksum: int
+    timings: Timings
+
+    @property
+    def ref_results_int32(self) -> int:
+        """The int32 the reference prints as `%d results` (hash_join_clustered_probe.cu:984-986)."""
+        v = self.checksum & 0xFFFFFFFF
+        return v - (1 << 32) if v >= (1 << 31) else v
+
+
+def lib_path() -> str:
+    return os.path.join(HERE, "lib", "libgpujoin.so")
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libgpujoin.so.  Fails loudly when it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise GJError(-2, f"{path} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C icde2019-gpu-join_b200/csrc); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, u64, u32, i32p = C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p
+    L.gj_create.argtypes = [C.POINTER(vp), C.c_int, u64, u64]
+    L.gj_destroy.argtypes = [vp]
+    L.gj_destroy.restype = None
+    L.gj_last_error.restype = C.c_char_p
+    L.gj_set_stream.argtypes = [vp, vp]
+    L.gj_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.gj_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
+    L.gj_join_aggregate.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
+    L.gj_join_aggregate_host.argtypes = L.gj_join_aggregate.argtypes
+    L.gj_join_aggregate_tuples.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
+    L.gj_join_materialize.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, i32p, i32p, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
+    L.gj_partition.argtypes = [vp, C.c_int, i32p, i32p, u64, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u32), C.POINTER(Timings)]
+    L.gj_shuffle_split.argtypes = [vp, i32p, i32p, u64, u32, u32, vp, C.POINTER(u64)]
+    L.gj_shuffle_scatter_peers.argtypes = [vp, i32p, i32p, u64, u32, u32, C.POINTER(vp), C.POINTER(u64)]
+    L.gj_shuffle_count.argtypes = [vp, i32p, u64, u32, u32, C.POINTER(u64)]
+    L.gj_generate_unique.argtypes = [vp, i32p, i32p, u64, u64, u64, u32, u32]
+    L.gj_bijection.argtypes = [u64, u64, u32]
+    L.gj_bijection.restype = u32
+    L.gj_payload_of_key.argtypes = [u32, u32]
+    L.gj_payload_of_key.restype = C.c_int32
+    L.gj_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.gj_malloc_device.argtypes = [C.POINTER(vp), u64]
+    L.gj_free_device.argtypes = [vp]
+    L.gj_malloc_pinned.argtypes = [C.POINTER(vp), u64]
+    L.gj_free_pinned.argtypes = [vp]
+    L.gj_memcpy_h2d.argtypes = [vp, vp, u64]
+    L.gj_memcpy_d2h.argtypes = [vp, vp, u64]
+    L.gj_flush_l2.argtypes = [vp]
+    L.gj_kernel_launch_count.restype = u64
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise GJError(rc, lib().gj_last_error().decode(errors="replace"))
+
+
+def kernel_launch_count() -> int:
+    return int(lib().gj_kernel_launch_count())
+
+
+def bijection(row: int, n_total: int, seed: int) -> int:
+    return int(lib().gj_bijection(row, n_total, seed))
+
+
+def payload_of_key(key: int, pay_seed: int) -> int:
+    return int(lib().gj_payload_of_key(key & 0xFFFFFFFF, pay_seed))
+
+
+def _dev_ptr(t, n_expected=None, what="tensor"):
+    """data_ptr of a contiguous int32 CUDA tensor."""
+    import torch
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{what}: expected a CUDA torch tensor")
+    if t.dtype not in (torch.int32, torch.uint32) or not t.is_contiguous():
+        raise TypeError(f"{what}: expected a contiguous int32 tensor")
+    if n_expected is not None and t.numel() != n_expected:
+        raise ValueError(f"{what}: expected {n_expected} elements, got {t.numel()}")
+    return C.c_void_p(t.data_ptr() if t.numel() else 0)
+
+
+def _host_ptr(a, what="array"):
+    import torch
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda or a.dtype != torch.int32 or not a.is_contiguous():
+            raise TypeError(f"{what}: expected a contiguous int32 CPU tensor")
+        return C.c_void_p(a.data_ptr() if a.numel() else 0), a.numel()
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return C.c_void_p(a.ctypes.data if a.size else 0), a.size, a
+
+
+class JoinEngine:
+    """One engine context per GPU (gj_create / gj_destroy)."""
+
+    def __init__(self, max_R: int, max_S: int, device: int = 0, **options):
+        self._L = lib()
+        self._ctx = C.c_void_p()
+        self.device = device
+        self.max_R, self.max_S = int(max_R), int(max_S)
+        _check(self._L.gj_create(C.byref(self._ctx), device, self.max_R, self.max_S))
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._L.gj_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- options / streams --------------------------------------------------------------
+    def set_option(self, name: str, value: int):
+        _check(self._L.gj_set_option(self._ctx, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int64()
+        _check(self._L.gj_get_option(self._ctx, name.encode(), C.byref(v)))
+        return int(v.value)
+
+    def use_torch_stream(self, stream=None):
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _check(self._L.gj_set_stream(self._ctx, C.c_void_p(s.cuda_stream)))
+
+    def _sync_inputs(self):
+        """The engine runs on its own stream: make sure torch has finished producing the inputs."""
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def flush_l2(self):
+        _check(self._L.gj_flush_l2(self._ctx))
+
+    # -- joins ----------------------------------------------------------------------------
+    def join_aggregate(self, Rk, Rp, Sk, Sp) -> JoinResult:
+        self._sync_inputs()
+        nR, nS = Rk.numel(), Sk.numel()
+        m, c, t = C.c_uint64(), C.c_uint64(), Timings()
+        _check(self._L.gj_join_aggregate(self._ctx, _dev_ptr(Rk, nR, "Rk"), _dev_ptr(Rp, nR, "Rp"), nR,
+                                         _dev_ptr(Sk, nS, "Sk"), _dev_ptr(Sp, nS, "Sp"), nS,
+                                         C.byref(m), C.byref(c), C.byref(t)))
+        return JoinResult(int(m.value), int(c.value), t)
+
+    def join_aggregate_tuples(self, Rt, nR, St, nS) -> JoinResult:
+        """Rt/St: int32 CUDA tensors of shape [n, 2] (or int64 [n]) holding packed {key,payload}."""
+        self._sync_inputs()
+        m, c, t = C.c_uint64(), C.c_uint64(), Timings()
+        _check(self._L.gj_join_aggregate_tuples(self._ctx, C.c_void_p(Rt.data_ptr() if nR else 0), nR,
+                                                C.c_void_p(St.data_ptr() if nS else 0), nS,
+                                                C.byref(m), C.byref(c), C.byref(t)))
+        return JoinResult(int(m.value), int(c.value), t)
+
+    def join_aggregate_ptrs(self, ptr_R: int, nR: int, ptr_S: int, nS: int) -> JoinResult:
+        """Packed-tuple join over raw device pointers (peer-store receive buffers)."""
+        self._sync_inputs()
+        m, c, t = C.c_uint64(), C.c_uint64(), Timings()
+        _check(self._L.gj_join_aggregate_tuples(self._ctx, C.c_void_p(ptr_R), nR, C.c_void_p(ptr_S), nS,
+                                                C.byref(m), C.byref(c), C.byref(t)))
+        return JoinResult(int(m.value), int(c.value), t)
+
+    def join_aggregate_host(self, Rk, Rp, Sk, Sp) -> JoinResult:
+        """End-to-end entry: host columns in, H2D copies inside the call."""
+        keep = [_host_ptr(x, n) for x, n in ((Rk, "Rk"), (Rp, "Rp"), (Sk, "Sk"), (Sp, "Sp"))]
+        if keep[0][1] != keep[1][1] or keep[2][1] != keep[3][1]:
+            raise ValueError("key and payload columns differ in length")
+        m, c, t = C.c_uint64(), C.c_uint64(), Timings()
+        _check(self._L.gj_join_aggregate_host(self._ctx, keep[0][0], keep[1][0], keep[0][1],
+                                              keep[2][0], keep[3][0], keep[2][1],
+                                              C.byref(m), C.byref(c), C.byref(t)))
+        return JoinResult(int(m.value), int(c.value), t)
+
+    def join_materialize(self, Rk, Rp, Sk, Sp, out_Rp, out_Sp):
+        """Returns (n_pairs, JoinResult); at most out_Rp.numel() pairs are written."""
+        self._sync_inputs()
+        nR, nS, cap = Rk.numel(), Sk.numel(), out_Rp.numel()
+        if out_Sp.numel() != cap:
+            raise ValueError("output columns differ in length")
+        n, c, t = C.c_uint64(), C.c_uint64(), Timings()
+        _check(self._L.gj_join_materialize(self._ctx, _dev_ptr(Rk, nR, "Rk"), _dev_ptr(Rp, nR, "Rp"), nR,
+                                           _dev_ptr(Sk, nS, "Sk"), _dev_ptr(Sp, nS, "Sp"), nS,
+                                           _dev_ptr(out_Rp, cap, "out_Rp"), _dev_ptr(out_Sp, cap, "out_Sp"), cap,
+                                           C.byref(n), C.byref(c), C.byref(t)))
+        return int(n.value), JoinResult(int(n.value), int(c.value), t)
+
+    # -- partitioner ----------------------------------------------------------------------
+    def partition(self, keys, pays, radix_bits: int = 0, slot: int = 0):
+        """Returns (tuples [n,2] int32 numpy copy, offsets [2^B+1] int64 numpy, B, timings)."""
+        self._sync_inputs()
+        n = keys.numel()
+        tp, op, b, t = C.c_void_p(), C.c_void_p(), C.c_uint32(), Timings()
+        _check(self._L.gj_partition(self._ctx, slot, _dev_ptr(keys, n, "keys"), _dev_ptr(pays, n, "pays"), n,
+                                    radix_bits, C.byref(tp), C.byref(op), C.byref(b), C.byref(t)))
+        B = int(b.value)
+        offs = np.empty((1 << B) + 1, dtype=np.uint32)
+        if n:
+            _check(self._L.gj_memcpy_d2h(C.c_void_p(offs.ctypes.data), op, offs.nbytes))
+            host = np.empty((n, 2), dtype=np.int32)
+            _check(self._L.gj_memcpy_d2h(C.c_void_p(host.ctypes.data), tp, host.nbytes))
+            tuples = host
+        else:
+            offs[:] = 0
+            tuples = np.empty((0, 2), dtype=np.int32)
+        return tuples, offs.astype(np.int64), B, t
+
+    # -- multi-GPU shuffle step -------------------------------------------------------------
+    def shuffle_count(self, keys, n_gpus: int, gpu_shift: int) -> np.ndarray:
+        self._sync_inputs()
+        n = keys.numel()
+        cnt = (C.c_uint64 * n_gpus)()
+        _check(self._L.gj_shuffle_count(self._ctx, _dev_ptr(keys, n, "keys"), n, n_gpus, gpu_shift, cnt))
+        return np.array(list(cnt), dtype=np.int64)
+
+    def shuffle_split(self, keys, pays, n_gpus: int, gpu_shift: int, out_tuples) -> np.ndarray:
+        """out_tuples: int64 CUDA tensor with >= n elements (packed tuples grouped by destination)."""
+        self._sync_inputs()
+        n = keys.numel()
+        if out_tuples.numel() * out_tuples.element_size() < n * 8:
+            raise ValueError("out_tuples too small")
+        cnt = (C.c_uint64 * n_gpus)()
+        _check(self._L.gj_shuffle_split(self._ctx, _dev_ptr(keys, n, "keys"), _dev_ptr(pays, n, "pays"), n,
+                                        n_gpus, gpu_shift, C.c_void_p(out_tuples.data_ptr()), cnt))
+        return np.array(list(cnt), dtype=np.int64)
+
+    def shuffle_scatter_peers(self, keys, pays, n_gpus: int, gpu_shift: int, peer_ptrs, peer_offsets):
+        self._sync_inputs()
+        n = keys.numel()
+        bases = (C.c_void_p * n_gpus)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        offs = (C.c_uint64 * n_gpus)(*[int(o) for o in peer_offsets])
+        _check(self._L.gj_shuffle_scatter_peers(self._ctx, _dev_ptr(keys, n, "keys"), _dev_ptr(pays, n, "pays"), n,
+                                                n_gpus, gpu_shift, bases, offs))
+
+    # -- synthetic data ---------------------------------------------------------------------
+    def generate_unique(self, keys, pays, row_begin: int, n_total: int, seed: int, pay_seed: int):
+        n = keys.numel()
+        _check(self._L.gj_generate_unique(self._ctx, _dev_ptr(keys, n, "keys"), _dev_ptr(pays, n, "pays"),
+                                          row_begin, n, n_total, seed, pay_seed))

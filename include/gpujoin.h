@@ -1,0 +1,183 @@
+/*
+ * gpujoin.h -- C ABI of libgpujoin.so: a B200-native (sm_100a) radix hash-join engine.
+ *
+ * Drop-in boundary for the reference's in-GPU join path (psiul/ICDE2019-GPU-Join).  Every entry
+ * point names the reference interface it replaces (file:line into the reference's src/).
+ * Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success or a
+ * negative gj_status; gj_last_error() then describes the failure.  Nothing in here ever calls
+ * exit() (the reference's CHK_ERROR does, common.h:132-141) and there is no CPU fallback: when
+ * no CUDA device is usable every compute entry point fails with GJ_ERR_CUDA.
+ *
+ * Data model (reference: hash_join_clustered_probe.cu:802, join-primitives.cu:1582):
+ *   a relation is two device (or host, *_host variants) arrays of n int32: keys and payloads
+ *   ("columnar", as the reference passes R/Pr and S/Ps).  n < 2^32 - 2^20 per relation.
+ *   Join = inner equi-join on the full 32-bit key, all pairs (N:M allowed).
+ *   Aggregate = { matches, checksum } with checksum = SUM over result pairs of
+ *   (int64)Pr*(int64)Ps mod 2^64; its low 32 bits are the int32 the reference prints as
+ *   "%d results" (hash_join_clustered_probe.cu:984-986, join-primitives.cu:1073,1092).
+ */
+#ifndef GPUJOIN_H
+#define GPUJOIN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GJ_VERSION 1
+
+typedef enum gj_status {
+    GJ_OK = 0,
+    GJ_ERR_ARG = -1,      /* bad argument (null pointer, size over capacity, bad option) */
+    GJ_ERR_CUDA = -2,     /* a CUDA runtime call failed / no device */
+    GJ_ERR_NOMEM = -3,    /* device or host allocation failed */
+    GJ_ERR_STATE = -4     /* call sequence error (e.g. result queried before a join) */
+} gj_status;
+
+typedef struct gj_ctx gj_ctx;
+
+/* Device-side timings of the last call, CUDA events on the engine's stream (milliseconds).
+ * Same window as the reference's t1..t2 (hash_join_clustered_probe.cu:954-980): inputs resident
+ * in HBM, no allocation inside.  h2d_ms/d2h_ms are only filled by the *_host entry points. */
+typedef struct gj_timings {
+    float hist_ms;       /* radix histograms of R and S + offset scan + work planning */
+    float part_ms;       /* all radix scatter passes of R and S */
+    float join_ms;       /* per-partition build + probe + final reduction */
+    float total_ms;      /* hist + part + join, one event pair around everything */
+    float h2d_ms;        /* host->device copies (host entry points), else 0 */
+    float wall_ms;       /* host steady_clock around the whole call, including the final sync */
+    float pass_ms[4];    /* each scatter launch: build pass 1, build pass 2, probe pass 1, probe pass 2
+                            (pass-2 slots are 0 for a single-pass plan) */
+    uint32_t radix_bits;     /* total radix bits B used (2^B partitions) */
+    uint32_t pass1_bits;     /* bits of the first pass (== radix_bits when single pass) */
+    uint32_t pass2_bits;     /* bits of the second pass (0 when single pass) */
+    uint32_t kernel_launches;/* kernels launched inside the timed window */
+} gj_timings;
+
+/* ---- lifetime -------------------------------------------------------------------------------
+ * Replaces the 16+ cudaMalloc calls the reference issues per join and never frees
+ * (hash_join_clustered_probe.cu:832-872): all scratch is allocated once, here, for relations of
+ * up to max_R / max_S tuples, and released by gj_destroy. */
+int gj_create(gj_ctx** out, int device, uint64_t max_R, uint64_t max_S);
+void gj_destroy(gj_ctx* ctx);
+const char* gj_last_error(void);
+int gj_version(void);
+
+/* Run on a caller-owned cudaStream_t (passed as void*); NULL = the engine's own stream.
+ * Reference: the single explicit stream streams_R[1], hash_join_clustered_probe.cu:809-811. */
+int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
+
+/* Tuning knobs; the reference fixes these at compile time (common.h:51-71).  Names:
+ *   "radix_bits"   total radix bits B, 0 = choose from |build side| (default)
+ *   "pass1_bits"   bits of the first pass, 0 = choose
+ *   "scatter_cfg"  scatter kernel shape variant (0 = default)
+ *   "unit_tuples"  probe-side work-unit size in tuples (skew splitting), 0 = default
+ *   "gpu_bits"     number of key bits above the radix field consumed by the multi-GPU shuffle
+ *   "use_graph"    1 = replay the pipeline from a CUDA graph when shapes repeat */
+int gj_set_option(gj_ctx* ctx, const char* name, int64_t value);
+int gj_get_option(gj_ctx* ctx, const char* name, int64_t* value);
+
+/* ---- the operator --------------------------------------------------------------------------
+ * gj_join_aggregate replaces outOfGPU_Join1_payload's aggregate run
+ * (hash_join_clustered_probe.cu:944-991: prepare_Relation_payload x2, decompose_chains,
+ * join_partitioned_aggregate) with inputs already on the device.  d_* are device pointers. */
+int gj_join_aggregate(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
+                      const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS,
+                      uint64_t* matches, uint64_t* checksum, gj_timings* t);
+
+/* Same join over packed device tuples {key,payload} (int32 pairs, 8-byte aligned), the layout
+ * the multi-GPU shuffle delivers. */
+int gj_join_aggregate_tuples(gj_ctx* ctx, const void* d_Rtup, uint64_t nR, const void* d_Stup,
+                             uint64_t nS, uint64_t* matches, uint64_t* checksum, gj_timings* t);
+
+/* End-to-end variant: h_* are HOST pointers (pinned or pageable); the H2D copies are part of the
+ * call, chunked and overlapped with the radix histograms.  Replaces the cudaMemcpy H2D block +
+ * aggregate run of outOfGPU_Join1_payload (hash_join_clustered_probe.cu:874-877, 944-991). */
+int gj_join_aggregate_host(gj_ctx* ctx, const int32_t* h_Rk, const int32_t* h_Rp, uint64_t nR,
+                           const int32_t* h_Sk, const int32_t* h_Sp, uint64_t nS,
+                           uint64_t* matches, uint64_t* checksum, gj_timings* t);
+
+/* Materialising join: replaces join_partitioned_results (join-primitives.cu:1107-1416) and the
+ * first run of outOfGPU_Join1_payload (hash_join_clustered_probe.cu:883-940).  Writes result
+ * pairs (Pr, Ps) to the device columns d_out_Rp/d_out_Sp in unspecified order; at most `cap`
+ * pairs are written, *n_pairs is always the exact result size (the reference's ring buffer
+ * overwrites itself instead, join-primitives.cu:1097-1099).  matches/checksum as above. */
+int gj_join_materialize(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
+                        const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS, int32_t* d_out_Rp,
+                        int32_t* d_out_Sp, uint64_t cap, uint64_t* n_pairs, uint64_t* checksum,
+                        gj_timings* t);
+
+/* ---- the partitioner on its own --------------------------------------------------------------
+ * Replaces prepare_Relation_payload (join-primitives.cu:1582-1613: init_metadata_double,
+ * partition_pass_one, compute_bucket_info, partition_pass_two).  Partitions one relation on its
+ * low `radix_bits` key bits (identity hash, first_bit 0, like common.h:45-47 /
+ * hash_join_clustered_probe.cu:813) into 2^radix_bits CONTIGUOUS partitions (no bucket chains).
+ * radix_bits = 0 lets the engine choose from n.  Results stay in the context until the next call
+ * on the same slot (slot 0 = build side buffers, 1 = probe side buffers):
+ *   *d_tuples   device pointer to n packed {key,payload} pairs, partition p occupying
+ *               [offsets[p], offsets[p+1])
+ *   *d_offsets  device pointer to 2^B + 1 uint32 offsets
+ * Order inside a partition is unspecified. */
+int gj_partition(gj_ctx* ctx, int slot, const int32_t* d_keys, const int32_t* d_pays, uint64_t n,
+                 uint32_t radix_bits, const void** d_tuples, const uint32_t** d_offsets,
+                 uint32_t* radix_bits_used, gj_timings* t);
+
+/* ---- multi-GPU shuffle step (no reference counterpart) ----------------
+ * Splits one relation by destination GPU d = (key >> gpu_shift) & (n_gpus-1) (n_gpus a power of
+ * two <= 256).  Output: packed tuples grouped by destination in d_out_tuples (n tuples) and the
+ * per-destination counts in h_counts[n_gpus] (host).  The caller exchanges counts and ships the
+ * groups (NCCL all-to-all or peer stores), then runs gj_join_aggregate_tuples on what it
+ * received with option "gpu_bits" = log2(n_gpus). */
+int gj_shuffle_split(gj_ctx* ctx, const int32_t* d_keys, const int32_t* d_pays, uint64_t n,
+                     uint32_t n_gpus, uint32_t gpu_shift, void* d_out_tuples, uint64_t* h_counts);
+
+/* Peer-store variant: d_peer_bases[g] is a device pointer (local, or a peer / IPC mapping over
+ * NVLink) to GPU g's receive buffer of packed tuples and h_peer_offsets[g] the first tuple slot
+ * this GPU may write there.  The scatter kernel stores straight into the destinations from its
+ * shared-memory staging, so partitioning and the all-to-all are one kernel.  Counts as above. */
+int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, const int32_t* d_pays,
+                             uint64_t n, uint32_t n_gpus, uint32_t gpu_shift,
+                             void* const* d_peer_bases, const uint64_t* h_peer_offsets);
+
+/* CUDA IPC plumbing for the peer-store variant when every GPU is driven by its own process:
+ * export a gj_malloc_device allocation as a 64-byte handle, open a peer's handle (peer access is
+ * enabled lazily), close it again. */
+int gj_ipc_export(void* d_ptr, char handle[64]);
+int gj_ipc_open(const char handle[64], void** d_ptr);
+int gj_ipc_close(void* d_ptr);
+
+/* Per-destination histogram only (what ranks exchange before gj_shuffle_scatter_peers). */
+int gj_shuffle_count(gj_ctx* ctx, const int32_t* d_keys, uint64_t n, uint32_t n_gpus,
+                     uint32_t gpu_shift, uint64_t* h_counts);
+
+/* ---- synthetic relations on the device ---------------------
+ * rows [row_begin, row_begin+n_rows) of a relation of n_total unique keys: key = pi_seed(row), a
+ * seeded bijection on [0, n_total) (cycle-walking Feistel network); payload = mix(key, seed)
+ * so that the checksum of a join is a function of the key set only. */
+int gj_generate_unique(gj_ctx* ctx, int32_t* d_keys, int32_t* d_pays, uint64_t row_begin,
+                       uint64_t n_rows, uint64_t n_total, uint32_t seed, uint32_t pay_seed);
+
+/* Host helpers mirroring the device generator bit for bit (used to derive known answers). */
+uint32_t gj_bijection(uint64_t row, uint64_t n_total, uint32_t seed);
+int32_t gj_payload_of_key(uint32_t key, uint32_t pay_seed);
+
+/* ---- device memory convenience (so a plain-C host can drive the engine without cudart) ------ */
+int gj_device_count(int* n);
+int gj_malloc_device(void** p, uint64_t bytes);
+int gj_free_device(void* p);
+int gj_malloc_pinned(void** p, uint64_t bytes);
+int gj_free_pinned(void* p);
+int gj_memcpy_h2d(void* d, const void* h, uint64_t bytes);
+int gj_memcpy_d2h(void* h, const void* d, uint64_t bytes);
+int gj_device_synchronize(void);
+/* L2 flush helper for benchmarks: writes a scratch buffer larger than L2. */
+int gj_flush_l2(gj_ctx* ctx);
+/* Number of kernels this library has launched since it was loaded (bench.py's gpu_launches). */
+uint64_t gj_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUJOIN_H */

@@ -60,6 +60,11 @@ def _load() -> C.CDLL:
     lib.orc_partition.argtypes = [_i32p, _i32p, C.c_uint64, C.c_uint32, C.c_uint32, _u64p, _i32p, _i32p]
     lib.orc_partition_fingerprint.argtypes = [_i32p, _i32p, C.c_uint64, C.c_uint32, C.c_uint32, _u64p, _u64p]
     lib.orc_max_threads.restype = C.c_int
+    lib.orc_payload_of_keys.argtypes = [_i32p, C.c_uint64, C.c_uint32, _i32p]
+    lib.orc_bijection.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+    lib.orc_bijection.restype = C.c_uint32
+    lib.orc_unique_join_checksum.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+    lib.orc_unique_join_checksum.restype = C.c_uint64
     return lib
 
 
@@ -183,6 +188,21 @@ def partition_fingerprint(keys, pays, shift: int, bits: int):
     hsh = np.zeros(1 << bits, np.uint64)
     lib().orc_partition_fingerprint(keys, pays, keys.size, shift, bits, cnt, hsh)
     return cnt, hsh
+
+
+def payload_of_keys(keys, pay_seed: int) -> np.ndarray:
+    keys = _c(keys)
+    out = np.empty_like(keys)
+    lib().orc_payload_of_keys(keys, keys.size, pay_seed, out)
+    return out
+
+
+def bijection(row: int, n_total: int, seed: int) -> int:
+    return int(lib().orc_bijection(row, n_total, seed))
+
+
+def unique_join_checksum(k_begin: int, k_end: int, seed_a: int, seed_b: int) -> int:
+    return int(lib().orc_unique_join_checksum(k_begin, k_end, seed_a, seed_b))
 
 
 def max_threads() -> int:

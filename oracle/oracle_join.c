@@ -443,3 +443,44 @@ void orc_partition_fingerprint(const int32_t *keys, const int32_t *pays, uint64_
         hashes[d] += pair_mix(keys[i], pays ? pays[i] : 0);
     }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* 5. Synthetic unique relations of BASELINE config 5 (no reference counterpart)         */
+/* ------------------------------------------------------------------------------------ */
+/* Independent restatement of the engine's device generator contract (include/gpujoin.h,
+ * gj_generate_unique): key = seeded bijection of the row id on [0,n), payload = f(key, seed).
+ * With both relations holding every key of [0,n) exactly once the join has n matches and
+ * checksum = SUM_k f(k,seedR)*f(k,seedS) mod 2^64 -- a closed form over the key set. */
+static inline uint32_t orc_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+static inline int32_t orc_payload(uint32_t key, uint32_t pay_seed) {
+    return (int32_t)orc_mix32(key ^ (pay_seed * 0xC2B2AE35u + 0x27D4EB2Fu));
+}
+void orc_payload_of_keys(const int32_t *keys, uint64_t n, uint32_t pay_seed, int32_t *out) {
+    for (uint64_t i = 0; i < n; ++i) out[i] = orc_payload((uint32_t)keys[i], pay_seed);
+}
+uint32_t orc_bijection(uint64_t row, uint64_t n_total, uint32_t seed) {
+    uint32_t bits = 2;
+    while (bits < 32 && (1ull << bits) < n_total) ++bits;
+    uint32_t half = (bits + 1) >> 1, hm = (1u << half) - 1u;
+    uint64_t x = row;
+    do {
+        uint32_t L = (uint32_t)(x >> half) & hm, R = (uint32_t)x & hm;
+        for (uint32_t r = 0; r < 4; ++r) {
+            uint32_t f = orc_mix32(R + seed * 0x9E3779B9u + r * 0x85EBCA6Bu) & hm;
+            uint32_t nl = R; R = L ^ f; L = nl;
+        }
+        x = ((uint64_t)L << half) | R;
+    } while (x >= n_total);
+    return (uint32_t)x;
+}
+/* SUM over keys k in [k_begin,k_end) of f(k,a)*f(k,b) mod 2^64 */
+uint64_t orc_unique_join_checksum(uint64_t k_begin, uint64_t k_end, uint32_t seed_a, uint32_t seed_b) {
+    uint64_t s = 0;
+#pragma omp parallel for reduction(+ : s)
+    for (uint64_t k = k_begin; k < k_end; ++k)
+        s += pay_prod(orc_payload((uint32_t)k, seed_a), orc_payload((uint32_t)k, seed_b));
+    return s;
+}

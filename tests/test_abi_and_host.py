@@ -1,0 +1,123 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol
+include/gpujoin.h declares, fails loudly without a GPU (no CPU fallback), and the product's
+ETHZ-style generator (csrc/generator.cpp) reproduces the reference generator's golden vectors
+(tests/golden/, produced from the reference's object code by tests/golden/make_golden.py)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "generator_vectors.npz"))
+
+
+def test_library_exports_every_declared_symbol(gj):
+    L = gj.lib()
+    hdr = open(os.path.join(ROOT, "include", "gpujoin.h")).read()
+    declared = set(re.findall(r"\b(gj_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"gj_status", "gj_timings", "gj_ctx"}
+    assert declared, "no declarations parsed"
+    assert declared == set(gj.C_ABI_SYMBOLS), declared ^ set(gj.C_ABI_SYMBOLS)
+    for sym in sorted(declared):
+        assert hasattr(L, sym), f"libgpujoin.so does not export {sym}"
+    gen_hdr = open(os.path.join(ROOT, "include", "gpujoin_generator.h")).read()
+    for sym in set(re.findall(r"\b(gj_[a-z0-9_]+)\s*\(", gen_hdr)):
+        assert hasattr(L, sym), f"libgpujoin.so does not export {sym}"
+    assert hasattr(L, "gj_operator_last_result") and hasattr(L, "gj_operator_release")
+    # the reference-shaped C++ operator symbols (hash_join_clustered_probe.cu:802,1990,2062)
+    for mangled in ("_Z22hashJoinClusteredProbeP4argsP10timingInfo",
+                    "_Z17hj_ClusteredProbePimS_mP10timingInfo",
+                    "_Z22outOfGPU_Join1_payloadPiS_mS_S_mP10timingInfojjj"):
+        assert hasattr(L, mangled), mangled
+    assert L.gj_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback(gj):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    with pytest.raises(gj.GJError) as ei:
+        gj.JoinEngine(1024, 1024, 0)
+    assert ei.value.code == -2     # GJ_ERR_CUDA
+    L = gj.lib()
+    ctx = C.c_void_p()
+    assert L.gj_create(C.byref(ctx), 0, 16, 16) == -2 and not ctx.value
+    assert L.gj_last_error()
+
+
+def test_missing_library_raises(gj, monkeypatch, tmp_path):
+    from importlib import reload  # noqa: F401
+    import icde2019_gpu_join_b200.engine as eng
+    monkeypatch.setattr(eng, "_lib", None)
+    monkeypatch.setattr(eng, "HERE", str(tmp_path))
+    with pytest.raises(gj.GJError, match="no CPU fallback"):
+        eng.lib()
+
+
+def test_host_helpers_match_oracle(gj, orc):
+    for n, seed in ((1000, 1), (1 << 20, 7), (128_000_000, 4), (2_000_000_000, 9)):
+        for row in (0, 1, n // 3, n - 1):
+            assert gj.bijection(row, n, seed) == orc.bijection(row, n, seed) < n
+    keys = np.array([0, 1, 5, 2**31 - 1, -1, -2**31], dtype=np.int32)
+    want = orc.payload_of_keys(keys, 40)
+    assert [gj.payload_of_key(int(k), 40) for k in keys] == [int(x) for x in want]
+    # small bijection is a permutation
+    n = 5000
+    assert sorted(gj.bijection(i, n, 3) for i in range(n)) == list(range(n))
+
+
+# ---- product generator vs the reference's golden vectors (generator_ETHZ.cu:115-348) --------
+@pytest.mark.parametrize("seed", [1, 12345, 0xDEADBEEF])
+def test_generator_shuffle48(gj, seed):
+    g = gj.generator
+    got = g.knuth_shuffle48(np.arange(1000, dtype=np.int32), g.state48(seed))
+    assert np.array_equal(got, GOLD[f"shuffle48_seed{seed}"])
+
+
+def test_generator_rand_driven_functions(gj):
+    g = gj.generator
+    g.seed_generator(7)
+    assert np.array_equal(g.knuth_shuffle(np.arange(1000, dtype=np.int32)), GOLD["shuffle_srand7"])
+    g.seed_generator(3)
+    assert np.array_equal(g.random_gen(1000, 500), GOLD["random_gen_srand3_n1000_max500"])
+    pk = g.knuth_shuffle48(np.arange(64, dtype=np.int32), g.state48(5))
+    g.seed_generator(11)
+    assert np.array_equal(g.create_relation_fk_from_pk(200, pk), GOLD["fk_pk64_n200_srand11"])
+    for z in (0.5, 1.0):
+        g.seed_generator(42)
+        assert np.array_equal(g.gen_zipf(2000, 1000, z), GOLD[f"zipf_srand42_n2000_a1000_z{z}"])
+
+
+def test_generator_unique_multisets_and_file_cache(gj, orc, tmp_path):
+    g = gj.generator
+    assert np.array_equal(np.sort(g.create_relation_unique(40, 16, 1)), GOLD["unique_n40_max16_sorted"])
+    assert np.array_equal(np.sort(g.create_relation_unique(64, 64, 1)), GOLD["unique_n64_max64_sorted"])
+    assert np.array_equal(g.create_relation_unique(5000, 5000, 77), orc.random_unique_gen(5000, 5000, 77))
+    # file cache, raw little-endian int32 (generator_ETHZ.cu:38-72, 86-94)
+    f = str(tmp_path / "unique_5000.bin")
+    a = g.create_relation_unique(5000, 5000, 5, filename=f)
+    assert os.path.getsize(f) == 5000 * 4 and np.array_equal(np.fromfile(f, np.int32), a)
+    b = g.create_relation_unique(5000, 5000, 6, filename=f)     # second call reads the cache
+    assert np.array_equal(a, b)
+    assert np.array_equal(g.read_relation(f, 5000), a)
+    assert np.array_equal(g.create_relation_n(a[:10], 3), np.tile(a[:10], 3))
+
+
+def test_parallel_generators_keep_the_reference_distributions(gj):
+    g = gj.generator
+    n = 200_000
+    u = g.create_relation_unique_parallel(n, n, 3)
+    assert np.array_equal(np.sort(u), np.arange(n)) and not np.array_equal(u, np.arange(n))
+    assert np.array_equal(u, g.create_relation_unique_parallel(n, n, 3, threads=1))   # thread-count independent
+    fk = g.create_relation_unique_parallel(n, 1000, 4)      # 0,1..1000,1..1000,...
+    cnt = np.bincount(fk, minlength=1001)
+    assert cnt[0] == 1 and cnt.sum() == n and cnt[1:].min() >= (n - 1) // 1000
+    z = g.create_relation_zipf_parallel(n, 1000, 1.0, 5)
+    assert z.min() >= 1 and z.max() <= 1000
+    top = np.sort(np.bincount(z))[::-1]
+    h = (1.0 / np.arange(1, 1001)).sum()
+    assert abs(top[0] / n - 1 / h) < 0.01 and abs(top[1] / n - 0.5 / h) < 0.01
+    flat = g.create_relation_zipf_parallel(n, 1000, 0.0, 5)
+    assert np.bincount(flat)[1:].min() > 100

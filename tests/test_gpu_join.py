@@ -1,0 +1,364 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI against the CPU
+oracle on identical seeded inputs.  Bit-exact: match count, 64-bit checksum, pair multiset hash,
+partition offsets and per-partition multisets.  Reference semantics: join-primitives.cu:885-1095
+(aggregate), :1107-1416 (materialise), :58-535 (partition passes)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def dev(torch, *arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).cuda() for a in arrs]
+
+
+def rnd(rng, n, lo, hi):
+    return rng.integers(lo, hi, size=n, dtype=np.int64).astype(np.int32)
+
+
+@pytest.fixture(scope="module")
+def eng(gj, torch_cuda):
+    e = gj.JoinEngine(1 << 22, 1 << 23, 0)
+    yield e
+    e.close()
+
+
+def reset(eng):
+    for k in ("radix_bits", "pass1_bits", "scatter_cfg", "join_cfg", "unit_tuples", "gpu_bits"):
+        eng.set_option(k, 0)
+    eng.set_option("part_target", 4096)
+
+
+# ------------------------------------------------------------------------------- partitioner
+@pytest.mark.parametrize("n,bits", [(0, 4), (1, 1), (5, 3), (4096, 8), (4097, 8), (100_003, 0),
+                                    (1 << 20, 8), (300_000, 11), (1_000_000, 15), (777_777, 13)])
+def test_partition_matches_oracle(gj, orc, eng, torch_cuda, n, bits):
+    reset(eng)
+    rng = np.random.default_rng(n + bits)
+    keys, pays = rnd(rng, n, -2**31, 2**31), rnd(rng, n, -2**31, 2**31)
+    dk, dp = dev(torch_cuda, keys, pays)
+    tup, off, B, t = eng.partition(dk, dp, bits)
+    if bits:
+        assert B == bits
+    want_off, _, _ = orc.partition(keys, pays, 0, B)
+    assert np.array_equal(off, want_off.astype(np.int64))
+    ok, op = np.ascontiguousarray(tup[:, 0]), np.ascontiguousarray(tup[:, 1])
+    # every tuple sits inside the range of its own partition ...
+    pid = np.repeat(np.arange(1 << B), np.diff(off))
+    assert np.array_equal((ok.view(np.uint32) & ((1 << B) - 1)).astype(np.int64), pid)
+    # ... and each partition holds exactly the oracle's multiset
+    c1, h1 = orc.partition_fingerprint(keys, pays, 0, B)
+    c2, h2 = orc.partition_fingerprint(ok, op, 0, B)
+    assert np.array_equal(c1, c2) and np.array_equal(h1, h2)
+
+
+@pytest.mark.parametrize("cfg", range(10))
+def test_partition_every_scatter_variant(gj, orc, eng, torch_cuda, cfg):
+    reset(eng)
+    eng.set_option("scatter_cfg", cfg)
+    rng = np.random.default_rng(cfg)
+    n = 600_011
+    keys, pays = rnd(rng, n, 0, 1 << 20), np.arange(n, dtype=np.int32)
+    dk, dp = dev(torch_cuda, keys, pays)
+    for bits in (7, 12):
+        tup, off, B, _ = eng.partition(dk, dp, bits)
+        want_off, _, _ = orc.partition(keys, pays, 0, B)
+        assert np.array_equal(off, want_off.astype(np.int64))
+        c1, h1 = orc.partition_fingerprint(keys, pays, 0, B)
+        c2, h2 = orc.partition_fingerprint(np.ascontiguousarray(tup[:, 0]), np.ascontiguousarray(tup[:, 1]), 0, B)
+        assert np.array_equal(c1, c2) and np.array_equal(h1, h2)
+    reset(eng)
+
+
+def test_partition_skewed_digit(gj, orc, eng, torch_cuda):
+    """Most of a tile falls into one digit (Zipf-like): stresses same-address shared atomics."""
+    reset(eng)
+    rng = np.random.default_rng(9)
+    n = 500_000
+    keys = np.where(rng.random(n) < 0.8, 77, rng.integers(0, 1 << 16, n)).astype(np.int32)
+    pays = np.arange(n, dtype=np.int32)
+    tup, off, B, _ = eng.partition(*dev(torch_cuda, keys, pays), 10)
+    c1, h1 = orc.partition_fingerprint(keys, pays, 0, B)
+    c2, h2 = orc.partition_fingerprint(np.ascontiguousarray(tup[:, 0]), np.ascontiguousarray(tup[:, 1]), 0, B)
+    assert np.array_equal(c1, c2) and np.array_equal(h1, h2)
+
+
+# ------------------------------------------------------------------------------- aggregate join
+CASES = [
+    (0, 0, 0, 10), (0, 17, 0, 10), (17, 0, 0, 10), (1, 1, 5, 6), (3, 2, 0, 2),
+    (300, 500, 0, 64),                       # heavy duplicates on both sides (N:M)
+    (1000, 3000, -2**31, 2**31),             # full key range incl. negative keys
+    (5000, 5000, -50, 50),
+    (40_000, 9_000, 0, 20_000),              # build side becomes S (smaller)
+    (200_000, 700_000, 0, 150_000),
+    (1 << 20, 1 << 20, 0, 1 << 20),
+    (3_000_000, 5_000_000, -2**31, 2**31),   # two passes
+]
+
+
+@pytest.mark.parametrize("nR,nS,lo,hi", CASES)
+def test_join_aggregate_matches_oracle(gj, orc, eng, torch_cuda, nR, nS, lo, hi):
+    reset(eng)
+    rng = np.random.default_rng(nR * 7919 + nS)
+    Rk, Sk = rnd(rng, nR, lo, hi), rnd(rng, nS, lo, hi)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    got = eng.join_aggregate(*dev(torch_cuda, Rk, Rp, Sk, Sp))
+    assert (got.matches, got.checksum) == (want.matches, want.checksum)
+    assert got.ref_results_int32 == want.ref_results_int32
+    if nR and nS:
+        assert got.timings.kernel_launches >= 5
+
+
+def test_config1_reference_workload(gj, orc, eng, torch_cuda):
+    """BASELINE config 1: |R|=|S|=2^20 unique keys (generator_ETHZ.cu:127-149), FK join.
+    Known answer: 2^20 matches; with all-ones payloads the reference prints `1048576 results`."""
+    reset(eng)
+    n = 1 << 20
+    R = gj.generator.create_relation_unique(n, n, 1)
+    S = gj.generator.create_relation_unique(n, n, 2)
+    assert np.array_equal(R, orc.random_unique_gen(n, n, 1))      # product generator == oracle
+    ones = np.ones(n, np.int32)
+    got = eng.join_aggregate(*dev(torch_cuda, R, ones, S, ones))
+    assert (got.matches, got.checksum, got.ref_results_int32) == (n, n, n)
+    rid = np.arange(n, dtype=np.int32)
+    want = orc.join_check(R, rid, S, rid)
+    got = eng.join_aggregate(*dev(torch_cuda, R, rid, S, rid))
+    assert (got.matches, got.checksum) == (want.matches, want.checksum)
+    assert got.timings.radix_bits == 8 and got.timings.pass2_bits == 0
+
+
+def test_fk_pattern_known_answer(gj, orc, eng, torch_cuda):
+    """S = create_relation_unique(nS, maxid=nR) -> matches = nS - floor((nS-1)/nR)."""
+    reset(eng)
+    nR, nS = 1 << 18, 1 << 22
+    R = gj.generator.create_relation_unique(nR, nR, 3)
+    S = gj.generator.create_relation_unique(nS, nR, 4)
+    got = eng.join_aggregate(*dev(torch_cuda, R, np.ones(nR, np.int32), S, np.ones(nS, np.int32)))
+    assert got.matches == nS - (nS - 1) // nR == got.checksum
+
+
+@pytest.mark.parametrize("z", [0.5, 1.0])
+def test_zipf_probe_side(gj, orc, eng, torch_cuda, z):
+    """BASELINE config 4 (scaled down): Zipf-skewed probe side -> unit splitting of hot partitions."""
+    reset(eng)
+    nR, nS = 1 << 21, 1 << 22
+    R = gj.generator.create_relation_unique_parallel(nR, nR, 6)
+    S = gj.generator.create_relation_zipf_parallel(nS, nR, z, 7)
+    Rp, Sp = np.arange(nR, dtype=np.int32), np.arange(nS, dtype=np.int32) * 3
+    want = orc.join_check(R, Rp, S, Sp)
+    got = eng.join_aggregate(*dev(torch_cuda, R, Rp, S, Sp))
+    assert (got.matches, got.checksum) == (want.matches, want.checksum)
+    assert got.matches == nS - int((S == nR).sum())
+
+
+def test_build_partition_larger_than_shared_memory(gj, orc, eng, torch_cuda):
+    """Heavy-hitter BUILD keys: one partition exceeds the shared-memory table and is joined in
+    rounds (the reference's block-nested branch, join-primitives.cu:929-1003)."""
+    reset(eng)
+    rng = np.random.default_rng(3)
+    nR, nS = 60_000, 90_000
+    Rk = np.where(rng.random(nR) < 0.5, 42, rng.integers(0, 1000, nR)).astype(np.int32)
+    Sk = np.where(rng.random(nS) < 0.01, 42, rng.integers(0, 1000, nS)).astype(np.int32)
+    Rp, Sp = rnd(rng, nR, -1000, 1000), rnd(rng, nS, -1000, 1000)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    for jc in (0, 2, 6):
+        eng.set_option("join_cfg", jc)
+        got = eng.join_aggregate(*dev(torch_cuda, Rk, Rp, Sk, Sp))
+        assert (got.matches, got.checksum) == (want.matches, want.checksum), jc
+    reset(eng)
+
+
+def test_every_radix_split_and_join_variant(gj, orc, eng, torch_cuda):
+    reset(eng)
+    rng = np.random.default_rng(11)
+    nR, nS = 400_000, 900_000
+    Rk, Sk = rnd(rng, nR, 0, 300_000), rnd(rng, nS, 0, 300_000)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    d = dev(torch_cuda, Rk, Rp, Sk, Sp)
+    for bits in (1, 5, 8, 9, 12, 15):
+        eng.set_option("radix_bits", bits)
+        got = eng.join_aggregate(*d)
+        assert (got.matches, got.checksum) == (want.matches, want.checksum), bits
+        assert got.timings.radix_bits == bits
+    eng.set_option("radix_bits", 14)
+    for p1 in (6, 7, 8):
+        eng.set_option("pass1_bits", p1)
+        got = eng.join_aggregate(*d)
+        assert (got.matches, got.checksum) == (want.matches, want.checksum), p1
+        assert (got.timings.pass1_bits, got.timings.pass2_bits) == (p1, 14 - p1)
+    reset(eng)
+    for jc in range(eng.get_option("num_join_cfgs")):
+        eng.set_option("join_cfg", jc)
+        for unit in (0, 1024, 5000):
+            eng.set_option("unit_tuples", unit)
+            got = eng.join_aggregate(*d)
+            assert (got.matches, got.checksum) == (want.matches, want.checksum), (jc, unit)
+    reset(eng)
+
+
+def test_packed_tuple_entry(gj, orc, eng, torch_cuda):
+    reset(eng)
+    rng = np.random.default_rng(12)
+    nR, nS = 333_333, 1_000_001
+    Rk, Sk = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    Sk[: nR] = Rk    # guarantee matches
+    Rp, Sp = rnd(rng, nR, -9, 9), rnd(rng, nS, -9, 9)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    Rt = torch_cuda.from_numpy(np.stack([Rk, Rp], axis=1).copy()).cuda()
+    St = torch_cuda.from_numpy(np.stack([Sk, Sp], axis=1).copy()).cuda()
+    got = eng.join_aggregate_tuples(Rt, nR, St, nS)
+    assert (got.matches, got.checksum) == (want.matches, want.checksum)
+
+
+def test_host_entry_end_to_end(gj, orc, eng, torch_cuda):
+    reset(eng)
+    rng = np.random.default_rng(13)
+    nR, nS = 1_500_000, 2_500_000
+    Rk, Sk = rnd(rng, nR, 0, 1 << 21), rnd(rng, nS, 0, 1 << 21)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    eng.set_option("h2d_chunk", 300_000)    # many chunks: histogram chases the copies
+    got = eng.join_aggregate_host(Rk, Rp, Sk, Sp)
+    assert (got.matches, got.checksum) == (want.matches, want.checksum)
+    assert got.timings.h2d_ms > 0
+    pin = [torch_cuda.from_numpy(a).pin_memory() for a in (Sk, Sp, Rk, Rp)]   # swapped roles too
+    got = eng.join_aggregate_host(*pin)
+    assert (got.matches, got.checksum) == (want.matches, want.checksum)
+    eng.set_option("h2d_chunk", 8 << 20)
+
+
+# ------------------------------------------------------------------------------- materialise
+@pytest.mark.parametrize("nR,nS,hi", [(0, 5, 4), (2000, 3000, 50), (1 << 18, 1 << 19, 1 << 18), (900_000, 300_000, 1 << 19)])
+def test_materialize_pairs_match_oracle(gj, orc, eng, torch_cuda, nR, nS, hi):
+    reset(eng)
+    rng = np.random.default_rng(nR + nS)
+    Rk, Sk = rnd(rng, nR, 0, hi), rnd(rng, nS, 0, hi)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    cap = max(int(want.matches), 1)
+    out_r = torch_cuda.full((cap,), 123456789, dtype=torch_cuda.int32, device="cuda")
+    out_s = torch_cuda.full((cap,), 123456789, dtype=torch_cuda.int32, device="cuda")
+    n, res = eng.join_materialize(*dev(torch_cuda, Rk, Rp, Sk, Sp), out_r, out_s)
+    assert n == want.matches and res.checksum == want.checksum
+    k = int(want.matches)
+    assert orc.pairs_hash(out_r.cpu().numpy()[:k], out_s.cpu().numpy()[:k]) == want.pairhash
+
+
+def test_materialize_capped_output_keeps_exact_count(gj, orc, eng, torch_cuda):
+    """The reference's ring overwrites itself (join-primitives.cu:1097-1099); here pairs beyond
+    `cap` are counted but not written, and nothing is written past the buffer."""
+    reset(eng)
+    rng = np.random.default_rng(21)
+    nR, nS = 50_000, 80_000
+    Rk, Sk = rnd(rng, nR, 0, 5000), rnd(rng, nS, 0, 5000)
+    Rp, Sp = rnd(rng, nR, 1, 100), rnd(rng, nS, 1, 100)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    cap = 10_000
+    guard = 4096
+    out_r = torch_cuda.zeros(cap + guard, dtype=torch_cuda.int32, device="cuda")
+    out_s = torch_cuda.zeros(cap + guard, dtype=torch_cuda.int32, device="cuda")
+    n, res = eng.join_materialize(*dev(torch_cuda, Rk, Rp, Sk, Sp), out_r[:cap], out_s[:cap])
+    assert n == want.matches > cap and res.checksum == want.checksum
+    assert int((out_r[:cap] > 0).sum()) == cap and int(out_r[cap:].abs().sum()) == 0
+    assert int(out_s[cap:].abs().sum()) == 0
+
+
+# ------------------------------------------------------------------------------- multi-GPU step
+@pytest.mark.parametrize("G", [1, 2, 8])
+def test_virtual_shards_on_one_gpu(gj, orc, eng, torch_cuda, G):
+    """the shuffle logic with G virtual shards on one GPU -- split both
+    relations by destination, join every destination's tuples with gpu_bits set, add up."""
+    reset(eng)
+    rng = np.random.default_rng(G)
+    nR, nS = 700_000, 1_300_000
+    Rk, Sk = rnd(rng, nR, 0, 1 << 20), rnd(rng, nS, 0, 1 << 20)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    B = gj.distributed.choose_radix_bits(nR // G)
+    gbits = G.bit_length() - 1
+    dRk, dRp, dSk, dSp = dev(torch_cuda, Rk, Rp, Sk, Sp)
+    outR = torch_cuda.empty(nR, dtype=torch_cuda.int64, device="cuda")
+    outS = torch_cuda.empty(nS, dtype=torch_cuda.int64, device="cuda")
+    cR = eng.shuffle_split(dRk, dRp, G, B, outR)
+    cS = eng.shuffle_split(dSk, dSp, G, B, outS)
+    assert np.array_equal(cR, np.bincount((Rk.view(np.uint32) >> B) & (G - 1), minlength=G))
+    assert np.array_equal(cS, eng.shuffle_count(dSk, G, B))
+    eng.set_option("radix_bits", B)
+    eng.set_option("gpu_bits", gbits)
+    oR = np.concatenate(([0], np.cumsum(cR)))
+    oS = np.concatenate(([0], np.cumsum(cS)))
+    m = c = 0
+    for g in range(G):
+        grp = outR[oR[g]:oR[g + 1]].cpu().numpy().view(np.uint32).reshape(-1, 2)
+        assert np.all(((grp[:, 0] >> B) & (G - 1)) == g)
+        r = eng.join_aggregate_tuples(outR[oR[g]:], int(cR[g]), outS[oS[g]:], int(cS[g]))
+        m += r.matches
+        c = (c + r.checksum) % 2**64
+    assert (m, c) == (want.matches, want.checksum)
+    reset(eng)
+
+
+def test_peer_store_scatter_into_local_buffers(gj, orc, eng, torch_cuda):
+    """gj_shuffle_scatter_peers with every 'peer' being a local buffer: same kernel, same
+    per-destination pointer table as over NVLink."""
+    reset(eng)
+    rng = np.random.default_rng(31)
+    n, G, shift = 900_000, 4, 12
+    k, p = rnd(rng, n, 0, 1 << 20), rnd(rng, n, -2**31, 2**31)
+    dk, dp = dev(torch_cuda, k, p)
+    cnt = eng.shuffle_count(dk, G, shift)
+    pad = 1000
+    bufs = [torch_cuda.zeros(int(cnt[g]) + pad, dtype=torch_cuda.int64, device="cuda") for g in range(G)]
+    eng.shuffle_scatter_peers(dk, dp, G, shift, [b.data_ptr() for b in bufs], [pad // 2] * G)
+    c_all, h_all = orc.partition_fingerprint(k, p, shift, 2)
+    for g in range(G):
+        got = bufs[g].cpu().numpy()
+        assert not got[: pad // 2].any() and not got[pad // 2 + int(cnt[g]):].any()
+        t = got[pad // 2: pad // 2 + int(cnt[g])].view(np.int32).reshape(-1, 2)
+        c, h = orc.partition_fingerprint(np.ascontiguousarray(t[:, 0]), np.ascontiguousarray(t[:, 1]), shift, 2)
+        assert c[g] == cnt[g] == c_all[g] and h[g] == h_all[g] and c.sum() == c[g]
+
+
+# ------------------------------------------------------------------------------- device generator
+def test_device_generator_is_the_host_bijection(gj, orc, eng, torch_cuda):
+    n = 1_000_003
+    k = torch_cuda.empty(n, dtype=torch_cuda.int32, device="cuda")
+    p = torch_cuda.empty(n, dtype=torch_cuda.int32, device="cuda")
+    eng.generate_unique(k, p, 0, n, 5, 9)
+    hk, hp = k.cpu().numpy(), p.cpu().numpy()
+    assert np.array_equal(np.sort(hk), np.arange(n))
+    for row in (0, 1, 77, n - 1):
+        assert hk[row] == gj.bijection(row, n, 5)
+        assert hp[row] == gj.payload_of_key(int(hk[row]), 9)
+    # sharded generation == whole generation
+    k2 = torch_cuda.empty(1000, dtype=torch_cuda.int32, device="cuda")
+    p2 = torch_cuda.empty(1000, dtype=torch_cuda.int32, device="cuda")
+    eng.generate_unique(k2, p2, 5000, n, 5, 9)
+    assert np.array_equal(k2.cpu().numpy(), hk[5000:6000]) and np.array_equal(p2.cpu().numpy(), hp[5000:6000])
+    # oracle restates the payload function independently
+    assert np.array_equal(orc.payload_of_keys(hk[:4096], 9), hp[:4096])
+
+
+def test_error_behaviour(gj, eng, torch_cuda):
+    """Errors come back as codes + message, never exit() (reference: common.h:132-141)."""
+    big = torch_cuda.zeros((1 << 22) + 1, dtype=torch_cuda.int32, device="cuda")
+    small = torch_cuda.zeros(4, dtype=torch_cuda.int32, device="cuda")
+    with pytest.raises(gj.GJError) as ei:
+        eng.join_aggregate(big, big, small, small)
+    assert ei.value.code == -1 and "capacity" in str(ei.value)
+    with pytest.raises(gj.GJError):
+        eng.set_option("no_such_option", 1)
+    with pytest.raises(gj.GJError):
+        eng.set_option("radix_bits", 16)
+    with pytest.raises(gj.GJError):
+        gj.JoinEngine(16, 16, device=99)
