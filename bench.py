@@ -241,7 +241,8 @@ def reference_arm(args):
     line = base_line(args, w, args.gpus)
     cb = dict(cb, value=v)
     cb.pop("seconds", None)
-    line.update({"impl": "reference", "value": v, "ms_per_step": None, "cpu_baseline": cb,
+    sample_tuples = sum(int(x) for x in re.findall(r"\|[RS]\|=(\d+)", cb["sample"]))
+    line.update({"impl": "reference", "value": v, "ms_per_step": sample_tuples / v * 1e3, "cpu_baseline": cb,
                  "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0,
                  "note": "the reference has no CPU join (its joinCpu is dead code, hash_join_clustered_probe.cu:2013-2059); "
