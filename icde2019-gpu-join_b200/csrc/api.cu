@@ -48,27 +48,42 @@ static int fail(int code, const char* fmt, ...) {
 // kernel variant tables
 // ------------------------------------------------------------------------------------------
 typedef void (*scatter_fn)(ScatterArgs);
-struct ScatterCfg { int threads, ipt, mode; scatter_fn col, packed; };
-#define GJ_SC(T, I, M) { T, I, M, scatter_kernel<T, I, M, true>, scatter_kernel<T, I, M, false> }
+struct ScatterCfg { int threads, ipt, mode, out; scatter_fn col, packed; };
+#define GJ_SC(T, I, M, O, B) { T, I, M, O, scatter_kernel<T, I, M, O, true, B>, scatter_kernel<T, I, M, O, false, B> }
 static const ScatterCfg kScatter[] = {
-    GJ_SC(256, 16, 0), GJ_SC(512, 16, 0), GJ_SC(256, 16, 1), GJ_SC(512, 16, 1),
-    GJ_SC(512, 8, 0),  GJ_SC(1024, 8, 0), GJ_SC(1024, 8, 1), GJ_SC(512, 8, 1),
-    GJ_SC(256, 8, 0),  GJ_SC(256, 8, 1),
+    GJ_SC(256, 16, 1, 0, 4),   // 0 default: two shared atomics, 8-byte stores, 4 CTAs/SM
+    GJ_SC(256, 16, 0, 0, 3),   // 1 rank registers
+    GJ_SC(256, 16, 0, 0, 4),   // 2 rank registers squeezed to 64 registers
+    GJ_SC(512, 16, 1, 0, 2),   // 3
+    GJ_SC(256, 16, 1, 1, 4),   // 4 TMA bulk-copy output
+    GJ_SC(256, 16, 0, 1, 3),   // 5
+    GJ_SC(512, 16, 1, 1, 2),   // 6
+    GJ_SC(256, 8, 1, 0, 6),    // 7
+    GJ_SC(512, 8, 1, 0, 3),    // 8
+    GJ_SC(1024, 8, 1, 0, 1),   // 9
+    GJ_SC(256, 16, 1, 0, 5),   // 10
+    GJ_SC(512, 16, 1, 1, 1),   // 11
 };
 static const int kNumScatter = (int)(sizeof(kScatter) / sizeof(kScatter[0]));
+static size_t scatter_smem(const ScatterCfg& c) {
+    return ((size_t)c.threads * c.ipt + (c.out ? 2 * NB_MAX : 0)) * sizeof(tup_t);
+}
 
 typedef void (*join_fn)(JoinArgs);
-struct JoinCfg { int threads, cap; join_fn agg, mat; };
-#define GJ_JC(T, C) { T, C, join_kernel<T, C, false>, join_kernel<T, C, true> }
+struct JoinCfg { int threads, cap, u; join_fn agg, mat; size_t smem_agg, smem_mat; };
+// aggregate variant with SA stages, materialising variant with SM stages (needs 16 KB of pair staging)
+#define GJ_JC(T, C, U, SA, SM) { T, C, U, join_kernel<T, C, U, SA, false>, join_kernel<T, C, U, SM, true>, \
+                                 JoinSmem<C, U, SA, false>::total, JoinSmem<C, U, SM, true>::total }
 static const JoinCfg kJoin[] = {
-    GJ_JC(512, 8192), GJ_JC(256, 8192), GJ_JC(256, 4096), GJ_JC(512, 4096), GJ_JC(1024, 8192),
-    GJ_JC(128, 4096), GJ_JC(128, 2048), GJ_JC(256, 2048),
+    GJ_JC(1024, 4096, 4096, 3, 2),   // 0 default
+    GJ_JC(512, 4096, 4096, 3, 2),    // 1
+    GJ_JC(1024, 4096, 2048, 4, 3),   // 2
+    GJ_JC(1024, 8192, 2048, 2, 1),   // 3 big build partitions (radix bits capped)
+    GJ_JC(1024, 4096, 4096, 2, 2),   // 4
+    GJ_JC(1024, 2048, 2048, 5, 4),   // 5
+    GJ_JC(768, 4096, 4096, 3, 2),    // 6
 };
 static const int kNumJoin = (int)(sizeof(kJoin) / sizeof(kJoin[0]));
-
-static size_t join_smem(const JoinCfg& c, bool mat) {
-    return (size_t)c.cap * (sizeof(tup_t) + 4 + 2) + (mat ? (size_t)JOIN_STAGE * 8 : 0);
-}
 
 // ------------------------------------------------------------------------------------------
 // context
@@ -80,7 +95,8 @@ struct RelMeta {
     uint32_t* off;               // 2^15 + 1
     uint32_t* cur1;              // 256
     uint32_t* cur2;              // 2^15
-    uint32_t* tile_prefix;       // 257
+    uint4* tiles;                // pass-2 tile descriptors
+    uint32_t* num_tiles;         // (zeroed per call)
 };
 
 constexpr uint32_t FINE_MAX = 1u << MAX_RADIX_BITS;
@@ -98,9 +114,11 @@ struct gj_ctx {
     unsigned char* meta_block = nullptr;
     RelMeta meta[2];
     uint4* units = nullptr;
-    uint64_t units_cap = 0;
-    uint32_t* num_units = nullptr;
-    uint32_t* unit_ticket = nullptr;
+    uint64_t units_cap = 0, tiles_cap = 0;
+    uint32_t* unit_base = nullptr;            // 2^15 + 1, unit_base[nb] = number of units
+    unsigned long long* unit_desc = nullptr;  // scan descriptors of the unit sequence (zeroed)
+    uint32_t* unit_ticket = nullptr;          // scan ticket of the unit sequence (zeroed)
+    uint4* tiles_block = nullptr;
     unsigned long long* result = nullptr;
     unsigned long long* h_result = nullptr;   // pinned
     tup_t** d_dst_bases = nullptr;            // 256 pointers (shuffle)
@@ -131,13 +149,13 @@ static int set_func_attrs(gj_ctx* ctx) {
     CK(cudaFuncSetAttribute(hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << MAX_RADIX_BITS));
     CK(cudaFuncSetAttribute(hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << MAX_RADIX_BITS));
     for (int i = 0; i < kNumScatter; ++i) {
-        const int bytes = kScatter[i].threads * kScatter[i].ipt * (int)sizeof(tup_t);
+        const int bytes = (int)scatter_smem(kScatter[i]);
         CK(cudaFuncSetAttribute(kScatter[i].col, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         CK(cudaFuncSetAttribute(kScatter[i].packed, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
     for (int i = 0; i < kNumJoin; ++i) {
-        CK(cudaFuncSetAttribute(kJoin[i].agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem(kJoin[i], false)));
-        CK(cudaFuncSetAttribute(kJoin[i].mat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)join_smem(kJoin[i], true)));
+        CK(cudaFuncSetAttribute(kJoin[i].agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_agg));
+        CK(cudaFuncSetAttribute(kJoin[i].mat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_mat));
     }
     ctx->attrs_set = true;
     return GJ_OK;
@@ -153,7 +171,7 @@ extern "C" void gj_destroy(gj_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->out[0]); cudaFree(ctx->out[1]); cudaFree(ctx->scratch);
     cudaFree(ctx->zero_block); cudaFree(ctx->meta_block); cudaFree(ctx->units);
-    cudaFree(ctx->d_dst_bases); cudaFree(ctx->flush_buf);
+    cudaFree(ctx->d_dst_bases); cudaFree(ctx->flush_buf); cudaFree(ctx->tiles_block);
     for (int i = 0; i < 4; ++i) cudaFree(ctx->d_in[i]);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -186,16 +204,17 @@ static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) 
     for (auto& e : ctx->cev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
     const uint64_t mx = std::max(ctx->maxR, ctx->maxS);
-    if (cudaMalloc(&ctx->out[0], ctx->maxR * sizeof(tup_t)) != cudaSuccess ||
-        cudaMalloc(&ctx->out[1], ctx->maxS * sizeof(tup_t)) != cudaSuccess ||
-        cudaMalloc(&ctx->scratch, mx * sizeof(tup_t)) != cudaSuccess) {
+    // +16 tuples of slack: bulk copies and 16-byte loads round ranges out to tuple pairs
+    if (cudaMalloc(&ctx->out[0], (ctx->maxR + 16) * sizeof(tup_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->out[1], (ctx->maxS + 16) * sizeof(tup_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->scratch, (mx + 16) * sizeof(tup_t)) != cudaSuccess) {
         cudaGetLastError();
         return fail(GJ_ERR_NOMEM, "cudaMalloc of %.2f GB partition buffers failed", (ctx->maxR + ctx->maxS + mx) * 8e-9);
     }
     // zeroed-per-call block: ghist x2 | desc x2 | tickets + counters | result
     size_t zb = 0;
     const size_t o_hist = zb;   zb += 2 * FINE_MAX * sizeof(uint32_t);
-    const size_t o_desc = zb;   zb += 2 * SCAN_TILES_MAX * sizeof(unsigned long long);
+    const size_t o_desc = zb;   zb += 3 * SCAN_TILES_MAX * sizeof(unsigned long long);
     const size_t o_cnt = zb;    zb += 16 * sizeof(uint32_t);
     const size_t o_res = zb;    zb += 4 * sizeof(unsigned long long);
     ctx->zero_bytes = zb;
@@ -205,8 +224,11 @@ static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) 
     const size_t o_off = mb;    mb += 2 * (FINE_MAX + 4) * sizeof(uint32_t);
     const size_t o_cur1 = mb;   mb += 2 * NB_MAX * sizeof(uint32_t);
     const size_t o_cur2 = mb;   mb += 2 * FINE_MAX * sizeof(uint32_t);
-    const size_t o_tp = mb;     mb += 2 * (NB_MAX + 4) * sizeof(uint32_t);
+    const size_t o_ub = mb;     mb += (FINE_MAX + 4) * sizeof(uint32_t);
     CK(cudaMalloc(&ctx->meta_block, mb));
+    // pass-2 tile descriptors: smallest tile is 2048 tuples, one extra tile per first-pass partition
+    ctx->tiles_cap = mx / 2048 + NB_MAX + 16;
+    CK(cudaMalloc(&ctx->tiles_block, 2 * ctx->tiles_cap * sizeof(uint4)));
     for (int r = 0; r < 2; ++r) {
         RelMeta& m = ctx->meta[r];
         m.ghist = reinterpret_cast<uint32_t*>(ctx->zero_block + o_hist) + (size_t)r * FINE_MAX;
@@ -215,10 +237,12 @@ static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) 
         m.off = reinterpret_cast<uint32_t*>(ctx->meta_block + o_off) + (size_t)r * (FINE_MAX + 4);
         m.cur1 = reinterpret_cast<uint32_t*>(ctx->meta_block + o_cur1) + (size_t)r * NB_MAX;
         m.cur2 = reinterpret_cast<uint32_t*>(ctx->meta_block + o_cur2) + (size_t)r * FINE_MAX;
-        m.tile_prefix = reinterpret_cast<uint32_t*>(ctx->meta_block + o_tp) + (size_t)r * (NB_MAX + 4);
+        m.tiles = ctx->tiles_block + (size_t)r * ctx->tiles_cap;
+        m.num_tiles = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + 8 + r;
     }
     ctx->unit_ticket = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + 4;
-    ctx->num_units = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + 5;
+    ctx->unit_desc = reinterpret_cast<unsigned long long*>(ctx->zero_block + o_desc) + (size_t)2 * SCAN_TILES_MAX;
+    ctx->unit_base = reinterpret_cast<uint32_t*>(ctx->meta_block + o_ub);
     ctx->result = reinterpret_cast<unsigned long long*>(ctx->zero_block + o_res);
     // unit list: probe side cut every >= 1024 tuples, plus one per partition
     ctx->units_cap = mx / 1024 + FINE_MAX + 16;
@@ -337,33 +361,37 @@ static int enqueue_hist(gj_ctx* ctx, cudaStream_t s, const void* in, bool packed
     return GJ_OK;
 }
 
-static int enqueue_scan(gj_ctx* ctx, cudaStream_t s, uint32_t nrel, uint32_t nb) {
+static uint32_t unit_tuples(const gj_ctx* ctx) { return ctx->opt_unit ? (uint32_t)ctx->opt_unit : 8192u; }
+
+// scan of the fine histogram(s) of roles [first, first+nrel) and, for a join, of the unit counts
+static int enqueue_scan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, uint32_t nb, bool with_units) {
     ScanArgs a;
     for (uint32_t r = 0; r < 2; ++r) {
-        const RelMeta& m = ctx->meta[r < nrel ? r : 0];
-        a.rel[r].in = m.ghist; a.rel[r].out = m.off; a.rel[r].desc = m.desc; a.rel[r].ticket = m.ticket;
+        const RelMeta& m = ctx->meta[r < nrel ? first + (int)r : first];
+        a.seq[r].in = m.ghist; a.seq[r].out = m.off; a.seq[r].desc = m.desc; a.seq[r].ticket = m.ticket;
     }
-    a.nb = nb;
-    dim3 grid((nb + SCAN_TILE - 1) / SCAN_TILE, nrel);
+    a.seq[2].in = nullptr; a.seq[2].out = ctx->unit_base; a.seq[2].desc = ctx->unit_desc; a.seq[2].ticket = ctx->unit_ticket;
+    a.nb = nb; a.unit = unit_tuples(ctx);
+    dim3 grid((nb + SCAN_TILE - 1) / SCAN_TILE, with_units ? 3 : nrel);
     scan_lookback_kernel<<<grid, SCAN_THREADS, 0, s>>>(a);
     LAUNCHED();
     return GJ_OK;
 }
 
-static uint32_t unit_tuples(const gj_ctx* ctx) { return ctx->opt_unit ? (uint32_t)ctx->opt_unit : 16384u; }
-
-static int enqueue_plan(gj_ctx* ctx, cudaStream_t s, uint32_t nrel, const Plan& pl) {
+static int enqueue_plan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, const Plan& pl, bool with_units) {
     PlanArgs a;
     for (uint32_t r = 0; r < 2; ++r) {
-        const RelMeta& m = ctx->meta[r < nrel ? r : 0];
-        a.rel[r].off = m.off; a.rel[r].cur1 = m.cur1; a.rel[r].cur2 = m.cur2; a.rel[r].tile_prefix = m.tile_prefix;
+        const RelMeta& m = ctx->meta[r < nrel ? first + (int)r : first];
+        a.rel[r].off = m.off; a.rel[r].cur1 = m.cur1; a.rel[r].cur2 = m.cur2; a.rel[r].tiles = m.tiles; a.rel[r].num_tiles = m.num_tiles;
     }
-    a.nrel = nrel; a.b1 = pl.b1; a.b2 = pl.b2;
+    a.nrel = with_units ? 2 : nrel; a.b1 = pl.b1; a.b2 = pl.b2;
     const ScatterCfg& c2 = kScatter[ctx->opt_scatter_cfg2];
     a.tile = (uint32_t)(c2.threads * c2.ipt);
     a.unit = unit_tuples(ctx);
-    a.units = ctx->units; a.num_units = ctx->num_units;
-    plan_kernel<<<1, PLAN_THREADS, 0, s>>>(a);
+    a.unit_base = ctx->unit_base; a.units = ctx->units;
+    const uint32_t nb = 1u << pl.B;
+    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(128, (nb + PLAN_THREADS - 1) / PLAN_THREADS + (pl.b2 ? 32 : 0)));
+    plan_kernel<<<grid, PLAN_THREADS, 0, s>>>(a);
     LAUNCHED();
     return GJ_OK;
 }
@@ -383,7 +411,7 @@ static int enqueue_scatter(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role
     a.cursors = pl.b2 ? m.cur1 : m.cur2;
     const uint32_t grid1 = (uint32_t)((rel.n + T1 - 1) / T1);
     CK(cudaEventRecord(ctx->pev[role][0], s));
-    (rel.tup ? c1.packed : c1.col)<<<grid1, c1.threads, (size_t)T1 * sizeof(tup_t), s>>>(a);
+    (rel.tup ? c1.packed : c1.col)<<<grid1, c1.threads, scatter_smem(c1), s>>>(a);
     LAUNCHED();
     CK(cudaEventRecord(ctx->pev[role][1], s));
     if (pl.b2) {
@@ -393,9 +421,9 @@ static int enqueue_scatter(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role
         memset(&b, 0, sizeof(b));
         b.in_tup = ctx->scratch; b.out = dst; b.n = (uint32_t)rel.n;
         b.shift = 0; b.bits = pl.b2;
-        b.cursors = m.cur2; b.tile_prefix = m.tile_prefix; b.parent_off = m.off; b.nparent_bits = pl.b1;
-        const uint32_t grid2 = (uint32_t)(rel.n / T2) + (1u << pl.b1);   // upper bound on tiles
-        c2.packed<<<grid2, c2.threads, (size_t)T2 * sizeof(tup_t), s>>>(b);
+        b.cursors = m.cur2; b.tiles = m.tiles; b.num_tiles = m.num_tiles;
+        const uint32_t grid2 = (uint32_t)(rel.n / T2) + (1u << pl.b1) + 2;   // upper bound on tiles
+        c2.packed<<<grid2, c2.threads, scatter_smem(c2), s>>>(b);
         LAUNCHED();
         CK(cudaEventRecord(ctx->pev[role][2], s));
     }
@@ -413,19 +441,18 @@ static int fill_pass_times(gj_ctx* ctx, gj_timings* t, const Plan& pl, int nrole
 }
 
 static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup_t* prb, const Plan& pl,
-                        uint64_t n_prb, bool mat, int32_t* out_b, int32_t* out_p, uint64_t cap) {
-    const JoinCfg& jc = kJoin[ctx->opt_join_cfg];
+                        uint64_t n_bld, uint64_t n_prb, bool mat, int32_t* out_b, int32_t* out_p, uint64_t cap) {
+    int cfg = (int)ctx->opt_join_cfg;
+    if (cfg == 0 && (n_bld >> pl.B) > 4096) cfg = 3;   // radix bits capped: 8192-tuple build chunks
+    const JoinCfg& jc = kJoin[cfg];
     JoinArgs a;
-    a.bld = bld; a.off_bld = ctx->meta[0].off; a.prb = prb; a.off_prb = ctx->meta[1].off;
-    a.units = ctx->units; a.num_units = ctx->num_units; a.ticket = ctx->unit_ticket;
+    a.bld = bld; a.prb = prb;
+    a.units = ctx->units; a.num_units = ctx->unit_base + (1u << pl.B);
     a.hash_shift = pl.B + (uint32_t)ctx->opt_gpu_bits;
     a.result = ctx->result;
     a.out_bld_pay = out_b; a.out_prb_pay = out_p; a.cap = cap;
-    const size_t smem = join_smem(jc, mat);
-    int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mat ? jc.mat : jc.agg, jc.threads, smem));
-    occ = std::max(occ, 1);
-    uint64_t grid = (uint64_t)ctx->sm_count * occ;
+    const size_t smem = mat ? jc.smem_mat : jc.smem_agg;
+    uint64_t grid = (uint64_t)ctx->sm_count;   // persistent: one CTA per SM owns the whole shared memory
     if (ctx->opt_join_grid) grid = (uint64_t)ctx->opt_join_grid;
     const uint64_t max_units = n_prb / unit_tuples(ctx) + (1ull << pl.B);
     grid = std::max<uint64_t>(1, std::min(grid, max_units));
@@ -472,13 +499,13 @@ static int run_join(gj_ctx* ctx, Rel R, Rel S, bool mat, int32_t* out_Rp, int32_
     int rc;
     if ((rc = enqueue_hist(ctx, s, bld.tup ? (const void*)bld.tup : (const void*)bld.keys, bld.tup != nullptr, bld.n, 0, pl.B, ctx->meta[0].ghist))) return rc;
     if ((rc = enqueue_hist(ctx, s, prb.tup ? (const void*)prb.tup : (const void*)prb.keys, prb.tup != nullptr, prb.n, 0, pl.B, ctx->meta[1].ghist))) return rc;
-    if ((rc = enqueue_scan(ctx, s, 2, 1u << pl.B))) return rc;
-    if ((rc = enqueue_plan(ctx, s, 2, pl))) return rc;
+    if ((rc = enqueue_scan(ctx, s, 0, 2, 1u << pl.B, true))) return rc;
+    if ((rc = enqueue_plan(ctx, s, 0, 2, pl, true))) return rc;
     CK(cudaEventRecord(ctx->ev[1], s));
     if ((rc = enqueue_scatter(ctx, s, bld, 0, pl, ctx->out[bld.slot]))) return rc;
     if ((rc = enqueue_scatter(ctx, s, prb, 1, pl, ctx->out[prb.slot]))) return rc;
     CK(cudaEventRecord(ctx->ev[2], s));
-    if ((rc = enqueue_join(ctx, s, ctx->out[bld.slot], ctx->out[prb.slot], pl, prb.n, mat,
+    if ((rc = enqueue_join(ctx, s, ctx->out[bld.slot], ctx->out[prb.slot], pl, bld.n, prb.n, mat,
                            swap ? out_Sp : out_Rp, swap ? out_Rp : out_Sp, cap))) return rc;
     CK(cudaEventRecord(ctx->ev[3], s));
     CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -602,8 +629,8 @@ extern "C" int gj_join_aggregate_host(gj_ctx* ctx, const int32_t* h_Rk, const in
         CK(cudaEventRecord(pay_ev[r], c));
     }
     CK(cudaEventRecord(ctx->ev[4], c));   // end of all H2D traffic
-    if ((rc = enqueue_scan(ctx, s, 2, 1u << pl.B))) return rc;
-    if ((rc = enqueue_plan(ctx, s, 2, pl))) return rc;
+    if ((rc = enqueue_scan(ctx, s, 0, 2, 1u << pl.B, true))) return rc;
+    if ((rc = enqueue_plan(ctx, s, 0, 2, pl, true))) return rc;
     CK(cudaEventRecord(ctx->ev[1], s));
     for (int r = 0; r < 2; ++r) {
         Rel rel;
@@ -612,7 +639,7 @@ extern "C" int gj_join_aggregate_host(gj_ctx* ctx, const int32_t* h_Rk, const in
         if ((rc = enqueue_scatter(ctx, s, rel, r, pl, ctx->out[slot[r]]))) return rc;
     }
     CK(cudaEventRecord(ctx->ev[2], s));
-    if ((rc = enqueue_join(ctx, s, ctx->out[slot[0]], ctx->out[slot[1]], pl, nn[1], false, nullptr, nullptr, 0))) return rc;
+    if ((rc = enqueue_join(ctx, s, ctx->out[slot[0]], ctx->out[slot[1]], pl, nn[0], nn[1], false, nullptr, nullptr, 0))) return rc;
     CK(cudaEventRecord(ctx->ev[3], s));
     CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -657,23 +684,8 @@ extern "C" int gj_partition(gj_ctx* ctx, int slot, const int32_t* d_keys, const 
     CK(cudaEventRecord(ctx->ev[0], s));
     int rc;
     if ((rc = enqueue_hist(ctx, s, d_keys, false, n, 0, pl.B, ctx->meta[slot].ghist))) return rc;
-    {   // scan + plan of this one relation only (role = slot)
-        ScanArgs a;
-        const RelMeta& m = ctx->meta[slot];
-        for (int r = 0; r < 2; ++r) { a.rel[r].in = m.ghist; a.rel[r].out = m.off; a.rel[r].desc = m.desc; a.rel[r].ticket = m.ticket; }
-        a.nb = 1u << pl.B;
-        dim3 grid((a.nb + SCAN_TILE - 1) / SCAN_TILE, 1);
-        scan_lookback_kernel<<<grid, SCAN_THREADS, 0, s>>>(a);
-        LAUNCHED();
-        PlanArgs p;
-        for (int r = 0; r < 2; ++r) { p.rel[r].off = m.off; p.rel[r].cur1 = m.cur1; p.rel[r].cur2 = m.cur2; p.rel[r].tile_prefix = m.tile_prefix; }
-        p.nrel = 1; p.b1 = pl.b1; p.b2 = pl.b2;
-        const ScatterCfg& c2 = kScatter[ctx->opt_scatter_cfg2];
-        p.tile = (uint32_t)(c2.threads * c2.ipt);
-        p.unit = unit_tuples(ctx); p.units = ctx->units; p.num_units = ctx->num_units;
-        plan_kernel<<<1, PLAN_THREADS, 0, s>>>(p);
-        LAUNCHED();
-    }
+    if ((rc = enqueue_scan(ctx, s, slot, 1, 1u << pl.B, false))) return rc;
+    if ((rc = enqueue_plan(ctx, s, slot, 1, pl, false))) return rc;
     CK(cudaEventRecord(ctx->ev[1], s));
     if ((rc = enqueue_scatter(ctx, s, rel, slot, pl, ctx->out[slot]))) return rc;
     CK(cudaEventRecord(ctx->ev[2], s));
@@ -735,8 +747,8 @@ extern "C" int gj_shuffle_split(gj_ctx* ctx, const int32_t* d_keys, const int32_
     CK(cudaMemsetAsync(ctx->zero_block, 0, ctx->zero_bytes, s));
     if ((rc = enqueue_hist(ctx, s, d_keys, false, n, gpu_shift, bits, ctx->meta[0].ghist))) return rc;
     Plan pl; pl.B = bits; pl.b1 = bits; pl.b2 = 0;
-    if ((rc = enqueue_scan(ctx, s, 1, n_gpus))) return rc;
-    if ((rc = enqueue_plan(ctx, s, 1, pl))) return rc;
+    if ((rc = enqueue_scan(ctx, s, 0, 1, n_gpus, false))) return rc;
+    if ((rc = enqueue_plan(ctx, s, 0, 1, pl, false))) return rc;
     if (n) {
         const ScatterCfg& c1 = kScatter[ctx->opt_scatter_cfg1];
         const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
@@ -744,7 +756,7 @@ extern "C" int gj_shuffle_split(gj_ctx* ctx, const int32_t* d_keys, const int32_
         memset(&a, 0, sizeof(a));
         a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = (tup_t*)d_out_tuples;
         a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2;
-        c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, (size_t)T1 * sizeof(tup_t), s>>>(a);
+        c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, scatter_smem(c1), s>>>(a);
         LAUNCHED();
     }
     uint32_t tmp[NB_MAX];
@@ -779,7 +791,7 @@ extern "C" int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, cons
         a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = nullptr;
         a.dst_bases = ctx->d_dst_bases;
         a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2;
-        c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, (size_t)T1 * sizeof(tup_t), s>>>(a);
+        c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, scatter_smem(c1), s>>>(a);
         LAUNCHED();
     }
     CK(cudaStreamSynchronize(s));

@@ -13,7 +13,7 @@
 //   join_kernel
 //        -> decompose_chains (:843-874, probe-side splitting becomes the unit list written by
 //           plan_kernel), join_partitioned_aggregate (:885-1095) and join_partitioned_results
-//           (:1107-1416).
+//           (:1107-1416); fed by a TMA bulk-copy ring (cp.async.bulk + mbarrier).
 //
 // Data layout in HBM: inputs are columnar int32 keys / payloads (the reference's R/Pr, S/Ps);
 // between passes and into the join tuples are packed {key,payload} 8-byte pairs (tup_t) so one
@@ -117,30 +117,72 @@ hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bi
 }
 
 // ------------------------------------------------------------------------------------------
-// 2. Exclusive prefix sum of the histogram(s): single-pass chained scan with decoupled
-//    look-back.  Tile = 256 threads x 8 counters.  blockIdx.y selects the relation.
-//    Descriptor word = (status << 32) | value, status 0 = not ready, 1 = tile aggregate,
-//    2 = inclusive prefix; written and read as one 64-bit access, so no fence is needed
-//    between flag and value.  Tile ids come from an atomic ticket so a waiting tile's
-//    predecessors are always already running.
+// PTX helpers: mbarrier + bulk async copies (TMA engine, SASS UBLKCP)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes: multiple of 16, 16 B aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// 2. Exclusive prefix sums: single-pass chained scan with decoupled look-back.
+//    blockIdx.y selects the sequence: 0/1 = fine histogram of the build/probe relation -> offsets,
+//    2 = join units per partition (computed on the fly from the two histograms) -> unit bases.
+//    Tile = 256 threads x 8 values.  Descriptor word = (status << 32) | value, status 0 = not
+//    ready, 1 = tile aggregate, 2 = inclusive prefix; written and read as one 64-bit access, so
+//    no fence is needed between flag and value.  Tile ids come from an atomic ticket so a
+//    waiting tile's predecessors are always already running.
 // ------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_THREADS * SCAN_IPT;
 
-struct ScanRel {
-    const uint32_t* in;           // nb counters
-    uint32_t* out;                // nb + 1 offsets
+struct ScanSeq {
+    const uint32_t* in;           // nb values (sequences 0/1)
+    uint32_t* out;                // nb + 1 exclusive prefix sums
     unsigned long long* desc;     // one word per tile, zeroed
     uint32_t* ticket;             // zeroed
 };
 struct ScanArgs {
-    ScanRel rel[2];
+    ScanSeq seq[3];
     uint32_t nb;
+    uint32_t unit;                // probe tuples per join unit (sequence 2)
 };
+
+__device__ __forceinline__ uint32_t units_of(uint32_t n_bld, uint32_t n_prb, uint32_t unit) {
+    return (n_bld && n_prb) ? (n_prb + unit - 1) / unit : 0u;
+}
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_lookback_kernel(ScanArgs a) {
     __shared__ uint32_t s_tile, s_prefix, s_warp[SCAN_THREADS / 32];
-    const ScanRel r = a.rel[blockIdx.y];
+    const ScanSeq r = a.seq[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(r.ticket, 1u);
     __syncthreads();
@@ -150,7 +192,11 @@ scan_lookback_kernel(ScanArgs a) {
     uint32_t v[SCAN_IPT], tsum = 0;
 #pragma unroll
     for (int j = 0; j < SCAN_IPT; ++j) {
-        v[j] = (base + j < a.nb) ? r.in[base + j] : 0u;
+        v[j] = 0;
+        if (base + j < a.nb) {
+            if (blockIdx.y < 2) v[j] = r.in[base + j];
+            else v[j] = units_of(a.seq[0].in[base + j], a.seq[1].in[base + j], a.unit);
+        }
         tsum += v[j];
     }
     uint32_t incl = warp_incl_scan(tsum, lane);
@@ -205,17 +251,23 @@ scan_lookback_kernel(ScanArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// 3. Work planning (one CTA): scatter cursors, the pass-2 tile map, and the join's unit list
-//    (replaces decompose_chains, join-primitives.cu:843-874: probe partitions longer than
-//    `unit` tuples are cut into units that different CTAs join against the same build partition).
+// 3. Work planning (fully parallel): scatter cursors, pass-2 tile descriptors, and the join's
+//    unit list (replaces decompose_chains, join-primitives.cu:843-874: probe partitions longer
+//    than `unit` tuples are cut into units that different CTAs join against the same build
+//    partition).
+//    Tile descriptor {a0, lo, hi, cursor_base}: the tile covers slots [a0, a0+T) of the
+//    first-pass output, a0 EVEN (16-byte aligned tuple pairs), of which [lo, hi) belong to this
+//    tile's first-pass partition.  Unit descriptor {probe_begin, probe_end, build_begin,
+//    build_end}.
 // ------------------------------------------------------------------------------------------
-constexpr int PLAN_THREADS = 1024;
+constexpr int PLAN_THREADS = 256;
 
 struct PlanRel {
     const uint32_t* off;   // nb + 1 fine offsets
     uint32_t* cur1;        // 2^b1 cursors of the first pass (unused when single pass)
     uint32_t* cur2;        // nb cursors of the last pass
-    uint32_t* tile_prefix; // 2^b1 + 1 (pass-2 tiles per first-pass partition, exclusive scan)
+    uint4* tiles;          // pass-2 tile descriptors
+    uint32_t* num_tiles;
 };
 struct PlanArgs {
     PlanRel rel[2];        // [0] build side, [1] probe side
@@ -223,71 +275,66 @@ struct PlanArgs {
     uint32_t b1, b2;       // b2 == 0: single pass
     uint32_t tile;         // tuples per pass-2 scatter tile
     uint32_t unit;         // probe tuples per join unit
-    uint4* units;          // {partition, probe_begin, probe_end, 0}
-    uint32_t* num_units;
+    const uint32_t* unit_base;   // nb + 1 (exclusive scan of units per partition)
+    uint4* units;
 };
-
-__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t* total) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t incl = warp_incl_scan(v, lane);
-    __syncthreads();  // protect s_warp reuse
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    uint32_t woff = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < PLAN_THREADS / 32; ++w) {
-        uint32_t x = s_warp[w];
-        if (w < wid) woff += x;
-        tot += x;
-    }
-    *total = tot;
-    return incl - v + woff;
-}
 
 __global__ void __launch_bounds__(PLAN_THREADS)
 plan_kernel(PlanArgs a) {
-    __shared__ uint32_t s_warp[PLAN_THREADS / 32];
-    const uint32_t tid = threadIdx.x;
+    __shared__ uint32_t s_tp[NB_MAX + 1], s_a0[NB_MAX], s_warp[PLAN_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t gtid = blockIdx.x * PLAN_THREADS + tid, gsz = gridDim.x * PLAN_THREADS;
     const uint32_t B = a.b1 + a.b2, nb = 1u << B, n1 = 1u << a.b1;
     for (uint32_t r = 0; r < a.nrel; ++r) {
         const PlanRel R = a.rel[r];
-        for (uint32_t p = tid; p < nb; p += PLAN_THREADS) R.cur2[p] = R.off[p];
+        for (uint32_t p = gtid; p < nb; p += gsz) R.cur2[p] = R.off[p];
         if (a.b2) {
-            // first-pass partition d spans fine partitions [d << b2, (d+1) << b2)
-            uint32_t tiles = 0;
+            // every CTA recomputes the (<= 256 entry) tile prefix in shared memory
+            uint32_t lo = 0, hi = 0, a0 = 0, tiles = 0;
             if (tid < n1) {
-                const uint32_t lo = R.off[tid << a.b2], hi = R.off[(tid + 1) << a.b2];
-                R.cur1[tid] = lo;
-                tiles = (hi - lo + a.tile - 1) / a.tile;
+                lo = R.off[tid << a.b2]; hi = R.off[(tid + 1) << a.b2];
+                a0 = lo & ~1u;
+                tiles = hi > lo ? (hi - a0 + a.tile - 1) / a.tile : 0u;
+                if (blockIdx.x == 0) R.cur1[tid] = lo;
             }
-            uint32_t tot;
-            const uint32_t ex = block_excl_scan_1024(tiles, s_warp, &tot);
-            if (tid < n1) R.tile_prefix[tid] = ex;
-            if (tid == 0) R.tile_prefix[n1] = tot;
+            __syncthreads();   // previous relation's readers of s_tp are done
+            uint32_t incl = warp_incl_scan(tiles, lane);
+            if (lane == 31) s_warp[wid] = incl;
+            __syncthreads();
+            uint32_t woff = 0, tot = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < PLAN_THREADS / 32; ++w) {
+                const uint32_t x = s_warp[w];
+                if (w < wid) woff += x;
+                tot += x;
+            }
+            s_tp[tid] = incl - tiles + woff;
+            s_a0[tid] = a0;
+            if (tid == 0) s_tp[NB_MAX] = tot;
+            __syncthreads();
+            if (gtid == 0) *R.num_tiles = tot;
+            for (uint32_t t = gtid; t < tot; t += gsz) {
+                uint32_t l = 0, h = n1;   // largest parent with s_tp[parent] <= t and tiles > 0
+                while (h - l > 1) {
+                    const uint32_t m = (l + h) >> 1;
+                    if (s_tp[m] <= t) l = m; else h = m;
+                }
+                const uint32_t plo = R.off[l << a.b2], phi = R.off[(l + 1) << a.b2];
+                const uint32_t ta = s_a0[l] + (t - s_tp[l]) * a.tile;
+                R.tiles[t] = make_uint4(ta, max(ta, plo), min(ta + a.tile, phi), l << a.b2);
+            }
         }
     }
     if (a.nrel < 2) return;
-    // join units: blocked assignment, thread t owns partitions [t*per, (t+1)*per)
-    const uint32_t per = (nb + PLAN_THREADS - 1) / PLAN_THREADS;
-    const uint32_t p0 = tid * per;
     const uint32_t* offB = a.rel[0].off;
     const uint32_t* offP = a.rel[1].off;
-    uint32_t mine = 0;
-    for (uint32_t p = p0; p < p0 + per && p < nb; ++p) {
-        const uint32_t nbld = offB[p + 1] - offB[p], nprb = offP[p + 1] - offP[p];
-        if (nbld && nprb) mine += (nprb + a.unit - 1) / a.unit;
-    }
-    uint32_t tot;
-    uint32_t at = block_excl_scan_1024(mine, s_warp, &tot);
-    for (uint32_t p = p0; p < p0 + per && p < nb; ++p) {
-        const uint32_t nbld = offB[p + 1] - offB[p];
-        const uint32_t lo = offP[p], hi = offP[p + 1];
-        if (nbld && hi > lo) {
-            for (uint32_t s = lo; s < hi; s += a.unit)
-                a.units[at++] = make_uint4(p, s, min(hi, s + a.unit), 0u);
+    for (uint32_t p = gtid; p < nb; p += gsz) {
+        const uint32_t bb = offB[p], be = offB[p + 1], lo = offP[p], hi = offP[p + 1];
+        if (be > bb && hi > lo) {
+            uint32_t at = a.unit_base[p];
+            for (uint32_t s = lo; s < hi; s += a.unit) a.units[at++] = make_uint4(s, min(hi, s + a.unit), bb, be);
         }
     }
-    if (tid == 0) *a.num_units = tot;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -296,88 +343,75 @@ plan_kernel(PlanArgs a) {
 //      rank inside its digit -> block scan of the 2^bits counts + ONE global ticket per
 //      non-empty digit (atomicAdd on the partition cursor; partitioning needs no stable order,
 //      so no inter-tile dependency chain exists at all) -> tuples permuted into shared memory
-//      grouped by digit -> written out in tile order, so each digit's tuples form one
-//      contiguous run in HBM (avg run = tile/fanout tuples x 8 B).
+//      grouped by digit -> written out so each digit's tuples form one contiguous run in HBM
+//      (avg run = tile/fanout tuples x 8 B).
 //    Algorithmic bytes: 16 per tuple (8 read + 8 written).
 //    MODE 0: rank returned by the histogram atomic, kept in registers.
-//    MODE 1: count first, second shared atomic on a per-digit cursor yields the slot (no rank
-//            registers).
-//    Pass 1 (tile_prefix == nullptr): tiles cover the whole input.  Pass 2: the tile map sends
-//    each CTA to a chunk of ONE first-pass partition; cursors are the fine (2^B) cursors.
+//    MODE 1: count first, second shared atomic on a per-digit cursor yields the slot.
+//    OUT 0:  every thread stores tuples of consecutive tile slots (8-byte stores, one run per
+//            group of lanes).
+//    OUT 1:  TMA: each digit's run is laid out in shared memory with the same 16-byte phase as
+//            its destination and leaves the SM as ONE bulk async copy (cp.async.bulk, UBLKCP)
+//            issued by the thread that owns the digit; odd head/tail tuples use plain stores.
+//    Pass 1 (tiles == nullptr): tiles cover the whole input.  Pass 2: tile descriptors send each
+//    CTA to a chunk of ONE first-pass partition; cursors are the fine (2^B) cursors.
 //    With `dst_bases` the output base pointer is chosen per digit (multi-GPU: peer receive
 //    buffers mapped over NVLink) -- the all-to-all is the scatter itself.
 // ------------------------------------------------------------------------------------------
 struct ScatterArgs {
     const int32_t* in_keys;      // columnar input (COLUMNAR)
     const int32_t* in_pays;
-    const tup_t* in_tup;         // packed input (!COLUMNAR)
-    tup_t* out;                  // packed output
+    const tup_t* in_tup;         // packed input (!COLUMNAR), 16-byte aligned
+    tup_t* out;                  // packed output, 16-byte aligned
     tup_t* const* dst_bases;     // optional per-digit output bases (device array of 2^bits pointers)
     uint32_t n;
     uint32_t shift, bits;
     uint32_t* cursors;
-    const uint32_t* tile_prefix; // pass 2 only
-    const uint32_t* parent_off;  // fine offsets (pass 2 only)
-    uint32_t nparent_bits;       // b1 (pass 2 only)
+    const uint4* tiles;          // pass 2 only
+    const uint32_t* num_tiles;   // pass 2 only
 };
 
-template <int THREADS, int IPT, int MODE, bool COLUMNAR>
-__global__ void __launch_bounds__(THREADS)
+template <int THREADS, int IPT, int MODE, int OUT, bool COLUMNAR, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 scatter_kernel(ScatterArgs a) {
     constexpr uint32_t T = THREADS * IPT;
     static_assert(THREADS >= NB_MAX, "one thread per digit in the scan step");
     static_assert(IPT % 4 == 0, "vector loads");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    tup_t* tile = reinterpret_cast<tup_t*>(smem_raw);
+    tup_t* tile = reinterpret_cast<tup_t*>(smem_raw);   // T (+ 2*NB_MAX padding slots for OUT 1)
     __shared__ uint32_t s_hist[NB_MAX];
     __shared__ uint32_t s_lbase[NB_MAX];
     __shared__ tup_t* s_dst[NB_MAX];
     __shared__ uint32_t s_warp[NB_MAX / 32];
-    __shared__ uint32_t s_info[3];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t nb = 1u << a.bits, mask = nb - 1u;
 
-    if (tid == 0) {
-        uint32_t start, count, cbase;
-        if (a.tile_prefix == nullptr) {
-            const unsigned long long s = (unsigned long long)blockIdx.x * T;
-            start = (uint32_t)s;
-            count = (s < a.n) ? min(T, a.n - start) : 0u;
-            cbase = 0;
-        } else {
-            // largest parent with tile_prefix[parent] <= blockIdx.x
-            const uint32_t np = 1u << a.nparent_bits;
-            if (blockIdx.x >= a.tile_prefix[np]) {
-                start = 0; count = 0; cbase = 0;
-            } else {
-                uint32_t lo = 0, hi = np;  // invariant: tile_prefix[lo] <= t < tile_prefix[hi]
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (a.tile_prefix[mid] <= blockIdx.x) lo = mid; else hi = mid;
-                }
-                const uint32_t pbeg = a.parent_off[lo << a.bits];
-                const uint32_t pend = a.parent_off[(lo + 1) << a.bits];
-                start = pbeg + (blockIdx.x - a.tile_prefix[lo]) * T;
-                count = min(T, pend - start);
-                cbase = lo << a.bits;
-            }
-        }
-        s_info[0] = start; s_info[1] = count; s_info[2] = cbase;
+    // ---- which slots does this tile cover ----
+    uint32_t a0, lo, hi, cbase;
+    if (a.tiles == nullptr) {
+        const unsigned long long s = (unsigned long long)blockIdx.x * T;
+        a0 = (uint32_t)s; lo = a0;
+        hi = (s < a.n) ? a0 + min(T, a.n - a0) : a0;
+        cbase = 0;
+    } else {
+        if (blockIdx.x >= *a.num_tiles) return;
+        const uint4 td = __ldg(a.tiles + blockIdx.x);
+        a0 = td.x; lo = td.y; hi = td.z; cbase = td.w;
     }
+    if (hi <= lo) return;
     if (tid < NB_MAX) s_hist[tid] = 0;
     __syncthreads();
-    const uint32_t start = s_info[0], count = s_info[1], cbase = s_info[2];
-    if (count == 0) return;
+    const bool full = (lo == a0) && (hi - a0 == T);
 
-    // ---- load ----
+    // ---- load: item j of this thread is slot a0 + slot_of(j) ----
     uint32_t key[IPT], pay[IPT];
-    bool vec = false;
+    bool vec = true;
     if (COLUMNAR) {
-        vec = (count == T) && ((((size_t)(a.in_keys + start) | (size_t)(a.in_pays + start)) & 15u) == 0);
+        vec = full && ((((size_t)(a.in_keys + a0) | (size_t)(a.in_pays + a0)) & 15u) == 0);
         if (vec) {
-            const int4* kv = reinterpret_cast<const int4*>(a.in_keys + start);
-            const int4* pv = reinterpret_cast<const int4*>(a.in_pays + start);
+            const int4* kv = reinterpret_cast<const int4*>(a.in_keys + a0);
+            const int4* pv = reinterpret_cast<const int4*>(a.in_pays + a0);
 #pragma unroll
             for (int j = 0; j < IPT / 4; ++j) {
                 const int4 k = __ldg(kv + j * THREADS + tid);
@@ -391,25 +425,29 @@ scatter_kernel(ScatterArgs a) {
         } else {
 #pragma unroll
             for (int j = 0; j < IPT; ++j) {
-                const uint32_t i = j * THREADS + tid;
-                if (i < count) {
-                    key[j] = (uint32_t)__ldg(a.in_keys + start + i);
-                    pay[j] = (uint32_t)__ldg(a.in_pays + start + i);
+                const uint32_t i = a0 + j * THREADS + tid;
+                if (i >= lo && i < hi) {
+                    key[j] = (uint32_t)__ldg(a.in_keys + i);
+                    pay[j] = (uint32_t)__ldg(a.in_pays + i);
                 } else { key[j] = 0; pay[j] = 0; }
             }
         }
     } else {
+        // a0 is even and the buffer 16-byte aligned: one 16-byte load = two tuples
+        const uint4* tv = reinterpret_cast<const uint4*>(a.in_tup + a0);
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) {
-            const uint32_t i = j * THREADS + tid;
-            if (i < count) {
-                const tup_t t = __ldg(a.in_tup + start + i);
-                key[j] = t.x; pay[j] = t.y;
-            } else { key[j] = 0; pay[j] = 0; }
+        for (int j = 0; j < IPT / 2; ++j) {
+            const uint32_t pi = j * THREADS + tid;
+            uint4 t = make_uint4(0, 0, 0, 0);
+            if (a0 + 2 * pi < hi) t = __ldg(tv + pi);
+            key[2 * j] = t.x; pay[2 * j] = t.y; key[2 * j + 1] = t.z; pay[2 * j + 1] = t.w;
         }
     }
-    // item j of this thread is valid iff the tile is full (vector path) or its index < count
-#define GJ_VALID(j) (vec || ((uint32_t)(j) * THREADS + tid < count))
+    // slot index of item j inside [a0, a0+T)
+#define GJ_SLOT(j) (COLUMNAR ? (vec ? 4u * (((uint32_t)(j) >> 2) * THREADS + tid) + ((uint32_t)(j) & 3u)   \
+                                    : (uint32_t)(j) * THREADS + tid)                                       \
+                             : 2u * (((uint32_t)(j) >> 1) * THREADS + tid) + ((uint32_t)(j) & 1u))
+#define GJ_VALID(j) (full || (a0 + GJ_SLOT(j) >= lo && a0 + GJ_SLOT(j) < hi))
 
     // ---- per-tile histogram (+ rank) ----
     uint32_t rk[MODE == 0 ? IPT : 1];
@@ -424,26 +462,31 @@ scatter_kernel(ScatterArgs a) {
     __syncthreads();
 
     // ---- scan of the digit counts, global tickets ----
-    uint32_t cnt = 0, incl = 0;
+    // OUT 1 pads every digit's region to an even number of slots (+ room for a 1-slot phase
+    // shift) so that region starts are 16-byte aligned in shared memory.
+    uint32_t cnt = 0, sz = 0, incl = 0;
     if (tid < NB_MAX) {
         cnt = (tid < nb) ? s_hist[tid] : 0u;
-        incl = warp_incl_scan(cnt, lane);
+        sz = (OUT == 1) ? ((cnt + 2u) & ~1u) : cnt;
+        incl = warp_incl_scan(sz, lane);
         if (lane == 31) s_warp[wid] = incl;
     }
     __syncthreads();
+    uint32_t gb = 0, sbeg = 0;
+    tup_t* dbase = nullptr;
     if (tid < nb) {
         uint32_t woff = 0;
 #pragma unroll
         for (uint32_t w = 0; w < NB_MAX / 32; ++w)
             if (w < wid) woff += s_warp[w];
-        const uint32_t excl = incl - cnt + woff;
-        uint32_t gb = 0;
+        const uint32_t excl = incl - sz + woff;
         if (cnt) gb = atomicAdd(&a.cursors[cbase + tid], cnt);
-        tup_t* base = a.dst_bases ? a.dst_bases[tid] : a.out;
-        // slot i of the tile (i >= excl for this digit) goes to base[gb + (i - excl)]
-        s_dst[tid] = reinterpret_cast<tup_t*>(reinterpret_cast<unsigned long long>(base) +
-                                              ((long long)gb - (long long)excl) * (long long)sizeof(tup_t));
-        if (MODE == 0) s_lbase[tid] = excl; else s_hist[tid] = excl;
+        dbase = a.dst_bases ? a.dst_bases[tid] : a.out;
+        sbeg = (OUT == 1) ? excl + (gb & 1u) : excl;   // same 16-byte phase as the destination
+        // tile slot i (i >= sbeg for this digit) goes to dbase[gb + (i - sbeg)]
+        s_dst[tid] = reinterpret_cast<tup_t*>(reinterpret_cast<unsigned long long>(dbase) +
+                                              ((long long)gb - (long long)sbeg) * (long long)sizeof(tup_t));
+        if (MODE == 0) s_lbase[tid] = sbeg; else s_hist[tid] = sbeg;
     }
     __syncthreads();
 
@@ -459,162 +502,231 @@ scatter_kernel(ScatterArgs a) {
         }
     }
 #undef GJ_VALID
+#undef GJ_SLOT
+    if (OUT == 1) fence_proxy_async();   // generic-proxy writes -> visible to the bulk copy engine
     __syncthreads();
 
-    // ---- write out: consecutive threads -> consecutive slots of the same run ----
+    if (OUT == 0) {
+        // ---- write out: consecutive threads -> consecutive slots of the same run ----
+        const uint32_t count = hi - lo;
 #pragma unroll 4
-    for (uint32_t i = tid; i < count; i += THREADS) {
-        const tup_t t = tile[i];
-        const uint32_t d = (t.x >> a.shift) & mask;
-        s_dst[d][i] = t;
+        for (uint32_t i = tid; i < count; i += THREADS) {
+            const tup_t t = tile[i];
+            const uint32_t d = (t.x >> a.shift) & mask;
+            s_dst[d][i] = t;
+        }
+    } else {
+        // ---- one bulk copy per digit run ----
+        if (tid < nb && cnt) {
+            const tup_t* src = tile + sbeg;
+            tup_t* dst = dbase + gb;
+            uint32_t n = cnt;
+            if (gb & 1u) { *dst = *src; ++src; ++dst; --n; }
+            const uint32_t body = n & ~1u;
+            if (body) bulk_s2g(dst, src, body * (uint32_t)sizeof(tup_t));
+            if (n & 1u) dst[n - 1] = src[n - 1];
+            bulk_commit();
+            bulk_wait_read0();   // shared memory must stay valid until the engine has read it
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// 5. Per-partition hash join.  Persistent CTAs pull work units {partition, probe range} from a
-//    ticket.  Build: the build partition (<= CAP tuples per round) is copied into shared memory
-//    and chained into 2^hb heads with atomicExch (index-based chains: no sentinel key, N:M
-//    safe).  Hash = xor-fold of the key bits above the radix field -- the identity on dense
-//    keys (reference: identity hash, common.h:45-47), still a proper hash otherwise.
-//    Probe: 8-byte tuple loads, chain walk with full 32-bit key compare, per-thread 64-bit
-//    accumulators, one atomic per CTA at the end.  Build partitions larger than CAP are joined
-//    in CAP-sized rounds against the same probe range (the reference's block-nested branch,
-//    join-primitives.cu:929-1003).
+// 5. Per-partition hash join: persistent CTAs (one per SM), static round-robin over the unit
+//    list, and a TMA-fed shared-memory ring.
+//    A unit {probe range, build partition} is processed in steps of (build chunk <= CAP tuples)
+//    x (probe chunk <= U tuples).  One thread runs an iterator STAGES-1 steps ahead and issues
+//    two bulk async copies per step (build chunk, probe chunk) into the step's stage, completion
+//    on the stage's mbarrier -- all HBM traffic of the join is asynchronous bulk traffic, no
+//    load instructions, no register staging, latency hidden by the ring depth.
+//    Per step the CTA: waits on the stage, clears 2^hb heads, builds the chained table in place
+//    over the staged build tuples (atomicExch on the head, 16-bit next links: index chains need
+//    no sentinel key and are N:M safe), probes with the staged probe tuples (full 32-bit key
+//    compare, 64-bit per-thread accumulators), and hands the stage back to the loader.
+//    Hash = xor-fold of the key bits above the radix (+GPU) field: the identity on dense keys
+//    (the reference's choice, common.h:45-47), a real hash otherwise.
+//    Build partitions larger than CAP simply produce more steps (the reference's block-nested
+//    branch, join-primitives.cu:929-1003).
 //    MATERIALIZE: result pairs are staged per CTA in shared memory and flushed with ONE global
 //    reservation per flush as coalesced column writes; pairs beyond `cap` are counted, not
 //    written.  Algorithmic bytes: 8 per input tuple (+ 8 per result pair when materialising).
 // ------------------------------------------------------------------------------------------
 struct JoinArgs {
-    const tup_t* bld; const uint32_t* off_bld;
-    const tup_t* prb; const uint32_t* off_prb;
-    const uint4* units; const uint32_t* num_units; uint32_t* ticket;
+    const tup_t* bld; const tup_t* prb;     // partitioned tuples (16-byte aligned, +2 slack)
+    const uint4* units; const uint32_t* num_units;
     uint32_t hash_shift;
     unsigned long long* result;   // [0] matches [1] checksum [2] pairs reserved (materialise)
     int32_t* out_bld_pay; int32_t* out_prb_pay; unsigned long long cap;
 };
 
-constexpr int JOIN_STAGE = 2048;   // staged result pairs per CTA
-constexpr int JOIN_BATCH = 4;      // probe tuples per thread per round
+constexpr int JOIN_STAGE_PAIRS = 2048;   // staged result pairs per CTA (materialise)
+constexpr uint32_t STEP_DONE = 0xFFFFFFFFu;
 
-template <int THREADS, int CAP, bool MATERIALIZE>
-__global__ void __launch_bounds__(THREADS)
+template <int CAP, int U, int STAGES, bool MATERIALIZE>
+struct JoinSmem {
+    static constexpr size_t stage_bytes = (size_t)(CAP + 2 + U + 2) * sizeof(tup_t);
+    static constexpr size_t off_head = stage_bytes * STAGES;
+    static constexpr size_t off_next = off_head + (size_t)CAP * 4;
+    static constexpr size_t off_out = off_next + (size_t)CAP * 2;
+    static constexpr size_t off_hdr = off_out + (MATERIALIZE ? (size_t)JOIN_STAGE_PAIRS * 8 : 0);
+    static constexpr size_t off_bar = off_hdr + (size_t)STAGES * 16;
+    static constexpr size_t total = off_bar + (size_t)STAGES * 8;
+};
+
+template <int THREADS, int CAP, int U, int STAGES, bool MATERIALIZE>
+__global__ void __launch_bounds__(THREADS, 1)
 join_kernel(JoinArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    tup_t* s_tup = reinterpret_cast<tup_t*>(smem_raw);                       // CAP
-    uint32_t* s_head = reinterpret_cast<uint32_t*>(s_tup + CAP);             // CAP
-    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_head + CAP);            // CAP
-    int32_t* s_stage_b = reinterpret_cast<int32_t*>(s_next + CAP);           // JOIN_STAGE (mat.)
-    int32_t* s_stage_p = s_stage_b + JOIN_STAGE;                             // JOIN_STAGE (mat.)
-    __shared__ uint32_t s_unit, s_cnt;
+    using L = JoinSmem<CAP, U, STAGES, MATERIALIZE>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* s_head = reinterpret_cast<uint32_t*>(smem_raw + L::off_head);
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(smem_raw + L::off_next);
+    int32_t* s_out_b = reinterpret_cast<int32_t*>(smem_raw + L::off_out);
+    int32_t* s_out_p = s_out_b + JOIN_STAGE_PAIRS;
+    uint4* s_hdr = reinterpret_cast<uint4*>(smem_raw + L::off_hdr);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);
+    __shared__ uint32_t s_cnt;
     __shared__ unsigned long long s_base;
     __shared__ unsigned long long s_red[2][THREADS / 32];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t nunits = *a.num_units;
     unsigned long long matches = 0, sum = 0;
-    uint32_t built_p = EMPTY32;   // partition whose (single-round) table is currently in smem
-    if (MATERIALIZE) { if (tid == 0) s_cnt = 0; }
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_unit = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint32_t u = s_unit;
-        if (u >= nunits) break;
-        const uint4 ud = a.units[u];
-        const uint32_t p = ud.x, pb = ud.y, pe = ud.z;
-        const uint32_t bb = a.off_bld[p], be = a.off_bld[p + 1];
-        const bool single = (be - bb) <= (uint32_t)CAP;
-
-        for (uint32_t rc = bb; rc < be; rc += CAP) {
-            const uint32_t nr = min((uint32_t)CAP, be - rc);
-            uint32_t hb = 32u - __clz(max(nr, 32u) - 1u);   // ceil(log2(nr)), >= 5
-            const uint32_t H = 1u << hb, hmask = H - 1u;
-            if (!(single && built_p == p)) {
-                if (rc != bb) __syncthreads();   // previous round's probes are done with the table
-                for (uint32_t i = tid; i < H / 4; i += THREADS)
-                    reinterpret_cast<uint4*>(s_head)[i] = make_uint4(EMPTY32, EMPTY32, EMPTY32, EMPTY32);
-                __syncthreads();
-                for (uint32_t i = tid; i < nr; i += THREADS) {
-                    const tup_t t = __ldg(a.bld + rc + i);
-                    s_tup[i] = t;
-                    const uint32_t k = t.x >> a.hash_shift;
-                    const uint32_t h = (k ^ (k >> hb)) & hmask;
-                    s_next[i] = (uint16_t)atomicExch(&s_head[h], i);
-                }
-                __syncthreads();
-                built_p = single ? p : EMPTY32;
+    // ---- loader state (thread 0 only): iterator over (unit, build chunk, probe chunk) ----
+    uint32_t it_u = blockIdx.x, it_rc = 0, it_sc = 0;
+    uint4 it_d = make_uint4(0, 0, 0, 0), it_dn = make_uint4(0, 0, 0, 0);
+    bool it_valid = false;
+    auto issue = [&](uint32_t stage) {
+        tup_t* rbuf = reinterpret_cast<tup_t*>(smem_raw + L::stage_bytes * stage);
+        tup_t* sbuf = rbuf + (CAP + 2);
+        if (!it_valid) {
+            s_hdr[stage] = make_uint4(STEP_DONE, 0, 0, 0);
+            mbar_arrive_expect_tx(&s_bar[stage], 0);
+            return;
+        }
+        const uint32_t nr = min((uint32_t)CAP, it_d.w - it_rc), ns = min((uint32_t)U, it_d.y - it_sc);
+        const uint32_t rskip = it_rc & 1u, sskip = it_sc & 1u;
+        const uint32_t rbytes = ((nr + rskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
+        const uint32_t sbytes = ((ns + sskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
+        s_hdr[stage] = make_uint4(nr, ns, rskip, sskip);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&s_bar[stage], rbytes + sbytes);
+        bulk_g2s(rbuf, a.bld + (it_rc - rskip), rbytes, &s_bar[stage]);
+        bulk_g2s(sbuf, a.prb + (it_sc - sskip), sbytes, &s_bar[stage]);
+        // advance
+        it_sc += U;
+        if (it_sc >= it_d.y) {
+            it_sc = it_d.x;
+            it_rc += CAP;
+            if (it_rc >= it_d.w) {
+                it_u += gridDim.x;
+                it_valid = it_u < nunits;
+                it_d = it_dn;                                   // prefetched one unit ahead
+                it_rc = it_d.z; it_sc = it_d.x;
+                if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
             }
-            // probe
-            for (uint32_t j0 = pb; j0 < pe; j0 += THREADS * JOIN_BATCH) {
-                tup_t t[JOIN_BATCH];
-#pragma unroll
-                for (int q = 0; q < JOIN_BATCH; ++q) {
-                    const uint32_t j = j0 + q * THREADS + tid;
-                    if (j < pe) t[q] = __ldg(a.prb + j);
-                }
-#pragma unroll
-                for (int q = 0; q < JOIN_BATCH; ++q) {
-                    const uint32_t j = j0 + q * THREADS + tid;
-                    if (j < pe) {
-                        const uint32_t k = t[q].x >> a.hash_shift;
-                        uint32_t i = s_head[(k ^ (k >> hb)) & hmask];
-                        while (i != EMPTY32 && i != EMPTY16) {
-                            const tup_t r = s_tup[i];
-                            const uint32_t nx = s_next[i];
-                            if (r.x == t[q].x) {
-                                ++matches;
-                                sum += (unsigned long long)((long long)(int32_t)r.y * (long long)(int32_t)t[q].y);
-                                if (MATERIALIZE) {
-                                    const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                                    if (pos < (uint32_t)JOIN_STAGE) {
-                                        s_stage_b[pos] = (int32_t)r.y;
-                                        s_stage_p[pos] = (int32_t)t[q].y;
-                                    } else {   // staging full inside a round: rare direct path
-                                        const unsigned long long g = atomicAdd(&a.result[2], 1ull);
-                                        if (g < a.cap) {
-                                            a.out_bld_pay[g] = (int32_t)r.y;
-                                            a.out_prb_pay[g] = (int32_t)t[q].y;
-                                        }
-                                    }
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&s_bar[s], 1);
+        fence_mbar_init();
+        if (MATERIALIZE) s_cnt = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        it_valid = it_u < nunits;
+        if (it_valid) {
+            it_d = __ldg(a.units + it_u);
+            it_rc = it_d.z; it_sc = it_d.x;
+            if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
+        }
+        for (int s = 0; s < STAGES; ++s) issue(s);
+    }
+
+    for (uint32_t k = 0;; ++k) {
+        const uint32_t stage = k % STAGES, parity = (k / STAGES) & 1u;
+        mbar_wait(&s_bar[stage], parity);
+        const uint4 hdr = s_hdr[stage];
+        if (hdr.x == STEP_DONE) break;
+        const uint32_t nr = hdr.x, ns = hdr.y;
+        const tup_t* rbuf = reinterpret_cast<const tup_t*>(smem_raw + L::stage_bytes * stage) + hdr.z;
+        const tup_t* sbuf = reinterpret_cast<const tup_t*>(smem_raw + L::stage_bytes * stage) + (CAP + 2) + hdr.w;
+        const uint32_t hb = 32u - __clz(max(nr, 32u) - 1u);   // ceil(log2(nr)), >= 5
+        const uint32_t H = 1u << hb, hmask = H - 1u;
+
+        for (uint32_t i = tid; i < H / 4; i += THREADS)
+            reinterpret_cast<uint4*>(s_head)[i] = make_uint4(EMPTY32, EMPTY32, EMPTY32, EMPTY32);
+        __syncthreads();
+        for (uint32_t i = tid; i < nr; i += THREADS) {
+            const uint32_t kk = rbuf[i].x >> a.hash_shift;
+            s_next[i] = (uint16_t)atomicExch(&s_head[(kk ^ (kk >> hb)) & hmask], i);
+        }
+        __syncthreads();
+        const uint32_t rounds = (ns + THREADS - 1) / THREADS;
+        for (uint32_t q = 0; q < rounds; ++q) {
+            const uint32_t j = q * THREADS + tid;
+            if (j < ns) {
+                const tup_t t = sbuf[j];
+                const uint32_t kk = t.x >> a.hash_shift;
+                uint32_t i = s_head[(kk ^ (kk >> hb)) & hmask];
+                while (i != EMPTY32 && i != EMPTY16) {
+                    const tup_t r = rbuf[i];
+                    const uint32_t nx = s_next[i];
+                    if (r.x == t.x) {
+                        ++matches;
+                        sum += (unsigned long long)((long long)(int32_t)r.y * (long long)(int32_t)t.y);
+                        if (MATERIALIZE) {
+                            const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                            if (pos < (uint32_t)JOIN_STAGE_PAIRS) {
+                                s_out_b[pos] = (int32_t)r.y;
+                                s_out_p[pos] = (int32_t)t.y;
+                            } else {   // staging full inside a round: rare direct path
+                                const unsigned long long g = atomicAdd(&a.result[2], 1ull);
+                                if (g < a.cap) {
+                                    a.out_bld_pay[g] = (int32_t)r.y;
+                                    a.out_prb_pay[g] = (int32_t)t.y;
                                 }
                             }
-                            i = nx;
                         }
                     }
+                    i = nx;
                 }
-                if (MATERIALIZE) {
+            }
+            if (MATERIALIZE) {
+                __syncthreads();
+                const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE_PAIRS);
+                if (c + THREADS > (uint32_t)JOIN_STAGE_PAIRS) {
+                    if (tid == 0) s_base = atomicAdd(&a.result[2], (unsigned long long)c);
                     __syncthreads();
-                    const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE);
-                    if (c + THREADS * JOIN_BATCH > (uint32_t)JOIN_STAGE) {
-                        if (tid == 0) s_base = atomicAdd(&a.result[2], (unsigned long long)c);
-                        __syncthreads();
-                        const unsigned long long g0 = s_base;
-                        for (uint32_t i = tid; i < c; i += THREADS) {
-                            if (g0 + i < a.cap) {
-                                a.out_bld_pay[g0 + i] = s_stage_b[i];
-                                a.out_prb_pay[g0 + i] = s_stage_p[i];
-                            }
+                    const unsigned long long g0 = s_base;
+                    for (uint32_t i = tid; i < c; i += THREADS) {
+                        if (g0 + i < a.cap) {
+                            a.out_bld_pay[g0 + i] = s_out_b[i];
+                            a.out_prb_pay[g0 + i] = s_out_p[i];
                         }
-                        __syncthreads();
-                        if (tid == 0) s_cnt = 0;
-                        __syncthreads();
                     }
+                    __syncthreads();
+                    if (tid == 0) s_cnt = 0;
+                    __syncthreads();
                 }
             }
         }
+        __syncthreads();                 // everyone is done with this stage and the table
+        if (tid == 0) issue(stage);      // refill it STAGES steps ahead
     }
+
     if (MATERIALIZE) {
         __syncthreads();
-        const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE);
+        const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE_PAIRS);
         if (c) {
             if (tid == 0) s_base = atomicAdd(&a.result[2], (unsigned long long)c);
             __syncthreads();
             const unsigned long long g0 = s_base;
             for (uint32_t i = tid; i < c; i += THREADS) {
                 if (g0 + i < a.cap) {
-                    a.out_bld_pay[g0 + i] = s_stage_b[i];
-                    a.out_prb_pay[g0 + i] = s_stage_p[i];
+                    a.out_bld_pay[g0 + i] = s_out_b[i];
+                    a.out_prb_pay[g0 + i] = s_out_p[i];
                 }
             }
         }
