@@ -71,17 +71,17 @@ static size_t scatter_smem(const ScatterCfg& c) {
 
 typedef void (*join_fn)(JoinArgs);
 struct JoinCfg { int threads, cap, u; join_fn agg, mat; size_t smem_agg, smem_mat; };
-// aggregate variant with SA stages, materialising variant with SM stages (needs 16 KB of pair staging)
-#define GJ_JC(T, C, U, SA, SM) { T, C, U, join_kernel<T, C, U, SA, false>, join_kernel<T, C, U, SM, true>, \
-                                 JoinSmem<C, U, SA, false>::total, JoinSmem<C, U, SM, true>::total }
+// <threads, build chunk, probe chunk, R ring slots, S ring slots>
+#define GJ_JC(T, C, U, NR, NS) { T, C, U, join_kernel<T, C, U, NR, NS, false>, join_kernel<T, C, U, NR, NS, true>, \
+                                 JoinSmem<C, U, NR, NS, false>::total, JoinSmem<C, U, NR, NS, true>::total }
 static const JoinCfg kJoin[] = {
     GJ_JC(1024, 4096, 4096, 3, 2),   // 0 default
-    GJ_JC(512, 4096, 4096, 3, 2),    // 1
-    GJ_JC(1024, 4096, 2048, 4, 3),   // 2
-    GJ_JC(1024, 8192, 2048, 2, 1),   // 3 big build partitions (radix bits capped)
-    GJ_JC(1024, 4096, 4096, 2, 2),   // 4
-    GJ_JC(1024, 2048, 2048, 5, 4),   // 5
-    GJ_JC(768, 4096, 4096, 3, 2),    // 6
+    GJ_JC(1024, 4096, 2048, 3, 3),   // 1
+    GJ_JC(512, 4096, 4096, 3, 2),    // 2
+    GJ_JC(1024, 4096, 4096, 2, 2),   // 3
+    GJ_JC(768, 4096, 4096, 3, 2),    // 4
+    GJ_JC(1024, 2048, 2048, 4, 3),   // 5
+    GJ_JC(1024, 4096, 1024, 3, 4),   // 6
 };
 static const int kNumJoin = (int)(sizeof(kJoin) / sizeof(kJoin[0]));
 
@@ -409,7 +409,7 @@ static int enqueue_scatter(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role
     a.out = pl.b2 ? ctx->scratch : dst;
     a.shift = pl.b2; a.bits = pl.b1;
     a.cursors = pl.b2 ? m.cur1 : m.cur2;
-    const uint32_t grid1 = (uint32_t)((rel.n + T1 - 1) / T1);
+    const uint32_t grid1 = (uint32_t)((rel.n + (rel.tup ? 1 : 0) + T1 - 1) / T1);   // +1: alignment shift of packed input
     CK(cudaEventRecord(ctx->pev[role][0], s));
     (rel.tup ? c1.packed : c1.col)<<<grid1, c1.threads, scatter_smem(c1), s>>>(a);
     LAUNCHED();
@@ -442,9 +442,8 @@ static int fill_pass_times(gj_ctx* ctx, gj_timings* t, const Plan& pl, int nrole
 
 static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup_t* prb, const Plan& pl,
                         uint64_t n_bld, uint64_t n_prb, bool mat, int32_t* out_b, int32_t* out_p, uint64_t cap) {
-    int cfg = (int)ctx->opt_join_cfg;
-    if (cfg == 0 && (n_bld >> pl.B) > 4096) cfg = 3;   // radix bits capped: 8192-tuple build chunks
-    const JoinCfg& jc = kJoin[cfg];
+    (void)n_bld;
+    const JoinCfg& jc = kJoin[ctx->opt_join_cfg];
     JoinArgs a;
     a.bld = bld; a.prb = prb;
     a.units = ctx->units; a.num_units = ctx->unit_base + (1u << pl.B);

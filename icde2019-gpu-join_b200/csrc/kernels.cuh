@@ -389,10 +389,16 @@ scatter_kernel(ScatterArgs a) {
 
     // ---- which slots does this tile cover ----
     uint32_t a0, lo, hi, cbase;
+    const tup_t* in_tup = a.in_tup;
     if (a.tiles == nullptr) {
+        // caller-provided packed tuples may be only 8-byte aligned: step back one tuple so that
+        // slot pairs are 16-byte aligned, and treat slot 0 as not ours
+        const uint32_t mis = (!COLUMNAR && ((size_t)in_tup & 8u)) ? 1u : 0u;
+        in_tup -= mis;
         const unsigned long long s = (unsigned long long)blockIdx.x * T;
-        a0 = (uint32_t)s; lo = a0;
-        hi = (s < a.n) ? a0 + min(T, a.n - a0) : a0;
+        const unsigned long long n_eff = (unsigned long long)a.n + mis;
+        a0 = (uint32_t)s; lo = max(a0, mis);
+        hi = (s < n_eff) ? a0 + (uint32_t)min((unsigned long long)T, n_eff - s) : a0;
         cbase = 0;
     } else {
         if (blockIdx.x >= *a.num_tiles) return;
@@ -434,12 +440,17 @@ scatter_kernel(ScatterArgs a) {
         }
     } else {
         // a0 is even and the buffer 16-byte aligned: one 16-byte load = two tuples
-        const uint4* tv = reinterpret_cast<const uint4*>(a.in_tup + a0);
+        const uint4* tv = reinterpret_cast<const uint4*>(in_tup + a0);
 #pragma unroll
         for (int j = 0; j < IPT / 2; ++j) {
             const uint32_t pi = j * THREADS + tid;
+            const uint32_t s0 = a0 + 2 * pi;
             uint4 t = make_uint4(0, 0, 0, 0);
-            if (a0 + 2 * pi < hi) t = __ldg(tv + pi);
+            if (full || (s0 >= lo && s0 + 1 < hi)) t = __ldg(tv + pi);
+            else {   // tile edge: never touch a tuple outside [lo, hi)
+                if (s0 >= lo && s0 < hi) { const tup_t e = __ldg(in_tup + s0); t.x = e.x; t.y = e.y; }
+                if (s0 + 1 >= lo && s0 + 1 < hi) { const tup_t e = __ldg(in_tup + s0 + 1); t.z = e.x; t.w = e.y; }
+            }
             key[2 * j] = t.x; pay[2 * j] = t.y; key[2 * j + 1] = t.z; pay[2 * j + 1] = t.w;
         }
     }
@@ -533,16 +544,22 @@ scatter_kernel(ScatterArgs a) {
 
 // ------------------------------------------------------------------------------------------
 // 5. Per-partition hash join: persistent CTAs (one per SM), static round-robin over the unit
-//    list, and a TMA-fed shared-memory ring.
+//    list, fed by TMA bulk copies into two shared-memory rings.
 //    A unit {probe range, build partition} is processed in steps of (build chunk <= CAP tuples)
-//    x (probe chunk <= U tuples).  One thread runs an iterator STAGES-1 steps ahead and issues
-//    two bulk async copies per step (build chunk, probe chunk) into the step's stage, completion
-//    on the stage's mbarrier -- all HBM traffic of the join is asynchronous bulk traffic, no
-//    load instructions, no register staging, latency hidden by the ring depth.
-//    Per step the CTA: waits on the stage, clears 2^hb heads, builds the chained table in place
-//    over the staged build tuples (atomicExch on the head, 16-bit next links: index chains need
-//    no sentinel key and are N:M safe), probes with the staged probe tuples (full 32-bit key
-//    compare, 64-bit per-thread accumulators), and hands the stage back to the loader.
+//    x (probe chunk <= U tuples).  Thread 0 runs an iterator ahead of the CTA and issues bulk
+//    async copies (cp.async.bulk, completion on mbarriers): every step's probe chunk goes into
+//    the S ring (NS slots); a build chunk goes into the R ring (NR slots) only when it differs
+//    from the previous step's -- a build partition that is probed by many chunks / units
+//    (large or skewed probe sides) is loaded and hashed ONCE.  All HBM traffic of the join is
+//    asynchronous bulk traffic: no load instructions, no register staging, latency hidden by
+//    the ring depth.
+//    Per step the CTA waits on the slot's mbarrier; on a new build chunk it builds the chained
+//    table in place over the staged tuples (atomicExch on the head, 16-bit next links: index
+//    chains need no sentinel key and are N:M safe; a MULTI bit in the head marks buckets with
+//    more than one entry so the common single-entry probe never reads a link); then probes with
+//    the staged probe tuples (full 32-bit key compare, 64-bit per-thread accumulators).  Two
+//    head tables alternate, the idle one is cleared during a probe phase: 2 barriers per new
+//    build chunk, 1 per further probe chunk.
 //    Hash = xor-fold of the key bits above the radix (+GPU) field: the identity on dense keys
 //    (the reference's choice, common.h:45-47), a real hash otherwise.
 //    Build partitions larger than CAP simply produce more steps (the reference's block-nested
@@ -561,29 +578,35 @@ struct JoinArgs {
 
 constexpr int JOIN_STAGE_PAIRS = 2048;   // staged result pairs per CTA (materialise)
 constexpr uint32_t STEP_DONE = 0xFFFFFFFFu;
+constexpr uint32_t HEAD_EMPTY = 0x0000FFFFu;   // low 16 bits = entry index or 0xFFFF
+constexpr uint32_t HEAD_MULTI = 0x80000000u;   // bucket holds more than one entry
 
-template <int CAP, int U, int STAGES, bool MATERIALIZE>
+template <int CAP, int U, int NR, int NS, bool MATERIALIZE>
 struct JoinSmem {
-    static constexpr size_t stage_bytes = (size_t)(CAP + 2 + U + 2) * sizeof(tup_t);
-    static constexpr size_t off_head = stage_bytes * STAGES;
-    static constexpr size_t off_next = off_head + (size_t)CAP * 4;
-    static constexpr size_t off_out = off_next + (size_t)CAP * 2;
+    static constexpr size_t rbuf_bytes = (size_t)(CAP + 2) * sizeof(tup_t);
+    static constexpr size_t sbuf_bytes = (size_t)(U + 2) * sizeof(tup_t);
+    static constexpr size_t off_s = rbuf_bytes * NR;
+    static constexpr size_t off_head = off_s + sbuf_bytes * NS;
+    static constexpr size_t off_next = off_head + (size_t)2 * CAP * 4;
+    static constexpr size_t off_out = off_next + (size_t)2 * CAP * 2;
     static constexpr size_t off_hdr = off_out + (MATERIALIZE ? (size_t)JOIN_STAGE_PAIRS * 8 : 0);
-    static constexpr size_t off_bar = off_hdr + (size_t)STAGES * 16;
-    static constexpr size_t total = off_bar + (size_t)STAGES * 8;
+    static constexpr size_t off_bar = off_hdr + (size_t)NS * 32;
+    static constexpr size_t total = off_bar + (size_t)(NS + NR) * 8;
 };
 
-template <int THREADS, int CAP, int U, int STAGES, bool MATERIALIZE>
+template <int THREADS, int CAP, int U, int NR, int NS, bool MATERIALIZE>
 __global__ void __launch_bounds__(THREADS, 1)
 join_kernel(JoinArgs a) {
-    using L = JoinSmem<CAP, U, STAGES, MATERIALIZE>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t* s_head = reinterpret_cast<uint32_t*>(smem_raw + L::off_head);
-    uint16_t* s_next = reinterpret_cast<uint16_t*>(smem_raw + L::off_next);
+    using L = JoinSmem<CAP, U, NR, NS, MATERIALIZE>;
+    static_assert(CAP < 0xFFFF, "16-bit entry indices");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_head = reinterpret_cast<uint32_t*>(smem_raw + L::off_head);   // [2][CAP]
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(smem_raw + L::off_next);   // [2][CAP]
     int32_t* s_out_b = reinterpret_cast<int32_t*>(smem_raw + L::off_out);
     int32_t* s_out_p = s_out_b + JOIN_STAGE_PAIRS;
-    uint4* s_hdr = reinterpret_cast<uint4*>(smem_raw + L::off_hdr);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);
+    uint4* s_hdr = reinterpret_cast<uint4*>(smem_raw + L::off_hdr);           // [NS][2]
+    uint64_t* s_sbar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);    // [NS]
+    uint64_t* s_rbar = s_sbar + NS;                                           // [NR]
     __shared__ uint32_t s_cnt;
     __shared__ unsigned long long s_base;
     __shared__ unsigned long long s_red[2][THREADS / 32];
@@ -592,28 +615,45 @@ join_kernel(JoinArgs a) {
     const uint32_t nunits = *a.num_units;
     unsigned long long matches = 0, sum = 0;
 
-    // ---- loader state (thread 0 only): iterator over (unit, build chunk, probe chunk) ----
+    // ---- loader state (thread 0 only) ----
     uint32_t it_u = blockIdx.x, it_rc = 0, it_sc = 0;
     uint4 it_d = make_uint4(0, 0, 0, 0), it_dn = make_uint4(0, 0, 0, 0);
-    bool it_valid = false;
-    auto issue = [&](uint32_t stage) {
-        tup_t* rbuf = reinterpret_cast<tup_t*>(smem_raw + L::stage_bytes * stage);
-        tup_t* sbuf = rbuf + (CAP + 2);
+    bool it_valid = false, p_done = false;
+    uint32_t p_steps = 0, p_chunks = 0, last_rc = 0, last_nr = 0;
+    uint32_t c_steps = 0, c_chunk = 0;   // steps fully consumed / chunk the CTA is working on
+    // returns true if a step was issued and another one may fit
+    auto try_issue = [&]() -> bool {
+        if (p_done || p_steps - c_steps >= (uint32_t)NS) return false;
+        const uint32_t sslot = p_steps % NS;
         if (!it_valid) {
-            s_hdr[stage] = make_uint4(STEP_DONE, 0, 0, 0);
-            mbar_arrive_expect_tx(&s_bar[stage], 0);
-            return;
+            s_hdr[2 * sslot] = make_uint4(STEP_DONE, 0, 0, 0);
+            mbar_arrive_expect_tx(&s_sbar[sslot], 0);
+            p_done = true;
+            ++p_steps;
+            return false;
         }
         const uint32_t nr = min((uint32_t)CAP, it_d.w - it_rc), ns = min((uint32_t)U, it_d.y - it_sc);
+        const bool newc = (p_chunks == 0) || it_rc != last_rc || nr != last_nr;
+        // chunk p_chunks reuses the slot of chunk p_chunks - NR, which must be fully consumed
+        if (newc && p_chunks >= c_chunk + (uint32_t)NR) return false;
+        const uint32_t chunk = newc ? p_chunks : p_chunks - 1u;
         const uint32_t rskip = it_rc & 1u, sskip = it_sc & 1u;
-        const uint32_t rbytes = ((nr + rskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
-        const uint32_t sbytes = ((ns + sskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
-        s_hdr[stage] = make_uint4(nr, ns, rskip, sskip);
+        s_hdr[2 * sslot] = make_uint4(ns, sskip, newc ? 1u : 0u, chunk);
+        s_hdr[2 * sslot + 1] = make_uint4(nr, rskip, 0, 0);
         fence_proxy_async();
-        mbar_arrive_expect_tx(&s_bar[stage], rbytes + sbytes);
-        bulk_g2s(rbuf, a.bld + (it_rc - rskip), rbytes, &s_bar[stage]);
-        bulk_g2s(sbuf, a.prb + (it_sc - sskip), sbytes, &s_bar[stage]);
-        // advance
+        if (newc) {
+            const uint32_t rslot = chunk % NR;
+            const uint32_t rbytes = ((nr + rskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
+            mbar_arrive_expect_tx(&s_rbar[rslot], rbytes);
+            bulk_g2s(smem_raw + L::rbuf_bytes * rslot, a.bld + (it_rc - rskip), rbytes, &s_rbar[rslot]);
+            last_rc = it_rc; last_nr = nr;
+            ++p_chunks;
+        }
+        const uint32_t sbytes = ((ns + sskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
+        mbar_arrive_expect_tx(&s_sbar[sslot], sbytes);
+        bulk_g2s(smem_raw + L::off_s + L::sbuf_bytes * sslot, a.prb + (it_sc - sskip), sbytes, &s_sbar[sslot]);
+        ++p_steps;
+        // advance: probe chunks innermost, then build chunks, then the next unit of this CTA
         it_sc += U;
         if (it_sc >= it_d.y) {
             it_sc = it_d.x;
@@ -626,13 +666,17 @@ join_kernel(JoinArgs a) {
                 if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
             }
         }
+        return true;
     };
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&s_bar[s], 1);
+        for (int s = 0; s < NS; ++s) mbar_init(&s_sbar[s], 1);
+        for (int s = 0; s < NR; ++s) mbar_init(&s_rbar[s], 1);
         fence_mbar_init();
         if (MATERIALIZE) s_cnt = 0;
     }
+    for (uint32_t i = tid; i < (uint32_t)CAP / 4; i += THREADS)
+        reinterpret_cast<uint4*>(s_head)[i] = make_uint4(HEAD_EMPTY, HEAD_EMPTY, HEAD_EMPTY, HEAD_EMPTY);
     __syncthreads();
     if (tid == 0) {
         it_valid = it_u < nunits;
@@ -641,38 +685,45 @@ join_kernel(JoinArgs a) {
             it_rc = it_d.z; it_sc = it_d.x;
             if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
         }
-        for (int s = 0; s < STAGES; ++s) issue(s);
+        while (try_issue()) {}
     }
 
     for (uint32_t k = 0;; ++k) {
-        const uint32_t stage = k % STAGES, parity = (k / STAGES) & 1u;
-        mbar_wait(&s_bar[stage], parity);
-        const uint4 hdr = s_hdr[stage];
-        if (hdr.x == STEP_DONE) break;
-        const uint32_t nr = hdr.x, ns = hdr.y;
-        const tup_t* rbuf = reinterpret_cast<const tup_t*>(smem_raw + L::stage_bytes * stage) + hdr.z;
-        const tup_t* sbuf = reinterpret_cast<const tup_t*>(smem_raw + L::stage_bytes * stage) + (CAP + 2) + hdr.w;
+        const uint32_t sslot = k % NS;
+        mbar_wait(&s_sbar[sslot], (k / NS) & 1u);
+        const uint4 h0 = s_hdr[2 * sslot];
+        if (h0.x == STEP_DONE) break;
+        const uint4 h1 = s_hdr[2 * sslot + 1];
+        const uint32_t ns = h0.x, nr = h1.x, chunk = h0.w, rslot = chunk % NR, tb = chunk & 1u;
+        const bool newc = (h0.z & 1u) != 0;
+        const tup_t* rbuf = reinterpret_cast<const tup_t*>(smem_raw + L::rbuf_bytes * rslot) + h1.y;
+        const tup_t* sbuf = reinterpret_cast<const tup_t*>(smem_raw + L::off_s + L::sbuf_bytes * sslot) + h0.y;
+        uint32_t* head = s_head + tb * CAP;
+        uint16_t* next = s_next + tb * CAP;
         const uint32_t hb = 32u - __clz(max(nr, 32u) - 1u);   // ceil(log2(nr)), >= 5
-        const uint32_t H = 1u << hb, hmask = H - 1u;
+        const uint32_t hmask = (1u << hb) - 1u;
 
-        for (uint32_t i = tid; i < H / 4; i += THREADS)
-            reinterpret_cast<uint4*>(s_head)[i] = make_uint4(EMPTY32, EMPTY32, EMPTY32, EMPTY32);
-        __syncthreads();
-        for (uint32_t i = tid; i < nr; i += THREADS) {
-            const uint32_t kk = rbuf[i].x >> a.hash_shift;
-            s_next[i] = (uint16_t)atomicExch(&s_head[(kk ^ (kk >> hb)) & hmask], i);
+        if (newc) {
+            mbar_wait(&s_rbar[rslot], (chunk / NR) & 1u);
+            for (uint32_t i = tid; i < nr; i += THREADS) {
+                const uint32_t kk = rbuf[i].x >> a.hash_shift;
+                uint32_t* hp = &head[(kk ^ (kk >> hb)) & hmask];
+                const uint32_t old = atomicExch(hp, i);
+                next[i] = (uint16_t)old;
+                if ((old & 0xFFFFu) != 0xFFFFu) atomicOr(hp, HEAD_MULTI);
+            }
+            __syncthreads();
         }
-        __syncthreads();
         const uint32_t rounds = (ns + THREADS - 1) / THREADS;
         for (uint32_t q = 0; q < rounds; ++q) {
             const uint32_t j = q * THREADS + tid;
             if (j < ns) {
                 const tup_t t = sbuf[j];
                 const uint32_t kk = t.x >> a.hash_shift;
-                uint32_t i = s_head[(kk ^ (kk >> hb)) & hmask];
-                while (i != EMPTY32 && i != EMPTY16) {
+                const uint32_t w = head[(kk ^ (kk >> hb)) & hmask];
+                uint32_t i = w & 0xFFFFu;
+                while (i != 0xFFFFu) {
                     const tup_t r = rbuf[i];
-                    const uint32_t nx = s_next[i];
                     if (r.x == t.x) {
                         ++matches;
                         sum += (unsigned long long)((long long)(int32_t)r.y * (long long)(int32_t)t.y);
@@ -690,7 +741,7 @@ join_kernel(JoinArgs a) {
                             }
                         }
                     }
-                    i = nx;
+                    i = (w & HEAD_MULTI) ? (uint32_t)next[i] : 0xFFFFu;
                 }
             }
             if (MATERIALIZE) {
@@ -712,8 +763,16 @@ join_kernel(JoinArgs a) {
                 }
             }
         }
-        __syncthreads();                 // everyone is done with this stage and the table
-        if (tid == 0) issue(stage);      // refill it STAGES steps ahead
+        if (newc) {   // the other table (previous chunk's) is idle: clear it for the next chunk
+            uint32_t* other = s_head + (tb ^ 1u) * CAP;
+            for (uint32_t i = tid; i < (uint32_t)CAP / 4; i += THREADS)
+                reinterpret_cast<uint4*>(other)[i] = make_uint4(HEAD_EMPTY, HEAD_EMPTY, HEAD_EMPTY, HEAD_EMPTY);
+        }
+        __syncthreads();                 // everyone is done with this step's slots
+        if (tid == 0) {
+            c_steps = k + 1; c_chunk = chunk;
+            while (try_issue()) {}
+        }
     }
 
     if (MATERIALIZE) {

@@ -218,6 +218,13 @@ def test_packed_tuple_entry(gj, orc, eng, torch_cuda):
     St = torch_cuda.from_numpy(np.stack([Sk, Sp], axis=1).copy()).cuda()
     got = eng.join_aggregate_tuples(Rt, nR, St, nS)
     assert (got.matches, got.checksum) == (want.matches, want.checksum)
+    # packed input that is only 8-byte aligned (odd tuple offset inside a larger buffer)
+    Rt1 = torch_cuda.zeros((nR + 1, 2), dtype=torch_cuda.int32, device="cuda")
+    St1 = torch_cuda.zeros((nS + 3, 2), dtype=torch_cuda.int32, device="cuda")
+    Rt1[1:] = Rt
+    St1[3:] = St
+    got = eng.join_aggregate_tuples(Rt1[1:], nR, St1[3:], nS)
+    assert (got.matches, got.checksum) == (want.matches, want.checksum)
 
 
 def test_host_entry_end_to_end(gj, orc, eng, torch_cuda):

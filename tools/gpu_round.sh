@@ -36,6 +36,8 @@ fi
 if has sweep; then
   timeout 1200 python tools/sweep.py > $OUT/sweep.log 2>&1
   echo "exit $?" >> $OUT/sweep.log
+  timeout 600 python tools/sweep.py --n 16777216 --nS 268435456 --what join > $OUT/sweep_A.log 2>&1
+  echo "exit $?" >> $OUT/sweep_A.log
 fi
 if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \

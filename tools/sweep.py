@@ -17,7 +17,7 @@ def main():
     ap.add_argument("--n", type=int, default=128_000_000)
     ap.add_argument("--nS", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--what", default="scatter,join,bits,unit")
+    ap.add_argument("--what", default="scatter,join,bits,unit,combo")
     args = ap.parse_args()
     import torch
     gj = ge.load_package()
@@ -41,7 +41,7 @@ def main():
         pass
 
     def run(tag, **opts):
-        for k in ("radix_bits", "pass1_bits", "scatter_cfg", "join_cfg", "unit_tuples", "join_grid"):
+        for k in ("radix_bits", "pass1_bits", "scatter_cfg", "scatter_cfg1", "scatter_cfg2", "join_cfg", "unit_tuples", "join_grid"):
             eng.set_option(k, 0)
         for k, v in opts.items():
             eng.set_option(k, v)
@@ -83,6 +83,11 @@ def main():
             for p1 in (7, 8):
                 if b - p1 <= 8:
                     run("bits", radix_bits=b, pass1_bits=p1)
+    if "combo" in what:
+        for p1, c1s, c2s in ((7, (0, 3, 8), (0, 3, 4, 6, 8)), (8, (0, 3), (4, 6))):
+            for c1 in c1s:
+                for c2 in c2s:
+                    run("combo", radix_bits=15, pass1_bits=p1, scatter_cfg1=c1, scatter_cfg2=c2)
     if "unit" in what:
         for u in (4096, 8192, 32768, 65536):
             run("unit", unit_tuples=u)
