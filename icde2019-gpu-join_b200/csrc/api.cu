@@ -222,7 +222,7 @@ static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) 
     // persistent metadata block
     size_t mb = 0;
     const size_t o_off = mb;    mb += 2 * (FINE_MAX + 4) * sizeof(uint32_t);
-    const size_t o_cur1 = mb;   mb += 2 * NB_MAX * sizeof(uint32_t);
+    const size_t o_cur1 = mb;   mb += 2 * NB_MAX * CUR1_STRIDE * sizeof(uint32_t);
     const size_t o_cur2 = mb;   mb += 2 * FINE_MAX * sizeof(uint32_t);
     const size_t o_ub = mb;     mb += (FINE_MAX + 4) * sizeof(uint32_t);
     CK(cudaMalloc(&ctx->meta_block, mb));
@@ -235,7 +235,7 @@ static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) 
         m.desc = reinterpret_cast<unsigned long long*>(ctx->zero_block + o_desc) + (size_t)r * SCAN_TILES_MAX;
         m.ticket = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + r;
         m.off = reinterpret_cast<uint32_t*>(ctx->meta_block + o_off) + (size_t)r * (FINE_MAX + 4);
-        m.cur1 = reinterpret_cast<uint32_t*>(ctx->meta_block + o_cur1) + (size_t)r * NB_MAX;
+        m.cur1 = reinterpret_cast<uint32_t*>(ctx->meta_block + o_cur1) + (size_t)r * NB_MAX * CUR1_STRIDE;
         m.cur2 = reinterpret_cast<uint32_t*>(ctx->meta_block + o_cur2) + (size_t)r * FINE_MAX;
         m.tiles = ctx->tiles_block + (size_t)r * ctx->tiles_cap;
         m.num_tiles = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + 8 + r;
@@ -409,6 +409,7 @@ static int enqueue_scatter(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role
     a.out = pl.b2 ? ctx->scratch : dst;
     a.shift = pl.b2; a.bits = pl.b1;
     a.cursors = pl.b2 ? m.cur1 : m.cur2;
+    a.cursor_stride = pl.b2 ? CUR1_STRIDE : 1;
     const uint32_t grid1 = (uint32_t)((rel.n + (rel.tup ? 1 : 0) + T1 - 1) / T1);   // +1: alignment shift of packed input
     CK(cudaEventRecord(ctx->pev[role][0], s));
     (rel.tup ? c1.packed : c1.col)<<<grid1, c1.threads, scatter_smem(c1), s>>>(a);
@@ -421,7 +422,7 @@ static int enqueue_scatter(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role
         memset(&b, 0, sizeof(b));
         b.in_tup = ctx->scratch; b.out = dst; b.n = (uint32_t)rel.n;
         b.shift = 0; b.bits = pl.b2;
-        b.cursors = m.cur2; b.tiles = m.tiles; b.num_tiles = m.num_tiles;
+        b.cursors = m.cur2; b.cursor_stride = 1; b.tiles = m.tiles; b.num_tiles = m.num_tiles;
         const uint32_t grid2 = (uint32_t)(rel.n / T2) + (1u << pl.b1) + 2;   // upper bound on tiles
         c2.packed<<<grid2, c2.threads, scatter_smem(c2), s>>>(b);
         LAUNCHED();
@@ -754,7 +755,7 @@ extern "C" int gj_shuffle_split(gj_ctx* ctx, const int32_t* d_keys, const int32_
         ScatterArgs a;
         memset(&a, 0, sizeof(a));
         a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = (tup_t*)d_out_tuples;
-        a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2;
+        a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2; a.cursor_stride = 1;
         c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, scatter_smem(c1), s>>>(a);
         LAUNCHED();
     }
@@ -789,7 +790,7 @@ extern "C" int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, cons
         memset(&a, 0, sizeof(a));
         a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = nullptr;
         a.dst_bases = ctx->d_dst_bases;
-        a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2;
+        a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2; a.cursor_stride = 1;
         c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, scatter_smem(c1), s>>>(a);
         LAUNCHED();
     }

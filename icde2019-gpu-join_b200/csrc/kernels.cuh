@@ -29,6 +29,7 @@ typedef uint2 tup_t;  // .x = key bits, .y = payload bits
 constexpr int MAX_RADIX_BITS = 15;    // fine histogram: 2^15 u32 counters = 128 KB of smem
 constexpr int MAX_PASS_BITS = 8;      // fan-out per scatter pass <= 256
 constexpr int NB_MAX = 1 << MAX_PASS_BITS;
+constexpr uint32_t CUR1_STRIDE = 32;  // first-pass cursors live one per 128-byte line (L2 atomics serialise per line)
 constexpr uint32_t EMPTY32 = 0xFFFFFFFFu;
 constexpr uint32_t EMPTY16 = 0xFFFFu;
 
@@ -295,7 +296,7 @@ plan_kernel(PlanArgs a) {
                 lo = R.off[tid << a.b2]; hi = R.off[(tid + 1) << a.b2];
                 a0 = lo & ~1u;
                 tiles = hi > lo ? (hi - a0 + a.tile - 1) / a.tile : 0u;
-                if (blockIdx.x == 0) R.cur1[tid] = lo;
+                if (blockIdx.x == 0) R.cur1[tid * CUR1_STRIDE] = lo;
             }
             __syncthreads();   // previous relation's readers of s_tp are done
             uint32_t incl = warp_incl_scan(tiles, lane);
@@ -367,6 +368,7 @@ struct ScatterArgs {
     uint32_t n;
     uint32_t shift, bits;
     uint32_t* cursors;
+    uint32_t cursor_stride;      // words between consecutive cursors
     const uint4* tiles;          // pass 2 only
     const uint32_t* num_tiles;   // pass 2 only
 };
@@ -491,7 +493,7 @@ scatter_kernel(ScatterArgs a) {
         for (uint32_t w = 0; w < NB_MAX / 32; ++w)
             if (w < wid) woff += s_warp[w];
         const uint32_t excl = incl - sz + woff;
-        if (cnt) gb = atomicAdd(&a.cursors[cbase + tid], cnt);
+        if (cnt) gb = atomicAdd(&a.cursors[(size_t)(cbase + tid) * a.cursor_stride], cnt);
         dbase = a.dst_bases ? a.dst_bases[tid] : a.out;
         sbeg = (OUT == 1) ? excl + (gb & 1u) : excl;   // same 16-byte phase as the destination
         // tile slot i (i >= sbeg for this digit) goes to dbase[gb + (i - sbeg)]
@@ -705,17 +707,72 @@ join_kernel(JoinArgs a) {
 
         if (newc) {
             mbar_wait(&s_rbar[rslot], (chunk / NR) & 1u);
-            for (uint32_t i = tid; i < nr; i += THREADS) {
-                const uint32_t kk = rbuf[i].x >> a.hash_shift;
-                uint32_t* hp = &head[(kk ^ (kk >> hb)) & hmask];
-                const uint32_t old = atomicExch(hp, i);
-                next[i] = (uint16_t)old;
-                if ((old & 0xFFFFu) != 0xFFFFu) atomicOr(hp, HEAD_MULTI);
+            constexpr int KB = (CAP + THREADS - 1) / THREADS;
+            uint32_t bk[KB];
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                const uint32_t i = q * THREADS + tid;
+                bk[q] = (i < nr) ? rbuf[i].x : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < KB; ++q) {
+                const uint32_t i = q * THREADS + tid;
+                if (i < nr) {
+                    const uint32_t kk = bk[q] >> a.hash_shift;
+                    uint32_t* hp = &head[(kk ^ (kk >> hb)) & hmask];
+                    const uint32_t old = atomicExch(hp, i);
+                    next[i] = (uint16_t)old;
+                    if ((old & 0xFFFFu) != 0xFFFFu) atomicOr(hp, HEAD_MULTI);
+                }
             }
             __syncthreads();
         }
+        if (!MATERIALIZE) {
+            // straight-line probe of up to KP tuples per thread: all shared-memory loads of one
+            // kind are issued back to back; only multi-entry buckets take the chain loop
+            constexpr int KP = (U + THREADS - 1) / THREADS;
+            tup_t t[KP], r[KP];
+            uint32_t w[KP];
+            uint32_t m32 = 0;
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                const uint32_t j = q * THREADS + tid;
+                t[q] = (j < ns) ? sbuf[j] : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                const uint32_t j = q * THREADS + tid;
+                const uint32_t kk = t[q].x >> a.hash_shift;
+                w[q] = (j < ns) ? head[(kk ^ (kk >> hb)) & hmask] : HEAD_EMPTY;
+            }
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                const uint32_t i = w[q] & 0xFFFFu;
+                r[q] = rbuf[i == 0xFFFFu ? 0u : i];
+            }
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                uint32_t i = w[q] & 0xFFFFu;
+                if (i != 0xFFFFu) {
+                    if (r[q].x == t[q].x) {
+                        ++m32;
+                        sum += (unsigned long long)((long long)(int32_t)r[q].y * (long long)(int32_t)t[q].y);
+                    }
+                    if (w[q] & HEAD_MULTI) {
+                        for (i = next[i]; i != 0xFFFFu; i = next[i]) {
+                            const tup_t rr = rbuf[i];
+                            if (rr.x == t[q].x) {
+                                ++m32;
+                                sum += (unsigned long long)((long long)(int32_t)rr.y * (long long)(int32_t)t[q].y);
+                            }
+                        }
+                    }
+                }
+            }
+            matches += m32;
+        }
         const uint32_t rounds = (ns + THREADS - 1) / THREADS;
-        for (uint32_t q = 0; q < rounds; ++q) {
+        for (uint32_t q = 0; MATERIALIZE && q < rounds; ++q) {
             const uint32_t j = q * THREADS + tid;
             if (j < ns) {
                 const tup_t t = sbuf[j];
