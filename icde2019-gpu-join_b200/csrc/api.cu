@@ -75,13 +75,13 @@ struct JoinCfg { int threads, cap, u; join_fn agg, mat; size_t smem_agg, smem_ma
 #define GJ_JC(T, C, U, NR, NS) { T, C, U, join_kernel<T, C, U, NR, NS, false>, join_kernel<T, C, U, NR, NS, true>, \
                                  JoinSmem<C, U, NR, NS, false>::total, JoinSmem<C, U, NR, NS, true>::total }
 static const JoinCfg kJoin[] = {
-    GJ_JC(1024, 4096, 4096, 3, 2),   // 0 default
-    GJ_JC(1024, 4096, 2048, 3, 3),   // 1
-    GJ_JC(512, 4096, 4096, 3, 2),    // 2
-    GJ_JC(1024, 4096, 4096, 2, 2),   // 3
-    GJ_JC(768, 4096, 4096, 3, 2),    // 4
-    GJ_JC(1024, 2048, 2048, 4, 3),   // 5
-    GJ_JC(1024, 4096, 1024, 3, 4),   // 6
+    GJ_JC(1024, 4096, 4096, 3, 3),   // 0 default: two whole steps (build + probe chunk) in flight
+    GJ_JC(1024, 4096, 4096, 3, 2),   // 1
+    GJ_JC(1024, 4096, 4096, 2, 2),   // 2
+    GJ_JC(1024, 4096, 2048, 3, 4),   // 3
+    GJ_JC(768, 4096, 4096, 3, 3),    // 4
+    GJ_JC(512, 4096, 4096, 3, 3),    // 5
+    GJ_JC(1024, 2048, 2048, 4, 4),   // 6
 };
 static const int kNumJoin = (int)(sizeof(kJoin) / sizeof(kJoin[0]));
 
@@ -130,7 +130,7 @@ struct gj_ctx {
     size_t flush_bytes = 0;
     uint32_t launches = 0;
     // options
-    int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 0, opt_scatter_cfg2 = 0,
+    int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
             opt_join_grid = 0, opt_h2d_chunk = 8u << 20;
     bool attrs_set = false;
@@ -155,7 +155,8 @@ static int set_func_attrs(gj_ctx* ctx) {
     }
     for (int i = 0; i < kNumJoin; ++i) {
         CK(cudaFuncSetAttribute(kJoin[i].agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_agg));
-        CK(cudaFuncSetAttribute(kJoin[i].mat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_mat));
+        if (kJoin[i].smem_mat <= (size_t)227 * 1024)
+            CK(cudaFuncSetAttribute(kJoin[i].mat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_mat));
     }
     ctx->attrs_set = true;
     return GJ_OK;
@@ -290,14 +291,14 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
 extern "C" int gj_set_option(gj_ctx* ctx, const char* name, int64_t v) {
     if (!ctx || !name) return fail(GJ_ERR_ARG, "gj_set_option: NULL argument");
     if (!strcmp(name, "scatter_cfg")) {
-        if (v < 0 || v >= kNumScatter) return fail(GJ_ERR_ARG, "scatter_cfg %lld out of range [0,%d)", (long long)v, kNumScatter);
+        if (v < 0 || (v >= kNumScatter && v != 255)) return fail(GJ_ERR_ARG, "scatter_cfg %lld out of range [0,%d) (255 = auto)", (long long)v, kNumScatter);
         ctx->opt_scatter_cfg1 = ctx->opt_scatter_cfg2 = v;
         return GJ_OK;
     }
     int64_t* p = option_slot(ctx, name);
     if (!p) return fail(GJ_ERR_ARG, "unknown option '%s'", name);
     if (v < 0) return fail(GJ_ERR_ARG, "option '%s' must be >= 0", name);
-    if ((p == &ctx->opt_scatter_cfg1 || p == &ctx->opt_scatter_cfg2) && v >= kNumScatter)
+    if ((p == &ctx->opt_scatter_cfg1 || p == &ctx->opt_scatter_cfg2) && v >= kNumScatter && v != 255)
         return fail(GJ_ERR_ARG, "%s %lld out of range [0,%d)", name, (long long)v, kNumScatter);
     if (p == &ctx->opt_join_cfg && v >= kNumJoin) return fail(GJ_ERR_ARG, "join_cfg out of range [0,%d)", kNumJoin);
     if (p == &ctx->opt_radix_bits && v > MAX_RADIX_BITS) return fail(GJ_ERR_ARG, "radix_bits <= %d", MAX_RADIX_BITS);
@@ -338,7 +339,7 @@ static Plan choose_plan(const gj_ctx* ctx, uint64_t n_build, uint32_t forced_bit
     B = std::min<uint32_t>(B, MAX_RADIX_BITS);
     if (B <= (uint32_t)MAX_PASS_BITS) { p.b1 = B; p.b2 = 0; }
     else {
-        p.b1 = ctx->opt_pass1_bits ? (uint32_t)ctx->opt_pass1_bits : (B + 1) / 2;
+        p.b1 = ctx->opt_pass1_bits ? (uint32_t)ctx->opt_pass1_bits : B / 2;   // measured: the smaller fan-out first
         p.b1 = std::min<uint32_t>(std::max<uint32_t>(p.b1, B - MAX_PASS_BITS), MAX_PASS_BITS);
         p.b2 = B - p.b1;
     }
@@ -359,6 +360,15 @@ static int enqueue_hist(gj_ctx* ctx, cudaStream_t s, const void* in, bool packed
     else hist_kernel<false><<<grid, 1024, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
     LAUNCHED();
     return GJ_OK;
+}
+
+// scatter kernel variants: explicit option or, at 255, the measured best per fan-out
+// (profiles/: 8-byte stores win in the first pass, TMA bulk-copy runs win in the second)
+static const ScatterCfg& scatter_cfg1(const gj_ctx* ctx) {
+    return kScatter[ctx->opt_scatter_cfg1 == 255 ? 0 : ctx->opt_scatter_cfg1];
+}
+static const ScatterCfg& scatter_cfg2(const gj_ctx* ctx, uint32_t b2) {
+    return kScatter[ctx->opt_scatter_cfg2 == 255 ? (b2 <= 7 ? 4 : 6) : ctx->opt_scatter_cfg2];
 }
 
 static uint32_t unit_tuples(const gj_ctx* ctx) { return ctx->opt_unit ? (uint32_t)ctx->opt_unit : 8192u; }
@@ -385,7 +395,7 @@ static int enqueue_plan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, c
         a.rel[r].off = m.off; a.rel[r].cur1 = m.cur1; a.rel[r].cur2 = m.cur2; a.rel[r].tiles = m.tiles; a.rel[r].num_tiles = m.num_tiles;
     }
     a.nrel = with_units ? 2 : nrel; a.b1 = pl.b1; a.b2 = pl.b2;
-    const ScatterCfg& c2 = kScatter[ctx->opt_scatter_cfg2];
+    const ScatterCfg& c2 = scatter_cfg2(ctx, pl.b2);
     a.tile = (uint32_t)(c2.threads * c2.ipt);
     a.unit = unit_tuples(ctx);
     a.unit_base = ctx->unit_base; a.units = ctx->units;
@@ -400,7 +410,7 @@ static int enqueue_plan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, c
 static int enqueue_scatter(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role, const Plan& pl, tup_t* dst) {
     if (!rel.n) return GJ_OK;
     const RelMeta& m = ctx->meta[role];
-    const ScatterCfg& c1 = kScatter[ctx->opt_scatter_cfg1];
+    const ScatterCfg& c1 = scatter_cfg1(ctx);
     const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
     ScatterArgs a;
     memset(&a, 0, sizeof(a));
@@ -416,7 +426,7 @@ static int enqueue_scatter(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role
     LAUNCHED();
     CK(cudaEventRecord(ctx->pev[role][1], s));
     if (pl.b2) {
-        const ScatterCfg& c2 = kScatter[ctx->opt_scatter_cfg2];
+        const ScatterCfg& c2 = scatter_cfg2(ctx, pl.b2);
         const uint32_t T2 = (uint32_t)(c2.threads * c2.ipt);
         ScatterArgs b;
         memset(&b, 0, sizeof(b));
@@ -444,7 +454,9 @@ static int fill_pass_times(gj_ctx* ctx, gj_timings* t, const Plan& pl, int nrole
 static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup_t* prb, const Plan& pl,
                         uint64_t n_bld, uint64_t n_prb, bool mat, int32_t* out_b, int32_t* out_p, uint64_t cap) {
     (void)n_bld;
-    const JoinCfg& jc = kJoin[ctx->opt_join_cfg];
+    int cfg = (int)ctx->opt_join_cfg;
+    if (mat && kJoin[cfg].smem_mat > (size_t)227 * 1024) cfg = 2;   // pair staging needs 16 KB: smaller rings
+    const JoinCfg& jc = kJoin[cfg];
     JoinArgs a;
     a.bld = bld; a.prb = prb;
     a.units = ctx->units; a.num_units = ctx->unit_base + (1u << pl.B);
@@ -750,7 +762,7 @@ extern "C" int gj_shuffle_split(gj_ctx* ctx, const int32_t* d_keys, const int32_
     if ((rc = enqueue_scan(ctx, s, 0, 1, n_gpus, false))) return rc;
     if ((rc = enqueue_plan(ctx, s, 0, 1, pl, false))) return rc;
     if (n) {
-        const ScatterCfg& c1 = kScatter[ctx->opt_scatter_cfg1];
+        const ScatterCfg& c1 = scatter_cfg1(ctx);
         const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
         ScatterArgs a;
         memset(&a, 0, sizeof(a));
@@ -784,7 +796,7 @@ extern "C" int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, cons
     CK(cudaMemcpyAsync(ctx->meta[0].cur2, cur, n_gpus * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_dst_bases, d_peer_bases, n_gpus * sizeof(void*), cudaMemcpyHostToDevice, s));
     if (n) {
-        const ScatterCfg& c1 = kScatter[ctx->opt_scatter_cfg1];
+        const ScatterCfg& c1 = scatter_cfg1(ctx);
         const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
         ScatterArgs a;
         memset(&a, 0, sizeof(a));

@@ -29,7 +29,8 @@ typedef uint2 tup_t;  // .x = key bits, .y = payload bits
 constexpr int MAX_RADIX_BITS = 15;    // fine histogram: 2^15 u32 counters = 128 KB of smem
 constexpr int MAX_PASS_BITS = 8;      // fan-out per scatter pass <= 256
 constexpr int NB_MAX = 1 << MAX_PASS_BITS;
-constexpr uint32_t CUR1_STRIDE = 32;  // first-pass cursors live one per 128-byte line (L2 atomics serialise per line)
+constexpr uint32_t CUR1_STRIDE = 1;   // words between first-pass cursors (measured: padding to one cursor per 128-byte line
+                                      // is SLOWER, 0.71 -> 0.58 of HBM peak: a warp's 32 adjacent tickets coalesce into one L2 request)
 constexpr uint32_t EMPTY32 = 0xFFFFFFFFu;
 constexpr uint32_t EMPTY16 = 0xFFFFu;
 
@@ -559,9 +560,9 @@ scatter_kernel(ScatterArgs a) {
 //    table in place over the staged tuples (atomicExch on the head, 16-bit next links: index
 //    chains need no sentinel key and are N:M safe; a MULTI bit in the head marks buckets with
 //    more than one entry so the common single-entry probe never reads a link); then probes with
-//    the staged probe tuples (full 32-bit key compare, 64-bit per-thread accumulators).  Two
-//    head tables alternate, the idle one is cleared during a probe phase: 2 barriers per new
-//    build chunk, 1 per further probe chunk.
+//    the staged probe tuples (full 32-bit key compare, 64-bit per-thread accumulators).  Heads
+//    carry a 15-bit version = build chunk number, so the table is never cleared: 2 barriers per
+//    new build chunk, 1 per further probe chunk.
 //    Hash = xor-fold of the key bits above the radix (+GPU) field: the identity on dense keys
 //    (the reference's choice, common.h:45-47), a real hash otherwise.
 //    Build partitions larger than CAP simply produce more steps (the reference's block-nested
@@ -580,8 +581,10 @@ struct JoinArgs {
 
 constexpr int JOIN_STAGE_PAIRS = 2048;   // staged result pairs per CTA (materialise)
 constexpr uint32_t STEP_DONE = 0xFFFFFFFFu;
-constexpr uint32_t HEAD_EMPTY = 0x0000FFFFu;   // low 16 bits = entry index or 0xFFFF
+// head word = MULTI(1) | version(15) | entry index(16).  A head is live only if its version equals
+// the current build chunk's, so the table is never cleared between chunks.
 constexpr uint32_t HEAD_MULTI = 0x80000000u;   // bucket holds more than one entry
+constexpr uint32_t HEAD_VER_MASK = 0x7FFF0000u;
 
 template <int CAP, int U, int NR, int NS, bool MATERIALIZE>
 struct JoinSmem {
@@ -589,8 +592,8 @@ struct JoinSmem {
     static constexpr size_t sbuf_bytes = (size_t)(U + 2) * sizeof(tup_t);
     static constexpr size_t off_s = rbuf_bytes * NR;
     static constexpr size_t off_head = off_s + sbuf_bytes * NS;
-    static constexpr size_t off_next = off_head + (size_t)2 * CAP * 4;
-    static constexpr size_t off_out = off_next + (size_t)2 * CAP * 2;
+    static constexpr size_t off_next = off_head + (size_t)CAP * 4;
+    static constexpr size_t off_out = off_next + (size_t)CAP * 2;
     static constexpr size_t off_hdr = off_out + (MATERIALIZE ? (size_t)JOIN_STAGE_PAIRS * 8 : 0);
     static constexpr size_t off_bar = off_hdr + (size_t)NS * 32;
     static constexpr size_t total = off_bar + (size_t)(NS + NR) * 8;
@@ -602,8 +605,8 @@ join_kernel(JoinArgs a) {
     using L = JoinSmem<CAP, U, NR, NS, MATERIALIZE>;
     static_assert(CAP < 0xFFFF, "16-bit entry indices");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* s_head = reinterpret_cast<uint32_t*>(smem_raw + L::off_head);   // [2][CAP]
-    uint16_t* s_next = reinterpret_cast<uint16_t*>(smem_raw + L::off_next);   // [2][CAP]
+    uint32_t* head = reinterpret_cast<uint32_t*>(smem_raw + L::off_head);   // [CAP]
+    uint16_t* next = reinterpret_cast<uint16_t*>(smem_raw + L::off_next);   // [CAP]
     int32_t* s_out_b = reinterpret_cast<int32_t*>(smem_raw + L::off_out);
     int32_t* s_out_p = s_out_b + JOIN_STAGE_PAIRS;
     uint4* s_hdr = reinterpret_cast<uint4*>(smem_raw + L::off_hdr);           // [NS][2]
@@ -617,12 +620,27 @@ join_kernel(JoinArgs a) {
     const uint32_t nunits = *a.num_units;
     unsigned long long matches = 0, sum = 0;
 
-    // ---- loader state (thread 0 only) ----
-    uint32_t it_u = blockIdx.x, it_rc = 0, it_sc = 0;
-    uint4 it_d = make_uint4(0, 0, 0, 0), it_dn = make_uint4(0, 0, 0, 0);
-    bool it_valid = false, p_done = false;
-    uint32_t p_steps = 0, p_chunks = 0, last_rc = 0, last_nr = 0;
-    uint32_t c_steps = 0, c_chunk = 0;   // steps fully consumed / chunk the CTA is working on
+    // ---- loader state: lives in shared memory, touched by thread 0 only (keeps it out of every
+    //      other thread's registers) ----
+    struct Loader {
+        uint4 it_d, it_dn;                    // current / prefetched unit descriptor
+        uint32_t it_u, it_rc, it_sc;          // unit, build chunk start, probe chunk start
+        uint32_t p_steps, p_chunks;           // steps / build chunks issued so far
+        uint32_t c_steps, c_chunks;           // steps / build chunks fully consumed
+        uint32_t it_valid, p_done, p_newc;    // p_newc: the next step starts a new build chunk
+    };
+    __shared__ Loader s_ld;
+    uint4& it_d = s_ld.it_d; uint4& it_dn = s_ld.it_dn;
+    uint32_t& it_u = s_ld.it_u; uint32_t& it_rc = s_ld.it_rc; uint32_t& it_sc = s_ld.it_sc;
+    uint32_t& p_steps = s_ld.p_steps; uint32_t& p_chunks = s_ld.p_chunks;
+    uint32_t& c_steps = s_ld.c_steps; uint32_t& c_chunks = s_ld.c_chunks;
+    uint32_t& it_valid = s_ld.it_valid; uint32_t& p_done = s_ld.p_done; uint32_t& p_newc = s_ld.p_newc;
+    if (tid == 0) {
+        it_d = make_uint4(0, 0, 0, 0); it_dn = make_uint4(0, 0, 0, 0);
+        it_u = blockIdx.x; it_rc = 0; it_sc = 0;
+        p_steps = 0; p_chunks = 0; c_steps = 0; c_chunks = 0;
+        it_valid = 0; p_done = 0; p_newc = 1;
+    }
     // returns true if a step was issued and another one may fit
     auto try_issue = [&]() -> bool {
         if (p_done || p_steps - c_steps >= (uint32_t)NS) return false;
@@ -630,44 +648,51 @@ join_kernel(JoinArgs a) {
         if (!it_valid) {
             s_hdr[2 * sslot] = make_uint4(STEP_DONE, 0, 0, 0);
             mbar_arrive_expect_tx(&s_sbar[sslot], 0);
-            p_done = true;
+            p_done = 1;
             ++p_steps;
             return false;
         }
+        // build chunk p_chunks reuses the slot of chunk p_chunks - NR, which must be consumed
+        if (p_newc && p_chunks >= c_chunks + (uint32_t)NR) return false;
         const uint32_t nr = min((uint32_t)CAP, it_d.w - it_rc), ns = min((uint32_t)U, it_d.y - it_sc);
-        const bool newc = (p_chunks == 0) || it_rc != last_rc || nr != last_nr;
-        // chunk p_chunks reuses the slot of chunk p_chunks - NR, which must be fully consumed
-        if (newc && p_chunks >= c_chunk + (uint32_t)NR) return false;
-        const uint32_t chunk = newc ? p_chunks : p_chunks - 1u;
-        const uint32_t rskip = it_rc & 1u, sskip = it_sc & 1u;
-        s_hdr[2 * sslot] = make_uint4(ns, sskip, newc ? 1u : 0u, chunk);
+        const uint32_t chunk = p_newc ? p_chunks : p_chunks - 1u;
+        const uint32_t rc = it_rc, sc = it_sc;
+        const bool newc = p_newc != 0;
+        // advance: probe chunks innermost, then build chunks, then the next unit of this CTA;
+        // the step is the last of its build chunk iff the next step loads a different one
+        bool lastc = false;
+        it_sc += U;
+        if (it_sc >= it_d.y) {
+            it_sc = it_d.x;
+            it_rc += CAP;
+            lastc = true;
+            if (it_rc >= it_d.w) {
+                it_u += gridDim.x;
+                it_valid = it_u < nunits ? 1u : 0u;
+                const uint4 prev = it_d;
+                it_d = it_dn;                                   // prefetched one unit ahead
+                it_rc = it_d.z; it_sc = it_d.x;
+                if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
+                // consecutive units of one (hot) partition share a single-chunk build side
+                if (it_valid && it_d.z == prev.z && it_d.w == prev.w && prev.w - prev.z <= (uint32_t)CAP) lastc = false;
+            }
+        }
+        p_newc = lastc ? 1u : 0u;
+        const uint32_t rskip = rc & 1u, sskip = sc & 1u;
+        s_hdr[2 * sslot] = make_uint4(ns, sskip, (newc ? 1u : 0u) | (lastc ? 2u : 0u), chunk);
         s_hdr[2 * sslot + 1] = make_uint4(nr, rskip, 0, 0);
         fence_proxy_async();
         if (newc) {
             const uint32_t rslot = chunk % NR;
             const uint32_t rbytes = ((nr + rskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
             mbar_arrive_expect_tx(&s_rbar[rslot], rbytes);
-            bulk_g2s(smem_raw + L::rbuf_bytes * rslot, a.bld + (it_rc - rskip), rbytes, &s_rbar[rslot]);
-            last_rc = it_rc; last_nr = nr;
+            bulk_g2s(smem_raw + L::rbuf_bytes * rslot, a.bld + (rc - rskip), rbytes, &s_rbar[rslot]);
             ++p_chunks;
         }
         const uint32_t sbytes = ((ns + sskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
         mbar_arrive_expect_tx(&s_sbar[sslot], sbytes);
-        bulk_g2s(smem_raw + L::off_s + L::sbuf_bytes * sslot, a.prb + (it_sc - sskip), sbytes, &s_sbar[sslot]);
+        bulk_g2s(smem_raw + L::off_s + L::sbuf_bytes * sslot, a.prb + (sc - sskip), sbytes, &s_sbar[sslot]);
         ++p_steps;
-        // advance: probe chunks innermost, then build chunks, then the next unit of this CTA
-        it_sc += U;
-        if (it_sc >= it_d.y) {
-            it_sc = it_d.x;
-            it_rc += CAP;
-            if (it_rc >= it_d.w) {
-                it_u += gridDim.x;
-                it_valid = it_u < nunits;
-                it_d = it_dn;                                   // prefetched one unit ahead
-                it_rc = it_d.z; it_sc = it_d.x;
-                if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
-            }
-        }
         return true;
     };
 
@@ -677,11 +702,12 @@ join_kernel(JoinArgs a) {
         fence_mbar_init();
         if (MATERIALIZE) s_cnt = 0;
     }
+    // version 0 is never used by a chunk (versions are 1..0x7FFF), so an all-zero table is empty
     for (uint32_t i = tid; i < (uint32_t)CAP / 4; i += THREADS)
-        reinterpret_cast<uint4*>(s_head)[i] = make_uint4(HEAD_EMPTY, HEAD_EMPTY, HEAD_EMPTY, HEAD_EMPTY);
+        reinterpret_cast<uint4*>(head)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     if (tid == 0) {
-        it_valid = it_u < nunits;
+        it_valid = it_u < nunits ? 1u : 0u;
         if (it_valid) {
             it_d = __ldg(a.units + it_u);
             it_rc = it_d.z; it_sc = it_d.x;
@@ -696,16 +722,20 @@ join_kernel(JoinArgs a) {
         const uint4 h0 = s_hdr[2 * sslot];
         if (h0.x == STEP_DONE) break;
         const uint4 h1 = s_hdr[2 * sslot + 1];
-        const uint32_t ns = h0.x, nr = h1.x, chunk = h0.w, rslot = chunk % NR, tb = chunk & 1u;
+        const uint32_t ns = h0.x, nr = h1.x, chunk = h0.w, rslot = chunk % NR;
         const bool newc = (h0.z & 1u) != 0;
         const tup_t* rbuf = reinterpret_cast<const tup_t*>(smem_raw + L::rbuf_bytes * rslot) + h1.y;
         const tup_t* sbuf = reinterpret_cast<const tup_t*>(smem_raw + L::off_s + L::sbuf_bytes * sslot) + h0.y;
-        uint32_t* head = s_head + tb * CAP;
-        uint16_t* next = s_next + tb * CAP;
         const uint32_t hb = 32u - __clz(max(nr, 32u) - 1u);   // ceil(log2(nr)), >= 5
         const uint32_t hmask = (1u << hb) - 1u;
+        const uint32_t ver = ((chunk % 0x7FFFu) + 1u) << 16;  // 1..0x7FFF in bits 16..30
 
         if (newc) {
+            if (chunk && (chunk % 0x7FFFu) == 0u) {   // version wrap: wipe stale heads (rare)
+                for (uint32_t i = tid; i < (uint32_t)CAP / 4; i += THREADS)
+                    reinterpret_cast<uint4*>(head)[i] = make_uint4(0u, 0u, 0u, 0u);
+                __syncthreads();
+            }
             mbar_wait(&s_rbar[rslot], (chunk / NR) & 1u);
             constexpr int KB = (CAP + THREADS - 1) / THREADS;
             uint32_t bk[KB];
@@ -720,9 +750,10 @@ join_kernel(JoinArgs a) {
                 if (i < nr) {
                     const uint32_t kk = bk[q] >> a.hash_shift;
                     uint32_t* hp = &head[(kk ^ (kk >> hb)) & hmask];
-                    const uint32_t old = atomicExch(hp, i);
-                    next[i] = (uint16_t)old;
-                    if ((old & 0xFFFFu) != 0xFFFFu) atomicOr(hp, HEAD_MULTI);
+                    const uint32_t old = atomicExch(hp, ver | i);
+                    const bool live = (old & HEAD_VER_MASK) == ver;
+                    next[i] = live ? (uint16_t)old : (uint16_t)0xFFFFu;
+                    if (live) atomicOr(hp, HEAD_MULTI);
                 }
             }
             __syncthreads();
@@ -743,23 +774,22 @@ join_kernel(JoinArgs a) {
             for (int q = 0; q < KP; ++q) {
                 const uint32_t j = q * THREADS + tid;
                 const uint32_t kk = t[q].x >> a.hash_shift;
-                w[q] = (j < ns) ? head[(kk ^ (kk >> hb)) & hmask] : HEAD_EMPTY;
+                w[q] = (j < ns) ? head[(kk ^ (kk >> hb)) & hmask] : 0u;
             }
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
-                const uint32_t i = w[q] & 0xFFFFu;
-                r[q] = rbuf[i == 0xFFFFu ? 0u : i];
+                const bool live = (w[q] & HEAD_VER_MASK) == ver;
+                r[q] = rbuf[live ? (w[q] & 0xFFFFu) : 0u];
             }
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
-                uint32_t i = w[q] & 0xFFFFu;
-                if (i != 0xFFFFu) {
+                if ((w[q] & HEAD_VER_MASK) == ver) {
                     if (r[q].x == t[q].x) {
                         ++m32;
                         sum += (unsigned long long)((long long)(int32_t)r[q].y * (long long)(int32_t)t[q].y);
                     }
                     if (w[q] & HEAD_MULTI) {
-                        for (i = next[i]; i != 0xFFFFu; i = next[i]) {
+                        for (uint32_t i = next[w[q] & 0xFFFFu]; i != 0xFFFFu; i = next[i]) {
                             const tup_t rr = rbuf[i];
                             if (rr.x == t[q].x) {
                                 ++m32;
@@ -778,56 +808,48 @@ join_kernel(JoinArgs a) {
                 const tup_t t = sbuf[j];
                 const uint32_t kk = t.x >> a.hash_shift;
                 const uint32_t w = head[(kk ^ (kk >> hb)) & hmask];
-                uint32_t i = w & 0xFFFFu;
+                uint32_t i = ((w & HEAD_VER_MASK) == ver) ? (w & 0xFFFFu) : 0xFFFFu;
                 while (i != 0xFFFFu) {
                     const tup_t r = rbuf[i];
                     if (r.x == t.x) {
                         ++matches;
                         sum += (unsigned long long)((long long)(int32_t)r.y * (long long)(int32_t)t.y);
-                        if (MATERIALIZE) {
-                            const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                            if (pos < (uint32_t)JOIN_STAGE_PAIRS) {
-                                s_out_b[pos] = (int32_t)r.y;
-                                s_out_p[pos] = (int32_t)t.y;
-                            } else {   // staging full inside a round: rare direct path
-                                const unsigned long long g = atomicAdd(&a.result[2], 1ull);
-                                if (g < a.cap) {
-                                    a.out_bld_pay[g] = (int32_t)r.y;
-                                    a.out_prb_pay[g] = (int32_t)t.y;
-                                }
+                        const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                        if (pos < (uint32_t)JOIN_STAGE_PAIRS) {
+                            s_out_b[pos] = (int32_t)r.y;
+                            s_out_p[pos] = (int32_t)t.y;
+                        } else {   // staging full inside a round: rare direct path
+                            const unsigned long long g = atomicAdd(&a.result[2], 1ull);
+                            if (g < a.cap) {
+                                a.out_bld_pay[g] = (int32_t)r.y;
+                                a.out_prb_pay[g] = (int32_t)t.y;
                             }
                         }
                     }
                     i = (w & HEAD_MULTI) ? (uint32_t)next[i] : 0xFFFFu;
                 }
             }
-            if (MATERIALIZE) {
+            __syncthreads();
+            const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE_PAIRS);
+            if (c + THREADS > (uint32_t)JOIN_STAGE_PAIRS) {
+                if (tid == 0) s_base = atomicAdd(&a.result[2], (unsigned long long)c);
                 __syncthreads();
-                const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE_PAIRS);
-                if (c + THREADS > (uint32_t)JOIN_STAGE_PAIRS) {
-                    if (tid == 0) s_base = atomicAdd(&a.result[2], (unsigned long long)c);
-                    __syncthreads();
-                    const unsigned long long g0 = s_base;
-                    for (uint32_t i = tid; i < c; i += THREADS) {
-                        if (g0 + i < a.cap) {
-                            a.out_bld_pay[g0 + i] = s_out_b[i];
-                            a.out_prb_pay[g0 + i] = s_out_p[i];
-                        }
+                const unsigned long long g0 = s_base;
+                for (uint32_t i = tid; i < c; i += THREADS) {
+                    if (g0 + i < a.cap) {
+                        a.out_bld_pay[g0 + i] = s_out_b[i];
+                        a.out_prb_pay[g0 + i] = s_out_p[i];
                     }
-                    __syncthreads();
-                    if (tid == 0) s_cnt = 0;
-                    __syncthreads();
                 }
+                __syncthreads();
+                if (tid == 0) s_cnt = 0;
+                __syncthreads();
             }
         }
-        if (newc) {   // the other table (previous chunk's) is idle: clear it for the next chunk
-            uint32_t* other = s_head + (tb ^ 1u) * CAP;
-            for (uint32_t i = tid; i < (uint32_t)CAP / 4; i += THREADS)
-                reinterpret_cast<uint4*>(other)[i] = make_uint4(HEAD_EMPTY, HEAD_EMPTY, HEAD_EMPTY, HEAD_EMPTY);
-        }
-        __syncthreads();                 // everyone is done with this step's slots
+        __syncthreads();                 // everyone is done with this step's slots (and the table)
         if (tid == 0) {
-            c_steps = k + 1; c_chunk = chunk;
+            c_steps = k + 1;
+            c_chunks = chunk + ((h0.z & 2u) ? 1u : 0u);
             while (try_issue()) {}
         }
     }

@@ -32,8 +32,9 @@ def eng(gj, torch_cuda):
 
 
 def reset(eng):
-    for k in ("radix_bits", "pass1_bits", "scatter_cfg", "join_cfg", "unit_tuples", "gpu_bits"):
+    for k in ("radix_bits", "pass1_bits", "join_cfg", "unit_tuples", "gpu_bits"):
         eng.set_option(k, 0)
+    eng.set_option("scatter_cfg", 255)   # auto
     eng.set_option("part_target", 4096)
 
 

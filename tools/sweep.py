@@ -41,8 +41,9 @@ def main():
         pass
 
     def run(tag, **opts):
-        for k in ("radix_bits", "pass1_bits", "scatter_cfg", "scatter_cfg1", "scatter_cfg2", "join_cfg", "unit_tuples", "join_grid"):
+        for k in ("radix_bits", "pass1_bits", "join_cfg", "unit_tuples", "join_grid"):
             eng.set_option(k, 0)
+        eng.set_option("scatter_cfg", 255)
         for k, v in opts.items():
             eng.set_option(k, v)
         ts = []
@@ -74,17 +75,13 @@ def main():
     if "join" in what:
         for c in range(eng.get_option("num_join_cfgs")):
             run("join", join_cfg=c)
-        for c in (0, 2, 5):
-            for pt in (2048,):
-                run("join_small_parts", join_cfg=c, part_target=pt)
-        eng.set_option("part_target", 4096)
     if "bits" in what:
         for b in (13, 14, 15):
             for p1 in (7, 8):
                 if b - p1 <= 8:
                     run("bits", radix_bits=b, pass1_bits=p1)
     if "combo" in what:
-        for p1, c1s, c2s in ((7, (0, 4, 6), (0, 4, 6)), (8, (0, 3), (4, 6))):
+        for p1, c1s, c2s in ((7, (0, 3, 4, 6, 8), (0, 4, 6)), (8, (0, 3), (4, 6))):
             for c1 in c1s:
                 for c2 in c2s:
                     run("combo", radix_bits=15, pass1_bits=p1, scatter_cfg1=c1, scatter_cfg2=c2)
