@@ -440,7 +440,12 @@ def multi_gpu(args):
                                   "achieved": 16.0 * (r.local_R + r.local_S) * (2 if tm.get("pass2_bits") else 1) / (tm["part_ms"] * 1e-3) / 1e9 if tm.get("part_ms") else None,
                                   "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
                                   "local_phases_ms": {k: tm.get(k) for k in ("hist_ms", "part_ms", "join_ms", "total_ms")}},
-                     "shuffle": {"mode": args.shuffle, "tuples_per_gpu_out": int((r.local_R + r.local_S) * (world - 1) / world)},
+                     "shuffle": {"mode": args.shuffle, "tuples_per_gpu_out": int((nR + nS) * (world - 1) / world),
+                                 "scatter_kernel_ms": tm.get("shuffle_scatter_ms"),
+                                 "nvlink_out_GBs_per_gpu": (8.0 * (nR + nS) * (world - 1) / world / (tm["shuffle_scatter_ms"] * 1e-3) / 1e9)
+                                 if tm.get("shuffle_scatter_ms") else None,
+                                 "nvlink_peak_GBs": 770.0,
+                                 "note": "peer-store scatter: one kernel reads the local shard (8 B/tuple HBM) and stores each run into the destination GPU's HBM over NVLink"},
                      "checked": f"matches == checksum == {expect} every step"})
         if line["roofline"]["achieved"]:
             line["roofline"]["frac"] = line["roofline"]["achieved"] / peak

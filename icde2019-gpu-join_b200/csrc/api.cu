@@ -129,6 +129,7 @@ struct gj_ctx {
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     uint32_t launches = 0;
+    float last_shuffle_ms = 0.f;
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
@@ -317,6 +318,7 @@ extern "C" int gj_get_option(gj_ctx* ctx, const char* name, int64_t* v) {
     if (!strcmp(name, "num_scatter_cfgs")) { *v = kNumScatter; return GJ_OK; }
     if (!strcmp(name, "num_join_cfgs")) { *v = kNumJoin; return GJ_OK; }
     if (!strcmp(name, "sm_count")) { *v = ctx->sm_count; return GJ_OK; }
+    if (!strcmp(name, "last_shuffle_us")) { *v = (int64_t)(ctx->last_shuffle_ms * 1000.f); return GJ_OK; }
     int64_t* p = option_slot(ctx, name);
     if (!p) return fail(GJ_ERR_ARG, "unknown option '%s'", name);
     *v = *p;
@@ -803,10 +805,14 @@ extern "C" int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, cons
         a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = nullptr;
         a.dst_bases = ctx->d_dst_bases;
         a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2; a.cursor_stride = 1;
+        CK(cudaEventRecord(ctx->ev[0], s));
         c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, scatter_smem(c1), s>>>(a);
         LAUNCHED();
+        CK(cudaEventRecord(ctx->ev[1], s));
     }
     CK(cudaStreamSynchronize(s));
+    ctx->last_shuffle_ms = 0.f;
+    if (n) CK(cudaEventElapsedTime(&ctx->last_shuffle_ms, ctx->ev[0], ctx->ev[1]));
     return GJ_OK;
 }
 

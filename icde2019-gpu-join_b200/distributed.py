@@ -57,7 +57,7 @@ class ShardedResult:
 class GpuOps:
     """Device steps backed by libgpujoin.so (the product path)."""
 
-    def __init__(self, max_R: int, max_S: int, device: int, slack: float = 1.3):
+    def __init__(self, max_R: int, max_S: int, device: int, slack: float = 1.3, with_send_buffers: bool = True):
         import torch
         from .engine import JoinEngine
         self.torch = torch
@@ -68,10 +68,13 @@ class GpuOps:
         self.stream = torch.cuda.Stream(device)
         self.engine.use_torch_stream(self.stream)
         dev = torch.device("cuda", device)
-        self.send = [torch.empty(self.cap_R, dtype=torch.int64, device=dev),
-                     torch.empty(self.cap_S, dtype=torch.int64, device=dev)]
-        self.recv = [torch.empty(self.cap_R, dtype=torch.int64, device=dev),
-                     torch.empty(self.cap_S, dtype=torch.int64, device=dev)]
+        self.dev = dev
+        self.send = self.recv = None
+        if with_send_buffers:   # only the NCCL shuffle stages tuples; peer stores need neither
+            self.send = [torch.empty(self.cap_R, dtype=torch.int64, device=dev),
+                         torch.empty(self.cap_S, dtype=torch.int64, device=dev)]
+            self.recv = [torch.empty(self.cap_R, dtype=torch.int64, device=dev),
+                         torch.empty(self.cap_S, dtype=torch.int64, device=dev)]
 
     def configure(self, radix_bits: int, gpu_bits: int):
         self.engine.set_option("radix_bits", radix_bits)
@@ -85,6 +88,14 @@ class GpuOps:
 
     def scatter_peers(self, keys, pays, G, shift, peer_ptrs, offsets):
         self.engine.shuffle_scatter_peers(keys, pays, G, shift, peer_ptrs, offsets)
+        return self.engine.get_option("last_shuffle_us") * 1e-3   # kernel time, ms
+
+    def exchange_counts(self, dist, group, mine):
+        """All ranks' count vectors in ONE small NCCL all-gather (doubles as a barrier)."""
+        t = self.torch.tensor([int(x) for x in mine], dtype=self.torch.int64, device=self.dev)
+        out = self.torch.empty(dist.get_world_size(group) * t.numel(), dtype=self.torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out.cpu().numpy().reshape(dist.get_world_size(group), -1)
 
     def local_join(self, nR, nS):
         res = self.engine.join_aggregate_tuples(self.recv[0], nR, self.recv[1], nS)
@@ -117,7 +128,8 @@ class ShardedJoin:
         self.gpu_bits = int(math.log2(self.world))
         self.mode = mode
         self.part_target = part_target
-        self.ops = ops if ops is not None else GpuOps(max_local_R, max_local_S, device)
+        self.ops = ops if ops is not None else GpuOps(max_local_R, max_local_S, device,
+                                                      with_send_buffers=(mode == "nccl"))
         self.max_local = (max_local_R, max_local_S)
         self._peers = None
         if mode == "p2p":
@@ -169,6 +181,8 @@ class ShardedJoin:
 
     # -- helpers ---------------------------------------------------------------------------
     def _all_gather_counts(self, mine: np.ndarray) -> np.ndarray:
+        if hasattr(self.ops, "exchange_counts"):
+            return self.ops.exchange_counts(self.dist, self.group, mine)
         out = [None] * self.world
         self.dist.all_gather_object(out, [int(x) for x in mine], group=self.group)
         return np.array(out, dtype=np.int64)
@@ -202,23 +216,27 @@ class ShardedJoin:
             if hasattr(ops, "stream"):
                 ops.stream.synchronize()
         else:
-            all_counts = []
-            for which, (k, p) in enumerate(rels):
-                all_counts.append(self._all_gather_counts(ops.count(k, G, shift)))
-            dist.barrier(group=self.group)   # peers are done reading their receive buffers
+            # both relations' counts travel in one all-gather, which is also the barrier that
+            # tells every rank its peers are done reading their receive buffers
+            mine = np.concatenate([ops.count(k, G, shift) for k, _ in rels])
+            both = self._all_gather_counts(mine)
+            all_counts = [both[:, :G], both[:, G:]]
+            shuffle_ms = 0.0
             for which, (k, p) in enumerate(rels):
                 recv_counts, _, write_at = receive_layout(all_counts[which], rank)
                 n_in = int(recv_counts.sum())
                 cap = ops.cap_R if which == 0 else ops.cap_S
                 if n_in > cap:
                     raise RuntimeError(f"rank {rank}: receives {n_in} tuples, capacity {cap}")
-                ops.scatter_peers(k, p, G, shift, self._peers[which], write_at)
+                shuffle_ms += ops.scatter_peers(k, p, G, shift, self._peers[which], write_at) or 0.0
                 local_n[which] = n_in
             dist.barrier(group=self.group)   # every rank's stores have landed
         if self.mode == "p2p":
             m, c, tm = ops.local_join_ptrs(self._own[0], local_n[0], self._own[1], local_n[1])
         else:
             m, c, tm = ops.local_join(local_n[0], local_n[1])
+        if self.mode == "p2p":
+            tm = dict(tm, shuffle_scatter_ms=shuffle_ms)
         res = ops.result_tensor(m, c)
         dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
         vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
