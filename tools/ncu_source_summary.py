@@ -10,8 +10,9 @@ rep, rx = sys.argv[1], sys.argv[2]
 inst = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{rx}"],
                      capture_output=True, text=True).stdout
-blocks = out.split('"Kernel Name",')
-blk = blocks[1 + inst]
+import re
+blocks = [b for b in out.split('"Kernel Name",')[1:] if re.search(rx, b.split("\n")[0])]
+blk = blocks[inst]
 lines = blk.split("\n")
 print("kernel:", lines[0][:120])
 rows = list(csv.reader(io.StringIO("\n".join(lines[1:]))))
