@@ -72,16 +72,16 @@ static size_t scatter_smem(const ScatterCfg& c) {
 typedef void (*join_fn)(JoinArgs);
 struct JoinCfg { int threads, cap, u; join_fn agg, mat; size_t smem_agg, smem_mat; };
 // <threads, build chunk, probe chunk, R ring slots, S ring slots>
-#define GJ_JC(T, C, U, NR, NS) { T, C, U, join_kernel<T, C, U, NR, NS, false>, join_kernel<T, C, U, NR, NS, true>, \
+#define GJ_JC(T, C, U, NR, NS, OPT) { T, C, U, join_kernel<T, C, U, NR, NS, false, OPT>, join_kernel<T, C, U, NR, NS, true, OPT>, \
                                  JoinSmem<C, U, NR, NS, false>::total, JoinSmem<C, U, NR, NS, true>::total }
 static const JoinCfg kJoin[] = {
-    GJ_JC(1024, 4096, 4096, 3, 3),   // 0 default: two whole steps (build + probe chunk) in flight
-    GJ_JC(1024, 4096, 4096, 3, 2),   // 1
-    GJ_JC(1024, 4096, 4096, 2, 2),   // 2
-    GJ_JC(1024, 4096, 2048, 3, 4),   // 3
-    GJ_JC(768, 4096, 4096, 3, 3),    // 4
-    GJ_JC(512, 4096, 4096, 3, 3),    // 5
-    GJ_JC(1024, 2048, 2048, 4, 4),   // 6
+    GJ_JC(1024, 4096, 4096, 3, 3, false),  // 0 default: two whole steps (build + probe chunk) in flight
+    GJ_JC(1024, 4096, 4096, 3, 3, true),   // 1 optimistic (atomic-free when collision-free) build
+    GJ_JC(1024, 4096, 4096, 2, 2, false),  // 2 small rings (fits the 16 KB pair staging when materialising)
+    GJ_JC(1024, 4096, 4096, 2, 2, true),   // 3
+    GJ_JC(768, 4096, 4096, 3, 3, true),    // 4
+    GJ_JC(512, 4096, 4096, 3, 3, true),    // 5
+    GJ_JC(1024, 4096, 2048, 3, 4, true),   // 6
 };
 static const int kNumJoin = (int)(sizeof(kJoin) / sizeof(kJoin[0]));
 

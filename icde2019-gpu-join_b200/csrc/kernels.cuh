@@ -599,7 +599,7 @@ struct JoinSmem {
     static constexpr size_t total = off_bar + (size_t)(NS + NR) * 8;
 };
 
-template <int THREADS, int CAP, int U, int NR, int NS, bool MATERIALIZE>
+template <int THREADS, int CAP, int U, int NR, int NS, bool MATERIALIZE, bool OPTIMISTIC>
 __global__ void __launch_bounds__(THREADS, 1)
 join_kernel(JoinArgs a) {
     using L = JoinSmem<CAP, U, NR, NS, MATERIALIZE>;
@@ -746,19 +746,57 @@ join_kernel(JoinArgs a) {
                 const uint32_t i = q * THREADS + tid;
                 bk[q] = (i < nr) ? rbuf[i].x : 0u;
             }
+            if (OPTIMISTIC) {
+                // Optimistic build: plain stores, last writer wins; a thread whose entry survived
+                // owns a single-entry bucket.  With dense unique keys (no hash collisions) nobody
+                // loses and the build needs no atomics at all; losers (collisions, duplicate keys)
+                // are chained in with the atomic path afterwards.
+                uint32_t hq[KB];
 #pragma unroll
-            for (int q = 0; q < KB; ++q) {
-                const uint32_t i = q * THREADS + tid;
-                if (i < nr) {
+                for (int q = 0; q < KB; ++q) {
+                    const uint32_t i = q * THREADS + tid;
                     const uint32_t kk = bk[q] >> a.hash_shift;
-                    uint32_t* hp = &head[(kk ^ (kk >> hb)) & hmask];
-                    const uint32_t old = atomicExch(hp, ver | i);
-                    const bool live = (old & HEAD_VER_MASK) == ver;
-                    next[i] = live ? (uint16_t)old : (uint16_t)0xFFFFu;
-                    if (live) atomicOr(hp, HEAD_MULTI);
+                    hq[q] = (kk ^ (kk >> hb)) & hmask;
+                    if (i < nr) head[hq[q]] = ver | i;
                 }
+                __syncthreads();
+                uint32_t lost = 0;
+#pragma unroll
+                for (int q = 0; q < KB; ++q) {
+                    const uint32_t i = q * THREADS + tid;
+                    if (i < nr) {
+                        if (head[hq[q]] == (ver | i)) next[i] = (uint16_t)0xFFFFu;
+                        else lost |= 1u << q;
+                    }
+                }
+                if (__syncthreads_or((int)lost)) {
+#pragma unroll
+                    for (int q = 0; q < KB; ++q) {
+                        if (lost & (1u << q)) {
+                            const uint32_t i = q * THREADS + tid;
+                            uint32_t* hp = &head[hq[q]];
+                            const uint32_t old = atomicExch(hp, ver | i);
+                            next[i] = (uint16_t)old;      // the winner or an earlier loser: always live
+                            atomicOr(hp, HEAD_MULTI);
+                        }
+                    }
+                    __syncthreads();
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < KB; ++q) {
+                    const uint32_t i = q * THREADS + tid;
+                    if (i < nr) {
+                        const uint32_t kk = bk[q] >> a.hash_shift;
+                        uint32_t* hp = &head[(kk ^ (kk >> hb)) & hmask];
+                        const uint32_t old = atomicExch(hp, ver | i);
+                        const bool live = (old & HEAD_VER_MASK) == ver;
+                        next[i] = live ? (uint16_t)old : (uint16_t)0xFFFFu;
+                        if (live) atomicOr(hp, HEAD_MULTI);
+                    }
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
         if (!MATERIALIZE) {
             // straight-line probe of up to KP tuples per thread: all shared-memory loads of one
