@@ -623,20 +623,23 @@ join_kernel(JoinArgs a) {
     // ---- loader state: lives in shared memory, touched by thread 0 only (keeps it out of every
     //      other thread's registers) ----
     struct Loader {
-        uint4 it_d, it_dn;                    // current / prefetched unit descriptor
+        uint4 it_d;                           // current unit descriptor
         uint32_t it_u, it_rc, it_sc;          // unit, build chunk start, probe chunk start
         uint32_t p_steps, p_chunks;           // steps / build chunks issued so far
         uint32_t c_steps, c_chunks;           // steps / build chunks fully consumed
         uint32_t it_valid, p_done, p_newc;    // p_newc: the next step starts a new build chunk
     };
     __shared__ Loader s_ld;
-    uint4& it_d = s_ld.it_d; uint4& it_dn = s_ld.it_dn;
+    uint4& it_d = s_ld.it_d;
+    // the descriptor prefetched one unit ahead stays in registers: storing a just-issued global
+    // load into shared memory would make thread 0 wait ~1k cycles for it inside every issue
+    uint4 it_dn = make_uint4(0, 0, 0, 0);
     uint32_t& it_u = s_ld.it_u; uint32_t& it_rc = s_ld.it_rc; uint32_t& it_sc = s_ld.it_sc;
     uint32_t& p_steps = s_ld.p_steps; uint32_t& p_chunks = s_ld.p_chunks;
     uint32_t& c_steps = s_ld.c_steps; uint32_t& c_chunks = s_ld.c_chunks;
     uint32_t& it_valid = s_ld.it_valid; uint32_t& p_done = s_ld.p_done; uint32_t& p_newc = s_ld.p_newc;
     if (tid == 0) {
-        it_d = make_uint4(0, 0, 0, 0); it_dn = make_uint4(0, 0, 0, 0);
+        it_d = make_uint4(0, 0, 0, 0);
         it_u = blockIdx.x; it_rc = 0; it_sc = 0;
         p_steps = 0; p_chunks = 0; c_steps = 0; c_chunks = 0;
         it_valid = 0; p_done = 0; p_newc = 1;
