@@ -130,6 +130,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier over a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -549,8 +556,12 @@ scatter_kernel(ScatterArgs a) {
 // 5. Per-partition hash join: persistent CTAs (one per SM), static round-robin over the unit
 //    list, fed by TMA bulk copies into two shared-memory rings.
 //    A unit {probe range, build partition} is processed in steps of (build chunk <= CAP tuples)
-//    x (probe chunk <= U tuples).  Thread 0 runs an iterator ahead of the CTA and issues bulk
-//    async copies (cp.async.bulk, completion on mbarriers): every step's probe chunk goes into
+//    x (probe chunk <= U tuples).  A dedicated LOADER WARP (one lane) runs an iterator ahead of
+//    the consumer warps and issues bulk async copies (cp.async.bulk, completion on "full"
+//    mbarriers; slots come back through "empty" mbarriers; the consumers synchronise among
+//    themselves with a named barrier, so the ~1.3k-cycle issue path is off their critical
+//    path -- as thread 0's side job it made 31 warps wait at the post-build barrier, ncu):
+//    every step's probe chunk goes into
 //    the S ring (NS slots); a build chunk goes into the R ring (NR slots) only when it differs
 //    from the previous step's -- a build partition that is probed by many chunks / units
 //    (large or skewed probe sides) is loaded and hashed ONCE.  All HBM traffic of the join is
@@ -596,7 +607,7 @@ struct JoinSmem {
     static constexpr size_t off_out = off_next + (size_t)CAP * 2;
     static constexpr size_t off_hdr = off_out + (MATERIALIZE ? (size_t)JOIN_STAGE_PAIRS * 8 : 0);
     static constexpr size_t off_bar = off_hdr + (size_t)NS * 32;
-    static constexpr size_t total = off_bar + (size_t)(NS + NR) * 8;
+    static constexpr size_t total = off_bar + (size_t)(NS + NR) * 16;   // full + empty barriers
 };
 
 template <int THREADS, int CAP, int U, int NR, int NS, bool MATERIALIZE, bool OPTIMISTIC>
@@ -604,14 +615,18 @@ __global__ void __launch_bounds__(THREADS, 1)
 join_kernel(JoinArgs a) {
     using L = JoinSmem<CAP, U, NR, NS, MATERIALIZE>;
     static_assert(CAP < 0xFFFF, "16-bit entry indices");
+    constexpr uint32_t NC = THREADS - 32;      // consumer threads: warps 0 .. THREADS/32-2
+    constexpr uint32_t BAR_C = 1;              // named barrier of the consumer warps
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* head = reinterpret_cast<uint32_t*>(smem_raw + L::off_head);   // [CAP]
     uint16_t* next = reinterpret_cast<uint16_t*>(smem_raw + L::off_next);   // [CAP]
     int32_t* s_out_b = reinterpret_cast<int32_t*>(smem_raw + L::off_out);
     int32_t* s_out_p = s_out_b + JOIN_STAGE_PAIRS;
     uint4* s_hdr = reinterpret_cast<uint4*>(smem_raw + L::off_hdr);           // [NS][2]
-    uint64_t* s_sbar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);    // [NS]
-    uint64_t* s_rbar = s_sbar + NS;                                           // [NR]
+    uint64_t* s_sfull = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);   // [NS]
+    uint64_t* s_rfull = s_sfull + NS;                                         // [NR]
+    uint64_t* s_sempty = s_rfull + NR;                                        // [NS]
+    uint64_t* s_rempty = s_sempty + NS;                                       // [NR]
     __shared__ uint32_t s_cnt;
     __shared__ unsigned long long s_base;
     __shared__ unsigned long long s_red[2][THREADS / 32];
@@ -620,90 +635,9 @@ join_kernel(JoinArgs a) {
     const uint32_t nunits = *a.num_units;
     unsigned long long matches = 0, sum = 0;
 
-    // ---- loader state: lives in shared memory, touched by thread 0 only (keeps it out of every
-    //      other thread's registers) ----
-    struct Loader {
-        uint4 it_d;                           // current unit descriptor
-        uint32_t it_u, it_rc, it_sc;          // unit, build chunk start, probe chunk start
-        uint32_t p_steps, p_chunks;           // steps / build chunks issued so far
-        uint32_t c_steps, c_chunks;           // steps / build chunks fully consumed
-        uint32_t it_valid, p_done, p_newc;    // p_newc: the next step starts a new build chunk
-    };
-    __shared__ Loader s_ld;
-    uint4& it_d = s_ld.it_d;
-    // the descriptor prefetched one unit ahead stays in registers: storing a just-issued global
-    // load into shared memory would make thread 0 wait ~1k cycles for it inside every issue
-    uint4 it_dn = make_uint4(0, 0, 0, 0);
-    uint32_t& it_u = s_ld.it_u; uint32_t& it_rc = s_ld.it_rc; uint32_t& it_sc = s_ld.it_sc;
-    uint32_t& p_steps = s_ld.p_steps; uint32_t& p_chunks = s_ld.p_chunks;
-    uint32_t& c_steps = s_ld.c_steps; uint32_t& c_chunks = s_ld.c_chunks;
-    uint32_t& it_valid = s_ld.it_valid; uint32_t& p_done = s_ld.p_done; uint32_t& p_newc = s_ld.p_newc;
     if (tid == 0) {
-        it_d = make_uint4(0, 0, 0, 0);
-        it_u = blockIdx.x; it_rc = 0; it_sc = 0;
-        p_steps = 0; p_chunks = 0; c_steps = 0; c_chunks = 0;
-        it_valid = 0; p_done = 0; p_newc = 1;
-    }
-    // returns true if a step was issued and another one may fit
-    auto try_issue = [&]() -> bool {
-        if (p_done || p_steps - c_steps >= (uint32_t)NS) return false;
-        const uint32_t sslot = p_steps % NS;
-        if (!it_valid) {
-            s_hdr[2 * sslot] = make_uint4(STEP_DONE, 0, 0, 0);
-            mbar_arrive_expect_tx(&s_sbar[sslot], 0);
-            p_done = 1;
-            ++p_steps;
-            return false;
-        }
-        // build chunk p_chunks reuses the slot of chunk p_chunks - NR, which must be consumed
-        if (p_newc && p_chunks >= c_chunks + (uint32_t)NR) return false;
-        const uint32_t nr = min((uint32_t)CAP, it_d.w - it_rc), ns = min((uint32_t)U, it_d.y - it_sc);
-        const uint32_t chunk = p_newc ? p_chunks : p_chunks - 1u;
-        const uint32_t rc = it_rc, sc = it_sc;
-        const bool newc = p_newc != 0;
-        // advance: probe chunks innermost, then build chunks, then the next unit of this CTA;
-        // the step is the last of its build chunk iff the next step loads a different one
-        bool lastc = false;
-        it_sc += U;
-        if (it_sc >= it_d.y) {
-            it_sc = it_d.x;
-            it_rc += CAP;
-            lastc = true;
-            if (it_rc >= it_d.w) {
-                it_u += gridDim.x;
-                it_valid = it_u < nunits ? 1u : 0u;
-                const uint4 prev = it_d;
-                it_d = it_dn;                                   // prefetched one unit ahead
-                it_rc = it_d.z; it_sc = it_d.x;
-                if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
-                // consecutive units of one (hot) partition share a single-chunk build side
-                if (it_valid && it_d.z == prev.z && it_d.w == prev.w && prev.w - prev.z <= (uint32_t)CAP) lastc = false;
-            }
-        }
-        p_newc = lastc ? 1u : 0u;
-        const uint32_t rskip = rc & 1u, sskip = sc & 1u;
-        s_hdr[2 * sslot] = make_uint4(ns, sskip, (newc ? 1u : 0u) | (lastc ? 2u : 0u), chunk);
-        s_hdr[2 * sslot + 1] = make_uint4(nr, rskip, 0, 0);
-        // No proxy fence here: the slots were last READ through the generic proxy and the CTA
-        // barrier before this call orders those reads; fence.proxy.async costs a MEMBAR.ALL.CTA
-        // that stalled warp 0 ~1.2k cycles per step while 31 warps hammer shared memory (ncu).
-        if (newc) {
-            const uint32_t rslot = chunk % NR;
-            const uint32_t rbytes = ((nr + rskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
-            mbar_arrive_expect_tx(&s_rbar[rslot], rbytes);
-            bulk_g2s(smem_raw + L::rbuf_bytes * rslot, a.bld + (rc - rskip), rbytes, &s_rbar[rslot]);
-            ++p_chunks;
-        }
-        const uint32_t sbytes = ((ns + sskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
-        mbar_arrive_expect_tx(&s_sbar[sslot], sbytes);
-        bulk_g2s(smem_raw + L::off_s + L::sbuf_bytes * sslot, a.prb + (sc - sskip), sbytes, &s_sbar[sslot]);
-        ++p_steps;
-        return true;
-    };
-
-    if (tid == 0) {
-        for (int s = 0; s < NS; ++s) mbar_init(&s_sbar[s], 1);
-        for (int s = 0; s < NR; ++s) mbar_init(&s_rbar[s], 1);
+        for (int s = 0; s < NS; ++s) { mbar_init(&s_sfull[s], 1); mbar_init(&s_sempty[s], 1); }
+        for (int s = 0; s < NR; ++s) { mbar_init(&s_rfull[s], 1); mbar_init(&s_rempty[s], 1); }
         fence_mbar_init();
         if (MATERIALIZE) s_cnt = 0;
     }
@@ -711,194 +645,249 @@ join_kernel(JoinArgs a) {
     for (uint32_t i = tid; i < (uint32_t)CAP / 4; i += THREADS)
         reinterpret_cast<uint4*>(head)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    if (tid == 0) {
-        it_valid = it_u < nunits ? 1u : 0u;
-        if (it_valid) {
-            it_d = __ldg(a.units + it_u);
-            it_rc = it_d.z; it_sc = it_d.x;
-            if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
-        }
-        while (try_issue()) {}
-    }
 
-    for (uint32_t k = 0;; ++k) {
-        const uint32_t sslot = k % NS;
-        mbar_wait(&s_sbar[sslot], (k / NS) & 1u);
-        const uint4 h0 = s_hdr[2 * sslot];
-        if (h0.x == STEP_DONE) break;
-        const uint4 h1 = s_hdr[2 * sslot + 1];
-        const uint32_t ns = h0.x, nr = h1.x, chunk = h0.w, rslot = chunk % NR;
-        const bool newc = (h0.z & 1u) != 0;
-        const tup_t* rbuf = reinterpret_cast<const tup_t*>(smem_raw + L::rbuf_bytes * rslot) + h1.y;
-        const tup_t* sbuf = reinterpret_cast<const tup_t*>(smem_raw + L::off_s + L::sbuf_bytes * sslot) + h0.y;
-        const uint32_t hb = 32u - __clz(max(nr, 32u) - 1u);   // ceil(log2(nr)), >= 5
-        const uint32_t hmask = (1u << hb) - 1u;
-        const uint32_t ver = ((chunk % 0x7FFFu) + 1u) << 16;  // 1..0x7FFF in bits 16..30
-
-        if (newc) {
-            if (chunk && (chunk % 0x7FFFu) == 0u) {   // version wrap: wipe stale heads (rare)
-                for (uint32_t i = tid; i < (uint32_t)CAP / 4; i += THREADS)
-                    reinterpret_cast<uint4*>(head)[i] = make_uint4(0u, 0u, 0u, 0u);
-                __syncthreads();
+    if (tid >= NC) {
+        // ================= loader warp: one lane walks (unit, build chunk, probe chunk) ahead of
+        // the consumers and feeds the rings; it never touches a tuple =================
+        if (tid == NC) {
+            uint32_t it_u = blockIdx.x;
+            bool it_valid = it_u < nunits;
+            uint4 it_d = make_uint4(0, 0, 0, 0), it_dn = make_uint4(0, 0, 0, 0);
+            if (it_valid) {
+                it_d = __ldg(a.units + it_u);
+                if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
             }
-            mbar_wait(&s_rbar[rslot], (chunk / NR) & 1u);
-            constexpr int KB = (CAP + THREADS - 1) / THREADS;
-            uint32_t bk[KB];
-#pragma unroll
-            for (int q = 0; q < KB; ++q) {
-                const uint32_t i = q * THREADS + tid;
-                bk[q] = (i < nr) ? rbuf[i].x : 0u;
-            }
-            if (OPTIMISTIC) {
-                // Optimistic build: plain stores, last writer wins; a thread whose entry survived
-                // owns a single-entry bucket.  With dense unique keys (no hash collisions) nobody
-                // loses and the build needs no atomics at all; losers (collisions, duplicate keys)
-                // are chained in with the atomic path afterwards.
-                uint32_t hq[KB];
-#pragma unroll
-                for (int q = 0; q < KB; ++q) {
-                    const uint32_t i = q * THREADS + tid;
-                    const uint32_t kk = bk[q] >> a.hash_shift;
-                    hq[q] = (kk ^ (kk >> hb)) & hmask;
-                    if (i < nr) head[hq[q]] = ver | i;
+            uint32_t it_rc = it_d.z, it_sc = it_d.x;
+            uint32_t chunks = 0;          // build chunks issued so far
+            bool newc = true;             // the next step starts a new build chunk
+            for (uint32_t p = 0;; ++p) {
+                const uint32_t sslot = p % NS;
+                if (p >= (uint32_t)NS) mbar_wait(&s_sempty[sslot], ((p / NS) - 1u) & 1u);
+                if (!it_valid) {
+                    s_hdr[2 * sslot] = make_uint4(STEP_DONE, 0, 0, 0);
+                    mbar_arrive_expect_tx(&s_sfull[sslot], 0);
+                    break;
                 }
-                __syncthreads();
-                uint32_t lost = 0;
-#pragma unroll
-                for (int q = 0; q < KB; ++q) {
-                    const uint32_t i = q * THREADS + tid;
-                    if (i < nr) {
-                        if (head[hq[q]] == (ver | i)) next[i] = (uint16_t)0xFFFFu;
-                        else lost |= 1u << q;
+                const uint32_t nr = min((uint32_t)CAP, it_d.w - it_rc), ns = min((uint32_t)U, it_d.y - it_sc);
+                const uint32_t chunk = newc ? chunks : chunks - 1u;
+                const uint32_t rc = it_rc, sc = it_sc;
+                const bool this_new = newc;
+                // advance: probe chunks innermost, then build chunks, then this CTA's next unit; the
+                // step is the last of its build chunk iff the next step loads a different one
+                bool lastc = false;
+                it_sc += U;
+                if (it_sc >= it_d.y) {
+                    it_sc = it_d.x;
+                    it_rc += CAP;
+                    lastc = true;
+                    if (it_rc >= it_d.w) {
+                        it_u += gridDim.x;
+                        it_valid = it_u < nunits;
+                        const uint4 prev = it_d;
+                        it_d = it_dn;                               // prefetched one unit ahead
+                        it_rc = it_d.z; it_sc = it_d.x;
+                        if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
+                        // consecutive units of one (hot) partition share a single-chunk build side
+                        if (it_valid && it_d.z == prev.z && it_d.w == prev.w && prev.w - prev.z <= (uint32_t)CAP) lastc = false;
                     }
                 }
-                if (__syncthreads_or((int)lost)) {
+                newc = lastc;
+                const uint32_t rskip = rc & 1u, sskip = sc & 1u;
+                s_hdr[2 * sslot] = make_uint4(ns, sskip, (this_new ? 1u : 0u) | (lastc ? 2u : 0u), chunk);
+                s_hdr[2 * sslot + 1] = make_uint4(nr, rskip, 0, 0);
+                if (this_new) {
+                    const uint32_t rslot = chunk % NR;
+                    // the slot's previous tenant (chunk - NR) must have been released
+                    if (chunk >= (uint32_t)NR) mbar_wait(&s_rempty[rslot], ((chunk / NR) - 1u) & 1u);
+                    const uint32_t rbytes = ((nr + rskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
+                    mbar_arrive_expect_tx(&s_rfull[rslot], rbytes);
+                    bulk_g2s(smem_raw + L::rbuf_bytes * rslot, a.bld + (rc - rskip), rbytes, &s_rfull[rslot]);
+                    ++chunks;
+                }
+                const uint32_t sbytes = ((ns + sskip + 1u) & ~1u) * (uint32_t)sizeof(tup_t);
+                mbar_arrive_expect_tx(&s_sfull[sslot], sbytes);
+                bulk_g2s(smem_raw + L::off_s + L::sbuf_bytes * sslot, a.prb + (sc - sskip), sbytes, &s_sfull[sslot]);
+            }
+        }
+    } else {
+        // ================= consumer warps =================
+        for (uint32_t k = 0;; ++k) {
+            const uint32_t sslot = k % NS;
+            mbar_wait(&s_sfull[sslot], (k / NS) & 1u);
+            const uint4 h0 = s_hdr[2 * sslot];
+            if (h0.x == STEP_DONE) break;
+            const uint4 h1 = s_hdr[2 * sslot + 1];
+            const uint32_t ns = h0.x, nr = h1.x, chunk = h0.w, rslot = chunk % NR;
+            const bool newc = (h0.z & 1u) != 0;
+            const tup_t* rbuf = reinterpret_cast<const tup_t*>(smem_raw + L::rbuf_bytes * rslot) + h1.y;
+            const tup_t* sbuf = reinterpret_cast<const tup_t*>(smem_raw + L::off_s + L::sbuf_bytes * sslot) + h0.y;
+            const uint32_t hb = 32u - __clz(max(nr, 32u) - 1u);   // ceil(log2(nr)), >= 5
+            const uint32_t hmask = (1u << hb) - 1u;
+            const uint32_t ver = ((chunk % 0x7FFFu) + 1u) << 16;  // 1..0x7FFF in bits 16..30
+
+            if (newc) {
+                if (chunk && (chunk % 0x7FFFu) == 0u) {   // version wrap: wipe stale heads (rare)
+                    for (uint32_t i = tid; i < (uint32_t)CAP / 4; i += NC)
+                        reinterpret_cast<uint4*>(head)[i] = make_uint4(0u, 0u, 0u, 0u);
+                    named_bar_sync(BAR_C, NC);
+                }
+                mbar_wait(&s_rfull[rslot], (chunk / NR) & 1u);
+                constexpr int KB = (CAP + NC - 1) / NC;
+                uint32_t bk[KB];
+#pragma unroll
+                for (int q = 0; q < KB; ++q) {
+                    const uint32_t i = q * NC + tid;
+                    bk[q] = (i < nr) ? rbuf[i].x : 0u;
+                }
+                if (OPTIMISTIC) {
+                    // Optimistic build: plain stores, last writer wins; a thread whose entry
+                    // survived owns a single-entry bucket; losers (collisions, duplicate keys)
+                    // are chained in with the atomic path afterwards.  (Measured: slower than
+                    // the atomic build on B200 -- the extra barrier costs more than the atomics.)
+                    uint32_t hq[KB];
+#pragma unroll
+                    for (int q = 0; q < KB; ++q) {
+                        const uint32_t i = q * NC + tid;
+                        const uint32_t kk = bk[q] >> a.hash_shift;
+                        hq[q] = (kk ^ (kk >> hb)) & hmask;
+                        if (i < nr) head[hq[q]] = ver | i;
+                    }
+                    named_bar_sync(BAR_C, NC);
+                    uint32_t lost = 0;
+#pragma unroll
+                    for (int q = 0; q < KB; ++q) {
+                        const uint32_t i = q * NC + tid;
+                        if (i < nr) {
+                            if (head[hq[q]] == (ver | i)) next[i] = (uint16_t)0xFFFFu;
+                            else lost |= 1u << q;
+                        }
+                    }
+                    named_bar_sync(BAR_C, NC);
 #pragma unroll
                     for (int q = 0; q < KB; ++q) {
                         if (lost & (1u << q)) {
-                            const uint32_t i = q * THREADS + tid;
+                            const uint32_t i = q * NC + tid;
                             uint32_t* hp = &head[hq[q]];
                             const uint32_t old = atomicExch(hp, ver | i);
                             next[i] = (uint16_t)old;      // the winner or an earlier loser: always live
                             atomicOr(hp, HEAD_MULTI);
                         }
                     }
-                    __syncthreads();
-                }
-            } else {
+                    named_bar_sync(BAR_C, NC);
+                } else {
 #pragma unroll
-                for (int q = 0; q < KB; ++q) {
-                    const uint32_t i = q * THREADS + tid;
-                    if (i < nr) {
-                        const uint32_t kk = bk[q] >> a.hash_shift;
-                        uint32_t* hp = &head[(kk ^ (kk >> hb)) & hmask];
-                        const uint32_t old = atomicExch(hp, ver | i);
-                        const bool live = (old & HEAD_VER_MASK) == ver;
-                        next[i] = live ? (uint16_t)old : (uint16_t)0xFFFFu;
-                        if (live) atomicOr(hp, HEAD_MULTI);
+                    for (int q = 0; q < KB; ++q) {
+                        const uint32_t i = q * NC + tid;
+                        if (i < nr) {
+                            const uint32_t kk = bk[q] >> a.hash_shift;
+                            uint32_t* hp = &head[(kk ^ (kk >> hb)) & hmask];
+                            const uint32_t old = atomicExch(hp, ver | i);
+                            const bool live = (old & HEAD_VER_MASK) == ver;
+                            next[i] = live ? (uint16_t)old : (uint16_t)0xFFFFu;
+                            if (live) atomicOr(hp, HEAD_MULTI);
+                        }
                     }
+                    named_bar_sync(BAR_C, NC);
                 }
-                __syncthreads();
             }
-        }
-        if (!MATERIALIZE) {
-            // straight-line probe of up to KP tuples per thread: all shared-memory loads of one
-            // kind are issued back to back; only multi-entry buckets take the chain loop
-            constexpr int KP = (U + THREADS - 1) / THREADS;
-            tup_t t[KP], r[KP];
-            uint32_t w[KP];
-            uint32_t m32 = 0;
+            if (!MATERIALIZE) {
+                // straight-line probe of up to KP tuples per thread: all shared-memory loads of one
+                // kind are issued back to back; only multi-entry buckets take the chain loop
+                constexpr int KP = (U + NC - 1) / NC;
+                tup_t t[KP], r[KP];
+                uint32_t w[KP];
+                uint32_t m32 = 0;
 #pragma unroll
-            for (int q = 0; q < KP; ++q) {
-                const uint32_t j = q * THREADS + tid;
-                t[q] = (j < ns) ? sbuf[j] : make_uint2(0u, 0u);
-            }
+                for (int q = 0; q < KP; ++q) {
+                    const uint32_t j = q * NC + tid;
+                    t[q] = (j < ns) ? sbuf[j] : make_uint2(0u, 0u);
+                }
 #pragma unroll
-            for (int q = 0; q < KP; ++q) {
-                const uint32_t j = q * THREADS + tid;
-                const uint32_t kk = t[q].x >> a.hash_shift;
-                w[q] = (j < ns) ? head[(kk ^ (kk >> hb)) & hmask] : 0u;
-            }
+                for (int q = 0; q < KP; ++q) {
+                    const uint32_t j = q * NC + tid;
+                    const uint32_t kk = t[q].x >> a.hash_shift;
+                    w[q] = (j < ns) ? head[(kk ^ (kk >> hb)) & hmask] : 0u;
+                }
 #pragma unroll
-            for (int q = 0; q < KP; ++q) {
-                const bool live = (w[q] & HEAD_VER_MASK) == ver;
-                r[q] = rbuf[live ? (w[q] & 0xFFFFu) : 0u];
-            }
+                for (int q = 0; q < KP; ++q) {
+                    const bool live = (w[q] & HEAD_VER_MASK) == ver;
+                    r[q] = rbuf[live ? (w[q] & 0xFFFFu) : 0u];
+                }
 #pragma unroll
-            for (int q = 0; q < KP; ++q) {
-                if ((w[q] & HEAD_VER_MASK) == ver) {
-                    if (r[q].x == t[q].x) {
-                        ++m32;
-                        sum += (unsigned long long)((long long)(int32_t)r[q].y * (long long)(int32_t)t[q].y);
-                    }
-                    if (w[q] & HEAD_MULTI) {
-                        for (uint32_t i = next[w[q] & 0xFFFFu]; i != 0xFFFFu; i = next[i]) {
-                            const tup_t rr = rbuf[i];
-                            if (rr.x == t[q].x) {
-                                ++m32;
-                                sum += (unsigned long long)((long long)(int32_t)rr.y * (long long)(int32_t)t[q].y);
+                for (int q = 0; q < KP; ++q) {
+                    if ((w[q] & HEAD_VER_MASK) == ver) {
+                        if (r[q].x == t[q].x) {
+                            ++m32;
+                            sum += (unsigned long long)((long long)(int32_t)r[q].y * (long long)(int32_t)t[q].y);
+                        }
+                        if (w[q] & HEAD_MULTI) {
+                            for (uint32_t i = next[w[q] & 0xFFFFu]; i != 0xFFFFu; i = next[i]) {
+                                const tup_t rr = rbuf[i];
+                                if (rr.x == t[q].x) {
+                                    ++m32;
+                                    sum += (unsigned long long)((long long)(int32_t)rr.y * (long long)(int32_t)t[q].y);
+                                }
                             }
                         }
                     }
                 }
+                matches += m32;
             }
-            matches += m32;
-        }
-        const uint32_t rounds = (ns + THREADS - 1) / THREADS;
-        for (uint32_t q = 0; MATERIALIZE && q < rounds; ++q) {
-            const uint32_t j = q * THREADS + tid;
-            if (j < ns) {
-                const tup_t t = sbuf[j];
-                const uint32_t kk = t.x >> a.hash_shift;
-                const uint32_t w = head[(kk ^ (kk >> hb)) & hmask];
-                uint32_t i = ((w & HEAD_VER_MASK) == ver) ? (w & 0xFFFFu) : 0xFFFFu;
-                while (i != 0xFFFFu) {
-                    const tup_t r = rbuf[i];
-                    if (r.x == t.x) {
-                        ++matches;
-                        sum += (unsigned long long)((long long)(int32_t)r.y * (long long)(int32_t)t.y);
-                        const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                        if (pos < (uint32_t)JOIN_STAGE_PAIRS) {
-                            s_out_b[pos] = (int32_t)r.y;
-                            s_out_p[pos] = (int32_t)t.y;
-                        } else {   // staging full inside a round: rare direct path
-                            const unsigned long long g = atomicAdd(&a.result[2], 1ull);
-                            if (g < a.cap) {
-                                a.out_bld_pay[g] = (int32_t)r.y;
-                                a.out_prb_pay[g] = (int32_t)t.y;
+            const uint32_t rounds = (ns + NC - 1) / NC;
+            for (uint32_t q = 0; MATERIALIZE && q < rounds; ++q) {
+                const uint32_t j = q * NC + tid;
+                if (j < ns) {
+                    const tup_t t = sbuf[j];
+                    const uint32_t kk = t.x >> a.hash_shift;
+                    const uint32_t w = head[(kk ^ (kk >> hb)) & hmask];
+                    uint32_t i = ((w & HEAD_VER_MASK) == ver) ? (w & 0xFFFFu) : 0xFFFFu;
+                    while (i != 0xFFFFu) {
+                        const tup_t r = rbuf[i];
+                        if (r.x == t.x) {
+                            ++matches;
+                            sum += (unsigned long long)((long long)(int32_t)r.y * (long long)(int32_t)t.y);
+                            const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                            if (pos < (uint32_t)JOIN_STAGE_PAIRS) {
+                                s_out_b[pos] = (int32_t)r.y;
+                                s_out_p[pos] = (int32_t)t.y;
+                            } else {   // staging full inside a round: rare direct path
+                                const unsigned long long g = atomicAdd(&a.result[2], 1ull);
+                                if (g < a.cap) {
+                                    a.out_bld_pay[g] = (int32_t)r.y;
+                                    a.out_prb_pay[g] = (int32_t)t.y;
+                                }
                             }
                         }
-                    }
-                    i = (w & HEAD_MULTI) ? (uint32_t)next[i] : 0xFFFFu;
-                }
-            }
-            __syncthreads();
-            const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE_PAIRS);
-            if (c + THREADS > (uint32_t)JOIN_STAGE_PAIRS) {
-                if (tid == 0) s_base = atomicAdd(&a.result[2], (unsigned long long)c);
-                __syncthreads();
-                const unsigned long long g0 = s_base;
-                for (uint32_t i = tid; i < c; i += THREADS) {
-                    if (g0 + i < a.cap) {
-                        a.out_bld_pay[g0 + i] = s_out_b[i];
-                        a.out_prb_pay[g0 + i] = s_out_p[i];
+                        i = (w & HEAD_MULTI) ? (uint32_t)next[i] : 0xFFFFu;
                     }
                 }
-                __syncthreads();
-                if (tid == 0) s_cnt = 0;
-                __syncthreads();
+                named_bar_sync(BAR_C, NC);
+                const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE_PAIRS);
+                if (c + NC > (uint32_t)JOIN_STAGE_PAIRS) {
+                    if (tid == 0) s_base = atomicAdd(&a.result[2], (unsigned long long)c);
+                    named_bar_sync(BAR_C, NC);
+                    const unsigned long long g0 = s_base;
+                    for (uint32_t i = tid; i < c; i += NC) {
+                        if (g0 + i < a.cap) {
+                            a.out_bld_pay[g0 + i] = s_out_b[i];
+                            a.out_prb_pay[g0 + i] = s_out_p[i];
+                        }
+                    }
+                    named_bar_sync(BAR_C, NC);
+                    if (tid == 0) s_cnt = 0;
+                    named_bar_sync(BAR_C, NC);
+                }
             }
-        }
-        __syncthreads();                 // everyone is done with this step's slots (and the table)
-        if (tid == 0) {
-            c_steps = k + 1;
-            c_chunks = chunk + ((h0.z & 2u) ? 1u : 0u);
-            while (try_issue()) {}
+            named_bar_sync(BAR_C, NC);       // every consumer is done with this step's slots (and the table)
+            if (tid == 0) {                  // hand the slots back to the loader
+                mbar_arrive(&s_sempty[sslot]);
+                if (h0.z & 2u) mbar_arrive(&s_rempty[rslot]);
+            }
         }
     }
 
+    __syncthreads();
     if (MATERIALIZE) {
-        __syncthreads();
         const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE_PAIRS);
         if (c) {
             if (tid == 0) s_base = atomicAdd(&a.result[2], (unsigned long long)c);
