@@ -8,8 +8,7 @@ import sys
 
 rep, rx = sys.argv[1], sys.argv[2]
 inst = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{rx}"],
-                     capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 import re
 blocks = [b for b in out.split('"Kernel Name",')[1:] if re.search(rx, b.split("\n")[0])]
 blk = blocks[inst]
