@@ -375,7 +375,10 @@ def multi_gpu(args):
     if kind != "unique":
         raise SystemExit("multi-GPU bench supports the unique-key workloads (B, small)")
     NR, NS = nR * world, nS * world
-    sj = gj.distributed.ShardedJoin(nR, nS, device=local, mode=args.shuffle)
+    sj = gj.distributed.ShardedJoin(nR, nS, device=local, mode=args.shuffle, overlap=not args.no_overlap)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        sj.ops.engine.set_option(k, int(v))
     eng = sj.ops.engine
     dev = torch.device("cuda", local)
     cols = [torch.empty(n, dtype=torch.int32, device=dev) for n in (nR, nR, nS, nS)]
@@ -449,7 +452,8 @@ def multi_gpu(args):
                      "checked": f"matches == checksum == {expect} every step"})
         if line["roofline"]["achieved"]:
             line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
-        line["config"].update({"global_R": NR, "global_S": NS, "parallelism": f"radix-sharded over {world} GPUs, {args.shuffle} shuffle"})
+        line["config"].update({"global_R": NR, "global_S": NS, "parallelism": f"radix-sharded over {world} GPUs, {args.shuffle} shuffle"
+                               + ("" if args.no_overlap or args.shuffle != "p2p" else ", S shuffle overlapped with R's local passes")})
         print(json.dumps(line))
     sj.close()
     dist.destroy_process_group()
@@ -464,6 +468,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--shuffle", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: shuffle and local passes back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()

@@ -103,6 +103,8 @@ constexpr uint32_t FINE_MAX = 1u << MAX_RADIX_BITS;
 constexpr uint32_t SCAN_TILES_MAX = FINE_MAX / SCAN_TILE;
 constexpr int N_EVENTS = 64;
 
+struct Plan { uint32_t B, b1, b2; };
+
 struct gj_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
@@ -124,6 +126,16 @@ struct gj_ctx {
     tup_t** d_dst_bases = nullptr;            // 256 pointers (shuffle)
     cudaEvent_t ev[5] = {};
     cudaEvent_t pev[2][3] = {};   // per scatter launch: [role][before p1, after p1, after p2]
+    cudaEvent_t sev[2][2] = {};   // peer-scatter kernel of relation 0/1: before, after
+    cudaEvent_t stage_ev[4] = {}; // staged pipeline: partition done [side 0/1], scratch free, join done
+    // staged (multi-GPU overlap) pipeline state
+    struct { Plan pl; int role_of_side[2]; uint64_t n_side[2]; bool active, scratch_used; } stage = {};
+    uint32_t* shuf_cur[2] = {nullptr, nullptr};      // device: per-destination cursors of relation 0/1
+    tup_t** shuf_bases[2] = {nullptr, nullptr};      // device: per-destination base pointers
+    unsigned char* h_shuf = nullptr;                 // pinned staging for the two above
+    unsigned char* zero_role[2] = {nullptr, nullptr};
+    unsigned char* zero_common = nullptr;
+    size_t zero_role_bytes = 0, zero_common_bytes = 0;
     cudaEvent_t cev[N_EVENTS] = {};
     int32_t* d_in[4] = {nullptr, nullptr, nullptr, nullptr};   // host-entry staging Rk,Rp,Sk,Sp
     void* flush_buf = nullptr;
@@ -133,7 +145,7 @@ struct gj_ctx {
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
-            opt_join_grid = 0, opt_h2d_chunk = 8u << 20;
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0;
     bool attrs_set = false;
 };
 
@@ -178,6 +190,10 @@ extern "C" void gj_destroy(gj_ctx* ctx) {
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& r : ctx->pev) for (auto& e : r) if (e) cudaEventDestroy(e);
+    for (auto& r : ctx->sev) for (auto& e : r) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
+    cudaFree(ctx->shuf_cur[0]); cudaFree(ctx->shuf_bases[0]);
+    if (ctx->h_shuf) cudaFreeHost(ctx->h_shuf);
     for (auto& e : ctx->cev) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -203,6 +219,8 @@ static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) 
     ctx->stream = ctx->own_stream;
     for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
     for (auto& r : ctx->pev) for (auto& e : r) CK(cudaEventCreate(&e));
+    for (auto& r : ctx->sev) for (auto& e : r) CK(cudaEventCreate(&e));
+    for (auto& e : ctx->stage_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : ctx->cev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
     const uint64_t mx = std::max(ctx->maxR, ctx->maxS);
@@ -213,14 +231,22 @@ static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) 
         cudaGetLastError();
         return fail(GJ_ERR_NOMEM, "cudaMalloc of %.2f GB partition buffers failed", (ctx->maxR + ctx->maxS + mx) * 8e-9);
     }
-    // zeroed-per-call block: ghist x2 | desc x2 | tickets + counters | result
-    size_t zb = 0;
-    const size_t o_hist = zb;   zb += 2 * FINE_MAX * sizeof(uint32_t);
-    const size_t o_desc = zb;   zb += 3 * SCAN_TILES_MAX * sizeof(unsigned long long);
-    const size_t o_cnt = zb;    zb += 16 * sizeof(uint32_t);
-    const size_t o_res = zb;    zb += 4 * sizeof(unsigned long long);
-    ctx->zero_bytes = zb;
-    CK(cudaMalloc(&ctx->zero_block, zb));
+    // zeroed-per-call block: [role 0 | role 1 | common]; role = fine histogram, scan descriptors,
+    // scan ticket, tile count; common = unit-scan descriptors + ticket, result.  The staged
+    // (multi-GPU) pipeline zeroes the three regions independently.
+    const size_t r_hist = 0;
+    const size_t r_desc = r_hist + FINE_MAX * sizeof(uint32_t);
+    const size_t r_cnt = r_desc + SCAN_TILES_MAX * sizeof(unsigned long long);
+    const size_t role_bytes = r_cnt + 16;
+    const size_t c_desc = 0;
+    const size_t c_cnt = c_desc + SCAN_TILES_MAX * sizeof(unsigned long long);
+    const size_t c_res = c_cnt + 16;
+    const size_t common_bytes = c_res + 4 * sizeof(unsigned long long);
+    ctx->zero_role_bytes = role_bytes; ctx->zero_common_bytes = common_bytes;
+    ctx->zero_bytes = 2 * role_bytes + common_bytes;
+    CK(cudaMalloc(&ctx->zero_block, ctx->zero_bytes));
+    ctx->zero_role[0] = ctx->zero_block; ctx->zero_role[1] = ctx->zero_block + role_bytes;
+    ctx->zero_common = ctx->zero_block + 2 * role_bytes;
     // persistent metadata block
     size_t mb = 0;
     const size_t o_off = mb;    mb += 2 * (FINE_MAX + 4) * sizeof(uint32_t);
@@ -233,19 +259,25 @@ static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) 
     CK(cudaMalloc(&ctx->tiles_block, 2 * ctx->tiles_cap * sizeof(uint4)));
     for (int r = 0; r < 2; ++r) {
         RelMeta& m = ctx->meta[r];
-        m.ghist = reinterpret_cast<uint32_t*>(ctx->zero_block + o_hist) + (size_t)r * FINE_MAX;
-        m.desc = reinterpret_cast<unsigned long long*>(ctx->zero_block + o_desc) + (size_t)r * SCAN_TILES_MAX;
-        m.ticket = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + r;
+        m.ghist = reinterpret_cast<uint32_t*>(ctx->zero_role[r] + r_hist);
+        m.desc = reinterpret_cast<unsigned long long*>(ctx->zero_role[r] + r_desc);
+        m.ticket = reinterpret_cast<uint32_t*>(ctx->zero_role[r] + r_cnt);
+        m.num_tiles = reinterpret_cast<uint32_t*>(ctx->zero_role[r] + r_cnt) + 1;
         m.off = reinterpret_cast<uint32_t*>(ctx->meta_block + o_off) + (size_t)r * (FINE_MAX + 4);
         m.cur1 = reinterpret_cast<uint32_t*>(ctx->meta_block + o_cur1) + (size_t)r * NB_MAX * CUR1_STRIDE;
         m.cur2 = reinterpret_cast<uint32_t*>(ctx->meta_block + o_cur2) + (size_t)r * FINE_MAX;
         m.tiles = ctx->tiles_block + (size_t)r * ctx->tiles_cap;
-        m.num_tiles = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + 8 + r;
     }
-    ctx->unit_ticket = reinterpret_cast<uint32_t*>(ctx->zero_block + o_cnt) + 4;
-    ctx->unit_desc = reinterpret_cast<unsigned long long*>(ctx->zero_block + o_desc) + (size_t)2 * SCAN_TILES_MAX;
+    ctx->unit_desc = reinterpret_cast<unsigned long long*>(ctx->zero_common + c_desc);
+    ctx->unit_ticket = reinterpret_cast<uint32_t*>(ctx->zero_common + c_cnt);
+    ctx->result = reinterpret_cast<unsigned long long*>(ctx->zero_common + c_res);
     ctx->unit_base = reinterpret_cast<uint32_t*>(ctx->meta_block + o_ub);
-    ctx->result = reinterpret_cast<unsigned long long*>(ctx->zero_block + o_res);
+    // multi-GPU shuffle: per-relation cursors and destination bases (+ pinned staging)
+    CK(cudaMalloc(&ctx->shuf_cur[0], 2 * NB_MAX * sizeof(uint32_t)));
+    ctx->shuf_cur[1] = ctx->shuf_cur[0] + NB_MAX;
+    CK(cudaMalloc(&ctx->shuf_bases[0], 2 * NB_MAX * sizeof(tup_t*)));
+    ctx->shuf_bases[1] = ctx->shuf_bases[0] + NB_MAX;
+    CK(cudaHostAlloc(&ctx->h_shuf, 2 * NB_MAX * (sizeof(uint32_t) + sizeof(void*)), cudaHostAllocDefault));
     // unit list: probe side cut every >= 1024 tuples, plus one per partition
     ctx->units_cap = mx / 1024 + FINE_MAX + 16;
     CK(cudaMalloc(&ctx->units, ctx->units_cap * sizeof(uint4)));
@@ -284,6 +316,7 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
         {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
         {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
         {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
+        {"shuffle_grid", &ctx->opt_shuffle_grid},
     };
     for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
     return nullptr;
@@ -329,7 +362,6 @@ extern "C" int gj_get_option(gj_ctx* ctx, const char* name, int64_t* v) {
 // planning: how many radix bits, how they split over passes
 // (the reference freezes log_parts1 = 8, log_parts2 = 5 at compile time, common.h:51-52)
 // ------------------------------------------------------------------------------------------
-struct Plan { uint32_t B, b1, b2; };
 
 static Plan choose_plan(const gj_ctx* ctx, uint64_t n_build, uint32_t forced_bits) {
     Plan p;
@@ -353,13 +385,13 @@ static Plan choose_plan(const gj_ctx* ctx, uint64_t n_build, uint32_t forced_bit
 // enqueue helpers (no host synchronisation inside)
 // ------------------------------------------------------------------------------------------
 static int enqueue_hist(gj_ctx* ctx, cudaStream_t s, const void* in, bool packed, uint64_t n,
-                        uint32_t shift, uint32_t bits, uint32_t* ghist) {
+                        uint32_t shift, uint32_t bits, uint32_t* ghist, int threads = 1024) {
     if (!n) return GJ_OK;
-    const uint64_t per_cta = 1024ull * 16;
+    const uint64_t per_cta = (uint64_t)threads * 16;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count, (n + per_cta - 1) / per_cta));
     const size_t smem = (size_t)4 << bits;
-    if (packed) hist_kernel<true><<<grid, 1024, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
-    else hist_kernel<false><<<grid, 1024, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+    if (packed) hist_kernel<true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+    else hist_kernel<false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
     LAUNCHED();
     return GJ_OK;
 }
@@ -376,6 +408,7 @@ static const ScatterCfg& scatter_cfg2(const gj_ctx* ctx, uint32_t b2) {
 static uint32_t unit_tuples(const gj_ctx* ctx) { return ctx->opt_unit ? (uint32_t)ctx->opt_unit : 8192u; }
 
 // scan of the fine histogram(s) of roles [first, first+nrel) and, for a join, of the unit counts
+// nrel == 0 with with_units: only the unit sequence (staged pipeline: both histograms are final)
 static int enqueue_scan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, uint32_t nb, bool with_units) {
     ScanArgs a;
     for (uint32_t r = 0; r < 2; ++r) {
@@ -384,7 +417,14 @@ static int enqueue_scan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, u
     }
     a.seq[2].in = nullptr; a.seq[2].out = ctx->unit_base; a.seq[2].desc = ctx->unit_desc; a.seq[2].ticket = ctx->unit_ticket;
     a.nb = nb; a.unit = unit_tuples(ctx);
-    dim3 grid((nb + SCAN_TILE - 1) / SCAN_TILE, with_units ? 3 : nrel);
+    a.seq_base = 0;
+    if (nrel == 0) {           // unit sequence only; it reads the histograms of roles 0 and 1
+        for (uint32_t r = 0; r < 2; ++r) a.seq[r].in = ctx->meta[r].ghist;
+        a.seq_base = 2;
+    } else if (nrel == 1 && first == 1) {   // a single relation in role 1: sequence slot 0 carries it
+        a.seq_base = 0;
+    }
+    dim3 grid((nb + SCAN_TILE - 1) / SCAN_TILE, nrel == 0 ? 1 : (with_units ? 3 : nrel));
     scan_lookback_kernel<<<grid, SCAN_THREADS, 0, s>>>(a);
     LAUNCHED();
     return GJ_OK;
@@ -396,7 +436,8 @@ static int enqueue_plan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, c
         const RelMeta& m = ctx->meta[r < nrel ? first + (int)r : first];
         a.rel[r].off = m.off; a.rel[r].cur1 = m.cur1; a.rel[r].cur2 = m.cur2; a.rel[r].tiles = m.tiles; a.rel[r].num_tiles = m.num_tiles;
     }
-    a.nrel = with_units ? 2 : nrel; a.b1 = pl.b1; a.b2 = pl.b2;
+    a.nrel = nrel; a.with_units = with_units ? 1u : 0u; a.b1 = pl.b1; a.b2 = pl.b2;
+    if (nrel == 0) for (uint32_t r = 0; r < 2; ++r) a.rel[r].off = ctx->meta[r].off;   // units only
     const ScatterCfg& c2 = scatter_cfg2(ctx, pl.b2);
     a.tile = (uint32_t)(c2.threads * c2.ipt);
     a.unit = unit_tuples(ctx);
@@ -423,6 +464,7 @@ static int enqueue_scatter(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role
     a.cursors = pl.b2 ? m.cur1 : m.cur2;
     a.cursor_stride = pl.b2 ? CUR1_STRIDE : 1;
     const uint32_t grid1 = (uint32_t)((rel.n + (rel.tup ? 1 : 0) + T1 - 1) / T1);   // +1: alignment shift of packed input
+    a.ntiles = grid1;
     CK(cudaEventRecord(ctx->pev[role][0], s));
     (rel.tup ? c1.packed : c1.col)<<<grid1, c1.threads, scatter_smem(c1), s>>>(a);
     LAUNCHED();
@@ -770,7 +812,8 @@ extern "C" int gj_shuffle_split(gj_ctx* ctx, const int32_t* d_keys, const int32_
         memset(&a, 0, sizeof(a));
         a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = (tup_t*)d_out_tuples;
         a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2; a.cursor_stride = 1;
-        c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, scatter_smem(c1), s>>>(a);
+        a.ntiles = (uint32_t)((n + T1 - 1) / T1);
+        c1.col<<<a.ntiles, c1.threads, scatter_smem(c1), s>>>(a);
         LAUNCHED();
     }
     uint32_t tmp[NB_MAX];
@@ -805,14 +848,144 @@ extern "C" int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, cons
         a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = nullptr;
         a.dst_bases = ctx->d_dst_bases;
         a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->meta[0].cur2; a.cursor_stride = 1;
-        CK(cudaEventRecord(ctx->ev[0], s));
-        c1.col<<<(uint32_t)((n + T1 - 1) / T1), c1.threads, scatter_smem(c1), s>>>(a);
+        a.ntiles = (uint32_t)((n + T1 - 1) / T1);
+        // optional persistent grid ("shuffle_grid" CTAs looping over the tiles): leaves SM resources
+        // to the local passes of the other relation running concurrently on another stream
+        const uint32_t grid = ctx->opt_shuffle_grid ? std::min<uint32_t>((uint32_t)ctx->opt_shuffle_grid, a.ntiles) : a.ntiles;
+        CK(cudaEventRecord(ctx->sev[0][0], s));
+        c1.col<<<grid, c1.threads, scatter_smem(c1), s>>>(a);
         LAUNCHED();
-        CK(cudaEventRecord(ctx->ev[1], s));
+        CK(cudaEventRecord(ctx->sev[0][1], s));
     }
     CK(cudaStreamSynchronize(s));
     ctx->last_shuffle_ms = 0.f;
-    if (n) CK(cudaEventElapsedTime(&ctx->last_shuffle_ms, ctx->ev[0], ctx->ev[1]));
+    if (n) CK(cudaEventElapsedTime(&ctx->last_shuffle_ms, ctx->sev[0][0], ctx->sev[0][1]));
+    return GJ_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// asynchronous / staged entry points: the multi-GPU host overlaps one relation's shuffle with the
+// other relation's local radix passes.  Nothing here synchronises until gj_stage_finish.
+// ------------------------------------------------------------------------------------------
+extern "C" int gj_shuffle_scatter_peers_async(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays,
+                                              uint64_t n, uint32_t n_gpus, uint32_t gpu_shift,
+                                              void* const* d_peer_bases, const uint64_t* h_peer_offsets,
+                                              void* cuda_stream) {
+    uint32_t bits = 0;
+    int rc = shuffle_args_ok(ctx, n, n_gpus, gpu_shift, &bits);
+    if (rc) return rc;
+    if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 or 1");
+    if (!d_peer_bases || !h_peer_offsets || (n && (!d_keys || !d_pays))) return fail(GJ_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    // pinned staging: [which][cursors u32 x NB_MAX | bases ptr x NB_MAX]
+    unsigned char* hs = ctx->h_shuf + (size_t)which * NB_MAX * (sizeof(uint32_t) + sizeof(void*));
+    uint32_t* hcur = reinterpret_cast<uint32_t*>(hs);
+    void** hbase = reinterpret_cast<void**>(hs + NB_MAX * sizeof(uint32_t));
+    for (uint32_t g = 0; g < n_gpus; ++g) {
+        if (h_peer_offsets[g] > 0xFFFFFFFFull) return fail(GJ_ERR_ARG, "peer offset exceeds 2^32 tuples");
+        hcur[g] = (uint32_t)h_peer_offsets[g];
+        hbase[g] = d_peer_bases[g];
+    }
+    CK(cudaMemcpyAsync(ctx->shuf_cur[which], hcur, n_gpus * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->shuf_bases[which], hbase, n_gpus * sizeof(void*), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->sev[which][0], s));
+    if (n) {
+        const ScatterCfg& c1 = scatter_cfg1(ctx);
+        const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
+        ScatterArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = nullptr;
+        a.dst_bases = ctx->shuf_bases[which];
+        a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->shuf_cur[which]; a.cursor_stride = 1;
+        a.ntiles = (uint32_t)((n + T1 - 1) / T1);
+        const uint32_t grid = ctx->opt_shuffle_grid ? std::min<uint32_t>((uint32_t)ctx->opt_shuffle_grid, a.ntiles) : a.ntiles;
+        c1.col<<<grid, c1.threads, scatter_smem(c1), s>>>(a);
+        LAUNCHED();
+    }
+    CK(cudaEventRecord(ctx->sev[which][1], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_shuffle_scatter_ms(gj_ctx* ctx, int which, float* ms) {
+    if (!ctx || !ms || (which != 0 && which != 1)) return fail(GJ_ERR_ARG, "bad argument");
+    CK(cudaEventSynchronize(ctx->sev[which][1]));
+    CK(cudaEventElapsedTime(ms, ctx->sev[which][0], ctx->sev[which][1]));
+    return GJ_OK;
+}
+
+extern "C" int gj_stage_begin(gj_ctx* ctx, uint64_t nR, uint64_t nS, void* cuda_stream) {
+    int rc = check_caps(ctx, nR, nS);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    const bool swap = nR > nS;
+    ctx->stage.role_of_side[0] = swap ? 1 : 0;
+    ctx->stage.role_of_side[1] = swap ? 0 : 1;
+    ctx->stage.n_side[0] = nR; ctx->stage.n_side[1] = nS;
+    ctx->stage.pl = choose_plan(ctx, std::min(nR, nS), 0);
+    ctx->stage.active = true;
+    ctx->stage.scratch_used = false;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaMemsetAsync(ctx->zero_common, 0, ctx->zero_common_bytes, s));
+    CK(cudaEventRecord(ctx->stage_ev[3], s));   // "common block ready"
+    return GJ_OK;
+}
+
+extern "C" int gj_stage_partition(gj_ctx* ctx, int side, const void* d_tuples, void* cuda_stream) {
+    if (!ctx || !ctx->stage.active) return fail(GJ_ERR_STATE, "gj_stage_begin first");
+    if (side != 0 && side != 1) return fail(GJ_ERR_ARG, "side must be 0 (R) or 1 (S)");
+    const uint64_t n = ctx->stage.n_side[side];
+    if (n && (!d_tuples || ((size_t)d_tuples & 7u))) return fail(GJ_ERR_ARG, "packed tuples must be non-NULL and 8-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const int role = ctx->stage.role_of_side[side];
+    const Plan& pl = ctx->stage.pl;
+    int rc;
+    CK(cudaMemsetAsync(ctx->zero_role[role], 0, ctx->zero_role_bytes, s));
+    // 512-thread histogram CTAs: small enough to share an SM with the persistent peer-scatter CTAs
+    if ((rc = enqueue_hist(ctx, s, d_tuples, true, n, 0, pl.B, ctx->meta[role].ghist, 512))) return rc;
+    if ((rc = enqueue_scan(ctx, s, role, 1, 1u << pl.B, false))) return rc;
+    if ((rc = enqueue_plan(ctx, s, role, 1, pl, false))) return rc;
+    if (ctx->stage.scratch_used) CK(cudaStreamWaitEvent(s, ctx->stage_ev[2], 0));   // first-pass buffer is shared
+    Rel rel;
+    rel.tup = (const tup_t*)d_tuples; rel.n = n; rel.slot = side;
+    if ((rc = enqueue_scatter(ctx, s, rel, role, pl, ctx->out[side]))) return rc;
+    CK(cudaEventRecord(ctx->stage_ev[2], s));
+    ctx->stage.scratch_used = true;
+    CK(cudaEventRecord(ctx->stage_ev[side], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_stage_join(gj_ctx* ctx, void* cuda_stream) {
+    if (!ctx || !ctx->stage.active) return fail(GJ_ERR_STATE, "gj_stage_begin first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const Plan& pl = ctx->stage.pl;
+    const uint64_t nR = ctx->stage.n_side[0], nS = ctx->stage.n_side[1];
+    CK(cudaStreamWaitEvent(s, ctx->stage_ev[0], 0));
+    CK(cudaStreamWaitEvent(s, ctx->stage_ev[1], 0));
+    CK(cudaStreamWaitEvent(s, ctx->stage_ev[3], 0));
+    int rc;
+    if (nR && nS) {
+        const int bside = ctx->stage.role_of_side[0] == 0 ? 0 : 1;   // which side is the build role
+        if ((rc = enqueue_scan(ctx, s, 0, 0, 1u << pl.B, true))) return rc;
+        if ((rc = enqueue_plan(ctx, s, 0, 0, pl, true))) return rc;
+        if ((rc = enqueue_join(ctx, s, ctx->out[bside], ctx->out[1 - bside], pl, bside == 0 ? nR : nS,
+                               bside == 0 ? nS : nR, false, nullptr, nullptr, 0))) return rc;
+    }
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[3], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_stage_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum) {
+    if (!ctx || !ctx->stage.active) return fail(GJ_ERR_STATE, "gj_stage_begin first");
+    CK(cudaEventSynchronize(ctx->ev[3]));
+    ctx->stage.active = false;
+    if (matches) *matches = ctx->h_result[0];
+    if (checksum) *checksum = ctx->h_result[1];
     return GJ_OK;
 }
 

@@ -182,6 +182,7 @@ struct ScanArgs {
     ScanSeq seq[3];
     uint32_t nb;
     uint32_t unit;                // probe tuples per join unit (sequence 2)
+    uint32_t seq_base;            // blockIdx.y + seq_base selects the sequence
 };
 
 __device__ __forceinline__ uint32_t units_of(uint32_t n_bld, uint32_t n_prb, uint32_t unit) {
@@ -191,7 +192,8 @@ __device__ __forceinline__ uint32_t units_of(uint32_t n_bld, uint32_t n_prb, uin
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_lookback_kernel(ScanArgs a) {
     __shared__ uint32_t s_tile, s_prefix, s_warp[SCAN_THREADS / 32];
-    const ScanSeq r = a.seq[blockIdx.y];
+    const uint32_t which = blockIdx.y + a.seq_base;
+    const ScanSeq r = a.seq[which];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(r.ticket, 1u);
     __syncthreads();
@@ -203,7 +205,7 @@ scan_lookback_kernel(ScanArgs a) {
     for (int j = 0; j < SCAN_IPT; ++j) {
         v[j] = 0;
         if (base + j < a.nb) {
-            if (blockIdx.y < 2) v[j] = r.in[base + j];
+            if (which < 2) v[j] = r.in[base + j];
             else v[j] = units_of(a.seq[0].in[base + j], a.seq[1].in[base + j], a.unit);
         }
         tsum += v[j];
@@ -280,7 +282,8 @@ struct PlanRel {
 };
 struct PlanArgs {
     PlanRel rel[2];        // [0] build side, [1] probe side
-    uint32_t nrel;         // 1: partition only, 2: join
+    uint32_t nrel;         // relations whose cursors / tile descriptors are prepared (0, 1 or 2)
+    uint32_t with_units;   // also write the join's unit list (needs both relations' offsets)
     uint32_t b1, b2;       // b2 == 0: single pass
     uint32_t tile;         // tuples per pass-2 scatter tile
     uint32_t unit;         // probe tuples per join unit
@@ -334,7 +337,7 @@ plan_kernel(PlanArgs a) {
             }
         }
     }
-    if (a.nrel < 2) return;
+    if (!a.with_units) return;
     const uint32_t* offB = a.rel[0].off;
     const uint32_t* offP = a.rel[1].off;
     for (uint32_t p = gtid; p < nb; p += gsz) {
@@ -377,6 +380,7 @@ struct ScatterArgs {
     uint32_t shift, bits;
     uint32_t* cursors;
     uint32_t cursor_stride;      // words between consecutive cursors
+    uint32_t ntiles;             // pass 1: number of tiles (the grid may be smaller: CTAs loop)
     const uint4* tiles;          // pass 2 only
     const uint32_t* num_tiles;   // pass 2 only
 };
@@ -397,6 +401,10 @@ scatter_kernel(ScatterArgs a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t nb = 1u << a.bits, mask = nb - 1u;
 
+    // One tile per CTA when the grid covers all tiles; a smaller (persistent) grid loops -- used by
+    // the multi-GPU peer scatter so that it leaves SM resources to concurrently running kernels.
+    const uint32_t ntiles_total = (a.tiles == nullptr) ? a.ntiles : *a.num_tiles;
+    for (uint32_t tile_id = blockIdx.x; tile_id < ntiles_total; tile_id += gridDim.x) {
     // ---- which slots does this tile cover ----
     uint32_t a0, lo, hi, cbase;
     const tup_t* in_tup = a.in_tup;
@@ -405,17 +413,16 @@ scatter_kernel(ScatterArgs a) {
         // slot pairs are 16-byte aligned, and treat slot 0 as not ours
         const uint32_t mis = (!COLUMNAR && ((size_t)in_tup & 8u)) ? 1u : 0u;
         in_tup -= mis;
-        const unsigned long long s = (unsigned long long)blockIdx.x * T;
+        const unsigned long long s = (unsigned long long)tile_id * T;
         const unsigned long long n_eff = (unsigned long long)a.n + mis;
         a0 = (uint32_t)s; lo = max(a0, mis);
         hi = (s < n_eff) ? a0 + (uint32_t)min((unsigned long long)T, n_eff - s) : a0;
         cbase = 0;
     } else {
-        if (blockIdx.x >= *a.num_tiles) return;
-        const uint4 td = __ldg(a.tiles + blockIdx.x);
+        const uint4 td = __ldg(a.tiles + tile_id);
         a0 = td.x; lo = td.y; hi = td.z; cbase = td.w;
     }
-    if (hi <= lo) return;
+    if (hi <= lo) continue;
     if (tid < NB_MAX) s_hist[tid] = 0;
     __syncthreads();
     const bool full = (lo == a0) && (hi - a0 == T);
@@ -550,6 +557,7 @@ scatter_kernel(ScatterArgs a) {
             bulk_wait_read0();   // shared memory must stay valid until the engine has read it
         }
     }
+    }   // tile loop (the barrier at the top of the next iteration orders the reuse of shared memory)
 }
 
 // ------------------------------------------------------------------------------------------

@@ -67,6 +67,10 @@ class GpuOps:
         self.engine = JoinEngine(self.cap_R, self.cap_S, device)
         self.stream = torch.cuda.Stream(device)
         self.engine.use_torch_stream(self.stream)
+        # overlap: local radix passes run on a high-priority stream so that their CTAs get SM
+        # slots ahead of the (NVLink-bound) peer-scatter kernel of the other relation
+        self.stream_local = torch.cuda.Stream(device, priority=-1)
+        self.stream_shuffle = torch.cuda.Stream(device)
         dev = torch.device("cuda", device)
         self.dev = dev
         self.send = self.recv = None
@@ -89,6 +93,34 @@ class GpuOps:
     def scatter_peers(self, keys, pays, G, shift, peer_ptrs, offsets):
         self.engine.shuffle_scatter_peers(keys, pays, G, shift, peer_ptrs, offsets)
         return self.engine.get_option("last_shuffle_us") * 1e-3   # kernel time, ms
+
+    def overlapped_p2p(self, dist, group, rels, G, shift, peers, write_at, n_in, own_ptrs):
+        """Shuffle R -> [all ranks done] -> local passes of R  ||  shuffle S -> [done] -> local passes
+        of S -> join.  The cross-rank "done" points are 1-element NCCL all-reduces enqueued on the
+        streams, so nothing blocks the host until the final result read-back."""
+        torch, eng = self.torch, self.engine
+        sA, sB = self.stream_local, self.stream_shuffle
+        cur = torch.cuda.current_stream(self.device)
+        sA.wait_stream(cur); sB.wait_stream(cur)
+        tok = [torch.zeros(1, dtype=torch.int32, device=self.dev) for _ in range(2)]
+        eng.stage_begin(n_in[0], n_in[1], sA)
+        (Rk, Rp), (Sk, Sp) = rels
+        eng.shuffle_scatter_peers_async(0, Rk, Rp, G, shift, peers[0], write_at[0], sA)
+        r_sent = torch.cuda.Event()
+        r_sent.record(sA)
+        with torch.cuda.stream(sA):
+            dist.all_reduce(tok[0], group=group)          # every rank's R stores have landed
+        eng.stage_partition(0, own_ptrs[0], sA)
+        sB.wait_event(r_sent)                             # one relation on NVLink at a time
+        eng.shuffle_scatter_peers_async(1, Sk, Sp, G, shift, peers[1], write_at[1], sB)
+        with torch.cuda.stream(sB):
+            dist.all_reduce(tok[1], group=group)          # every rank's S stores have landed
+        eng.stage_partition(1, own_ptrs[1], sB)
+        eng.stage_join(sB)
+        m, c = eng.stage_finish()
+        sA.synchronize()
+        ms = eng.shuffle_scatter_ms(0) + eng.shuffle_scatter_ms(1)
+        return m, c, {"shuffle_scatter_ms": ms}
 
     def exchange_counts(self, dist, group, mine):
         """All ranks' count vectors in ONE small NCCL all-gather (doubles as a barrier)."""
@@ -117,7 +149,7 @@ class ShardedJoin:
     with its local shard (device int32 columns) and all ranks get the global result."""
 
     def __init__(self, max_local_R: int, max_local_S: int, device: int | None = None, group=None,
-                 mode: str = "nccl", ops=None, part_target: int = 4096):
+                 mode: str = "nccl", ops=None, part_target: int = 4096, overlap: bool = True):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -127,6 +159,7 @@ class ShardedJoin:
             raise ValueError("world size must be a power of two (GPU id = radix bits)")
         self.gpu_bits = int(math.log2(self.world))
         self.mode = mode
+        self.overlap = overlap
         self.part_target = part_target
         self.ops = ops if ops is not None else GpuOps(max_local_R, max_local_S, device,
                                                       with_send_buffers=(mode == "nccl"))
@@ -222,21 +255,25 @@ class ShardedJoin:
             both = self._all_gather_counts(mine)
             all_counts = [both[:, :G], both[:, G:]]
             shuffle_ms = 0.0
-            for which, (k, p) in enumerate(rels):
+            write_ats = []
+            for which in range(2):
                 recv_counts, _, write_at = receive_layout(all_counts[which], rank)
                 n_in = int(recv_counts.sum())
                 cap = ops.cap_R if which == 0 else ops.cap_S
                 if n_in > cap:
                     raise RuntimeError(f"rank {rank}: receives {n_in} tuples, capacity {cap}")
-                shuffle_ms += ops.scatter_peers(k, p, G, shift, self._peers[which], write_at) or 0.0
+                write_ats.append(write_at)
                 local_n[which] = n_in
-            dist.barrier(group=self.group)   # every rank's stores have landed
-        if self.mode == "p2p":
-            m, c, tm = ops.local_join_ptrs(self._own[0], local_n[0], self._own[1], local_n[1])
-        else:
+            if self.overlap and hasattr(ops, "overlapped_p2p"):
+                m, c, tm = ops.overlapped_p2p(dist, self.group, rels, G, shift, self._peers, write_ats, local_n, self._own)
+            else:
+                for which, (k, p) in enumerate(rels):
+                    shuffle_ms += ops.scatter_peers(k, p, G, shift, self._peers[which], write_ats[which]) or 0.0
+                dist.barrier(group=self.group)   # every rank's stores have landed
+                m, c, tm = ops.local_join_ptrs(self._own[0], local_n[0], self._own[1], local_n[1])
+                tm = dict(tm, shuffle_scatter_ms=shuffle_ms)
+        if self.mode != "p2p":
             m, c, tm = ops.local_join(local_n[0], local_n[1])
-        if self.mode == "p2p":
-            tm = dict(tm, shuffle_scatter_ms=shuffle_ms)
         res = ops.result_tensor(m, c)
         dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
         vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]

@@ -21,7 +21,8 @@ C_ABI_SYMBOLS = [
     "gj_create", "gj_destroy", "gj_last_error", "gj_version", "gj_set_stream", "gj_set_option",
     "gj_get_option", "gj_join_aggregate", "gj_join_aggregate_tuples", "gj_join_aggregate_host",
     "gj_join_materialize", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
-    "gj_shuffle_count", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
+    "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_stage_begin",
+    "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
     "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_device_synchronize", "gj_flush_l2",
     "gj_kernel_launch_count",
@@ -91,6 +92,12 @@ def lib() -> C.CDLL:
     L.gj_shuffle_split.argtypes = [vp, i32p, i32p, u64, u32, u32, vp, C.POINTER(u64)]
     L.gj_shuffle_scatter_peers.argtypes = [vp, i32p, i32p, u64, u32, u32, C.POINTER(vp), C.POINTER(u64)]
     L.gj_shuffle_count.argtypes = [vp, i32p, u64, u32, u32, C.POINTER(u64)]
+    L.gj_shuffle_scatter_peers_async.argtypes = [vp, C.c_int, i32p, i32p, u64, u32, u32, C.POINTER(vp), C.POINTER(u64), vp]
+    L.gj_shuffle_scatter_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    L.gj_stage_begin.argtypes = [vp, u64, u64, vp]
+    L.gj_stage_partition.argtypes = [vp, C.c_int, vp, vp]
+    L.gj_stage_join.argtypes = [vp, vp]
+    L.gj_stage_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.gj_generate_unique.argtypes = [vp, i32p, i32p, u64, u64, u64, u32, u32]
     L.gj_bijection.argtypes = [u64, u64, u32]
     L.gj_bijection.restype = u32
@@ -292,6 +299,34 @@ class JoinEngine:
         offs = (C.c_uint64 * n_gpus)(*[int(o) for o in peer_offsets])
         _check(self._L.gj_shuffle_scatter_peers(self._ctx, _dev_ptr(keys, n, "keys"), _dev_ptr(pays, n, "pays"), n,
                                                 n_gpus, gpu_shift, bases, offs))
+
+    # -- asynchronous / staged entry points (multi-GPU overlap) ------------------------------
+    def shuffle_scatter_peers_async(self, which: int, keys, pays, n_gpus: int, gpu_shift: int, peer_ptrs,
+                                    peer_offsets, stream):
+        n = keys.numel()
+        bases = (C.c_void_p * n_gpus)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        offs = (C.c_uint64 * n_gpus)(*[int(o) for o in peer_offsets])
+        _check(self._L.gj_shuffle_scatter_peers_async(self._ctx, which, _dev_ptr(keys, n, "keys"), _dev_ptr(pays, n, "pays"),
+                                                      n, n_gpus, gpu_shift, bases, offs, C.c_void_p(stream.cuda_stream)))
+
+    def shuffle_scatter_ms(self, which: int) -> float:
+        ms = C.c_float()
+        _check(self._L.gj_shuffle_scatter_ms(self._ctx, which, C.byref(ms)))
+        return float(ms.value)
+
+    def stage_begin(self, nR: int, nS: int, stream):
+        _check(self._L.gj_stage_begin(self._ctx, nR, nS, C.c_void_p(stream.cuda_stream)))
+
+    def stage_partition(self, side: int, ptr: int, stream):
+        _check(self._L.gj_stage_partition(self._ctx, side, C.c_void_p(ptr), C.c_void_p(stream.cuda_stream)))
+
+    def stage_join(self, stream):
+        _check(self._L.gj_stage_join(self._ctx, C.c_void_p(stream.cuda_stream)))
+
+    def stage_finish(self):
+        m, c = C.c_uint64(), C.c_uint64()
+        _check(self._L.gj_stage_finish(self._ctx, C.byref(m), C.byref(c)))
+        return int(m.value), int(c.value)
 
     # -- synthetic data ---------------------------------------------------------------------
     def generate_unique(self, keys, pays, row_begin: int, n_total: int, seed: int, pay_seed: int):

@@ -74,8 +74,10 @@ int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
  *   "pass1_bits"   bits of the first pass, 0 = choose
  *   "scatter_cfg"  scatter kernel shape variant (0 = default)
  *   "unit_tuples"  probe-side work-unit size in tuples (skew splitting), 0 = default
+ *   "scatter_cfg1"/"scatter_cfg2" per-pass variants; 255 = measured best per fan-out (default)
+ *   "join_cfg"     join kernel shape variant (0 = default)
  *   "gpu_bits"     number of key bits above the radix field consumed by the multi-GPU shuffle
- *   "use_graph"    1 = replay the pipeline from a CUDA graph when shapes repeat */
+ *   "shuffle_grid" persistent CTA count of the peer-store scatter (0 = one tile per CTA) */
 int gj_set_option(gj_ctx* ctx, const char* name, int64_t value);
 int gj_get_option(gj_ctx* ctx, const char* name, int64_t* value);
 
@@ -140,6 +142,28 @@ int gj_shuffle_split(gj_ctx* ctx, const int32_t* d_keys, const int32_t* d_pays, 
 int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, const int32_t* d_pays,
                              uint64_t n, uint32_t n_gpus, uint32_t gpu_shift,
                              void* const* d_peer_bases, const uint64_t* h_peer_offsets);
+
+/* Asynchronous peer-store scatter of relation `which` (0 = R, 1 = S) on `cuda_stream`: returns
+ * without synchronising; per-relation cursor/base buffers let both relations be in flight.
+ * With option "shuffle_grid" = k > 0 the kernel runs as k persistent CTAs that loop over the
+ * tiles, leaving SM resources to kernels running concurrently on other streams.
+ * gj_shuffle_scatter_ms waits for that kernel and returns its duration. */
+int gj_shuffle_scatter_peers_async(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays,
+                                   uint64_t n, uint32_t n_gpus, uint32_t gpu_shift,
+                                   void* const* d_peer_bases, const uint64_t* h_peer_offsets,
+                                   void* cuda_stream);
+int gj_shuffle_scatter_ms(gj_ctx* ctx, int which, float* ms);
+
+/* Staged form of gj_join_aggregate_tuples for overlapping with the shuffle: begin fixes the plan
+ * from (nR, nS); partition(side) enqueues histogram + scan + radix passes of one relation's
+ * received packed tuples on a stream of the caller's choice (the two sides may use different
+ * streams; they serialise only on the shared first-pass buffer); join enqueues unit planning +
+ * the join after both sides; finish synchronises and returns the aggregate.  Options
+ * "radix_bits" / "gpu_bits" as for gj_join_aggregate_tuples. */
+int gj_stage_begin(gj_ctx* ctx, uint64_t nR, uint64_t nS, void* cuda_stream);
+int gj_stage_partition(gj_ctx* ctx, int side, const void* d_tuples, void* cuda_stream);
+int gj_stage_join(gj_ctx* ctx, void* cuda_stream);
+int gj_stage_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum);
 
 /* CUDA IPC plumbing for the peer-store variant when every GPU is driven by its own process:
  * export a gj_malloc_device allocation as a 64-byte handle, open a peer's handle (peer access is

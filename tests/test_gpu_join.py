@@ -245,6 +245,30 @@ def test_host_entry_end_to_end(gj, orc, eng, torch_cuda):
     eng.set_option("h2d_chunk", 8 << 20)
 
 
+def test_staged_pipeline_equals_monolithic(gj, orc, eng, torch_cuda):
+    """gj_stage_begin/partition/join/finish (the multi-GPU overlap entry points): the two sides are
+    partitioned on different streams, in either order, and give the oracle's result."""
+    reset(eng)
+    torch = torch_cuda
+    rng = np.random.default_rng(41)
+    for nR, nS in ((600_000, 900_001), (1_200_000, 300_000), (5, 0)):
+        Rk, Sk = rnd(rng, nR, 0, 1 << 19), rnd(rng, nS, 0, 1 << 19)
+        Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+        want = orc.join_check(Rk, Rp, Sk, Sp)
+        Rt = torch.from_numpy(np.stack([Rk, Rp], axis=1).copy()).cuda()
+        St = torch.from_numpy(np.stack([Sk, Sp], axis=1).copy()).cuda()
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+        torch.cuda.synchronize()
+        for order in ((0, 1), (1, 0)):
+            eng.stage_begin(nR, nS, s1)
+            for side in order:
+                eng.stage_partition(side, (Rt if side == 0 else St).data_ptr(), s2 if side == 0 else s1)
+            eng.stage_join(s1)
+            assert eng.stage_finish() == (want.matches, want.checksum)
+    with pytest.raises(gj.GJError):
+        eng.stage_join(torch.cuda.Stream())        # no stage_begin
+
+
 # ------------------------------------------------------------------------------- materialise
 @pytest.mark.parametrize("nR,nS,hi", [(0, 5, 4), (2000, 3000, 50), (1 << 18, 1 << 19, 1 << 18), (900_000, 300_000, 1 << 19)])
 def test_materialize_pairs_match_oracle(gj, orc, eng, torch_cuda, nR, nS, hi):

@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_local, mode, q):
+def _worker(rank, world, port, n_local, mode, overlap, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch
@@ -29,7 +29,7 @@ def _worker(rank, world, port, n_local, mode, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         N = n_local * world
-        sj = gj.distributed.ShardedJoin(n_local, n_local, device=rank, mode=mode)
+        sj = gj.distributed.ShardedJoin(n_local, n_local, device=rank, mode=mode, overlap=overlap)
         eng = sj.ops.engine
         mk = lambda: torch.empty(n_local, dtype=torch.int32, device=f"cuda:{rank}")  # noqa: E731
         Rk, Rp, Sk, Sp = mk(), mk(), mk(), mk()
@@ -48,8 +48,8 @@ def _worker(rank, world, port, n_local, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p"])
-def test_sharded_join_on_real_gpus(mode):
+@pytest.mark.parametrize("mode,overlap", [("nccl", False), ("p2p", False), ("p2p", True)])
+def test_sharded_join_on_real_gpus(mode, overlap):
     import torch
     import torch.multiprocessing as mp
     ngpu = torch.cuda.device_count()
@@ -59,7 +59,7 @@ def test_sharded_join_on_real_gpus(mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 6_000_000, mode, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 6_000_000, mode, overlap, q)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=600) for _ in range(world)]
