@@ -63,6 +63,10 @@ static const ScatterCfg kScatter[] = {
     GJ_SC(1024, 8, 1, 0, 1),   // 9
     GJ_SC(256, 16, 1, 0, 5),   // 10
     GJ_SC(512, 16, 1, 1, 1),   // 11
+    GJ_SC(512, 8, 1, 1, 3),    // 12 TMA output at 1536 threads/SM
+    GJ_SC(1024, 4, 1, 1, 2),   // 13 TMA output at 2048 threads/SM
+    GJ_SC(1024, 4, 1, 0, 2),   // 14
+    GJ_SC(1024, 8, 1, 1, 1),   // 15
 };
 static const int kNumScatter = (int)(sizeof(kScatter) / sizeof(kScatter[0]));
 static size_t scatter_smem(const ScatterCfg& c) {
