@@ -225,7 +225,10 @@ class ShardedJoin:
 
     # -- the join ------------------------------------------------------------------------------
     def join_aggregate(self, Rk, Rp, Sk, Sp, n_R_global: int, n_S_global: int) -> ShardedResult:
+        import time
         G, rank, ops, dist = self.world, self.rank, self.ops, self.dist
+        t_host = [time.perf_counter()]
+        lap = lambda: t_host.append(time.perf_counter())  # noqa: E731
         B = self.plan_bits(min(n_R_global, n_S_global))
         ops.configure(B, self.gpu_bits)
         shift = B
@@ -252,7 +255,9 @@ class ShardedJoin:
             # both relations' counts travel in one all-gather, which is also the barrier that
             # tells every rank its peers are done reading their receive buffers
             mine = np.concatenate([ops.count(k, G, shift) for k, _ in rels])
+            lap()
             both = self._all_gather_counts(mine)
+            lap()
             all_counts = [both[:, :G], both[:, G:]]
             shuffle_ms = 0.0
             write_ats = []
@@ -274,9 +279,14 @@ class ShardedJoin:
                 tm = dict(tm, shuffle_scatter_ms=shuffle_ms)
         if self.mode != "p2p":
             m, c, tm = ops.local_join(local_n[0], local_n[1])
+        lap()
         res = ops.result_tensor(m, c)
         dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
         vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
+        lap()
+        if self.mode == "p2p" and len(t_host) == 6:
+            d = [1e3 * (b - a) for a, b in zip(t_host, t_host[1:])]
+            tm = dict(tm, host_ms={"plan": d[0], "count": d[1], "exchange": d[2], "shuffle+local": d[3], "reduce": d[4]})
         return ShardedResult(vals[0], vals[1], local_n[0], local_n[1], tm)
 
 
