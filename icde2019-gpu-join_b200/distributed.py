@@ -284,9 +284,9 @@ class ShardedJoin:
         dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
         vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
         lap()
-        if self.mode == "p2p" and len(t_host) == 6:
+        if self.mode == "p2p" and len(t_host) == 5:
             d = [1e3 * (b - a) for a, b in zip(t_host, t_host[1:])]
-            tm = dict(tm, host_ms={"plan": d[0], "count": d[1], "exchange": d[2], "shuffle+local": d[3], "reduce": d[4]})
+            tm = dict(tm, host_ms={"count": d[0], "exchange": d[1], "shuffle+local": d[2], "reduce": d[3]})
         return ShardedResult(vals[0], vals[1], local_n[0], local_n[1], tm)
 
 
