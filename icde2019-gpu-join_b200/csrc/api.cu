@@ -163,8 +163,11 @@ struct Rel {   // one input relation as handed to the pipeline
 
 static int set_func_attrs(gj_ctx* ctx) {
     if (ctx->attrs_set) return GJ_OK;
-    CK(cudaFuncSetAttribute(hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << MAX_RADIX_BITS));
-    CK(cudaFuncSetAttribute(hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << MAX_RADIX_BITS));
+    const int hist_smem = 4 << 15;   // 2^15 u32 counters or 2^16 packed u16 counters
+    CK(cudaFuncSetAttribute(hist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    CK(cudaFuncSetAttribute(hist_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    CK(cudaFuncSetAttribute(hist_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    CK(cudaFuncSetAttribute(hist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
     for (int i = 0; i < kNumScatter; ++i) {
         const int bytes = (int)scatter_smem(kScatter[i]);
         CK(cudaFuncSetAttribute(kScatter[i].col, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -393,9 +396,15 @@ static int enqueue_hist(gj_ctx* ctx, cudaStream_t s, const void* in, bool packed
     if (!n) return GJ_OK;
     const uint64_t per_cta = (uint64_t)threads * 16;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count, (n + per_cta - 1) / per_cta));
-    const size_t smem = (size_t)4 << bits;
-    if (packed) hist_kernel<true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
-    else hist_kernel<false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+    const bool p16 = bits > 15;   // two 16-bit counters per word
+    const size_t smem = p16 ? (size_t)2 << bits : (size_t)4 << bits;
+    if (packed) {
+        if (p16) hist_kernel<true, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+        else hist_kernel<true, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+    } else {
+        if (p16) hist_kernel<false, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+        else hist_kernel<false, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+    }
     LAUNCHED();
     return GJ_OK;
 }

@@ -26,7 +26,7 @@ namespace gj {
 
 typedef uint2 tup_t;  // .x = key bits, .y = payload bits
 
-constexpr int MAX_RADIX_BITS = 15;    // fine histogram: 2^15 u32 counters = 128 KB of smem
+constexpr int MAX_RADIX_BITS = 16;    // fine histogram: 128 KB of smem = 2^15 u32 or 2^16 packed u16 counters
 constexpr int MAX_PASS_BITS = 8;      // fan-out per scatter pass <= 256
 constexpr int NB_MAX = 1 << MAX_PASS_BITS;
 constexpr uint32_t CUR1_STRIDE = 1;   // words between first-pass cursors (measured: padding to one cursor per 128-byte line
@@ -45,21 +45,42 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 
 // ------------------------------------------------------------------------------------------
 // 1. Radix histogram (keys only).  digit = (key >> shift) & (2^bits - 1).
-//    Persistent grid (one 1024-thread CTA per SM), 2^bits counters in dynamic shared memory,
-//    16-byte loads, counters flushed with one global reduction per non-empty bin per CTA.
-//    Algorithmic bytes: 4 per tuple (columnar) -- the packed variant reads 8.
+//    Persistent grid (one 1024-thread CTA per SM), the 2^bits counters live in dynamic shared
+//    memory (128 KB -- only possible with Blackwell's 227 KB per CTA), 16-byte loads, counters
+//    flushed with one global reduction per non-empty bin per CTA.
+//    P16 = false: 32-bit counters, bits <= 15.  P16 = true (bits == 16): two 16-bit counters per
+//    word; the add that lifts a field to 0x8000 moves those 0x8000 counts to the global
+//    histogram at once, so a field never carries into its neighbour (that would take another
+//    32767 adds landing between that thread's add and its subtract).
+//    Algorithmic bytes: 4 per tuple (columnar) -- the packed-tuple variant reads 8.
 // ------------------------------------------------------------------------------------------
-template <bool PACKED>
+template <bool P16>
+__device__ __forceinline__ void hist_add(uint32_t* sh, uint32_t d, uint32_t* ghist) {
+    if (!P16) {
+        atomicAdd(&sh[d], 1u);
+    } else {
+        const uint32_t sft = (d & 1u) << 4;
+        const uint32_t old = atomicAdd(&sh[d >> 1], 1u << sft);
+        if (((old >> sft) & 0xFFFFu) == 0x7FFFu) {
+            atomicAdd(&ghist[d], 0x8000u);
+            atomicSub(&sh[d >> 1], 0x8000u << sft);
+        }
+    }
+}
+
+template <bool PACKED, bool P16>
 __global__ void __launch_bounds__(1024, 1)
 hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bits,
             uint32_t* __restrict__ ghist) {
     extern __shared__ uint32_t sh_hist[];
     const uint32_t nb = 1u << bits, mask = nb - 1u;
-    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) sh_hist[i] = 0;
+    const uint32_t nwords = P16 ? nb >> 1 : nb;
+    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
 
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gsz = gridDim.x * blockDim.x;
+#define GJ_HADD(key) hist_add<P16>(sh_hist, ((uint32_t)(key) >> shift) & mask, ghist)
     if (!PACKED) {
         const int32_t* keys = (const int32_t*)in;
         uint32_t head = (uint32_t)(((16u - (uint32_t)((size_t)keys & 15u)) & 15u) >> 2);
@@ -71,11 +92,7 @@ hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bi
         for (; i + 3 * gsz < nvec; i += 4 * gsz) {
             int4 k0 = __ldg(v + i), k1 = __ldg(v + i + gsz), k2 = __ldg(v + i + 2 * gsz),
                  k3 = __ldg(v + i + 3 * gsz);
-#define GJ_H4(k)                                                   \
-    atomicAdd(&sh_hist[((uint32_t)(k).x >> shift) & mask], 1u);    \
-    atomicAdd(&sh_hist[((uint32_t)(k).y >> shift) & mask], 1u);    \
-    atomicAdd(&sh_hist[((uint32_t)(k).z >> shift) & mask], 1u);    \
-    atomicAdd(&sh_hist[((uint32_t)(k).w >> shift) & mask], 1u);
+#define GJ_H4(k) GJ_HADD((k).x); GJ_HADD((k).y); GJ_HADD((k).z); GJ_HADD((k).w);
             GJ_H4(k0) GJ_H4(k1) GJ_H4(k2) GJ_H4(k3)
         }
         for (; i < nvec; i += gsz) {
@@ -85,8 +102,8 @@ hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bi
 #undef GJ_H4
         // unaligned head and the < 4 element tail
         const uint32_t tail0 = head + (nvec << 2);
-        if (gtid < head) atomicAdd(&sh_hist[((uint32_t)keys[gtid] >> shift) & mask], 1u);
-        if (tail0 + gtid < n) atomicAdd(&sh_hist[((uint32_t)keys[tail0 + gtid] >> shift) & mask], 1u);
+        if (gtid < head) GJ_HADD(keys[gtid]);
+        if (tail0 + gtid < n) GJ_HADD(keys[tail0 + gtid]);
     } else {
         const tup_t* tp = (const tup_t*)in;
         uint32_t head = (uint32_t)(((size_t)tp & 15u) ? 1u : 0u);
@@ -97,9 +114,7 @@ hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bi
         for (; i + 3 * gsz < nvec; i += 4 * gsz) {
             uint4 k0 = __ldg(v + i), k1 = __ldg(v + i + gsz), k2 = __ldg(v + i + 2 * gsz),
                   k3 = __ldg(v + i + 3 * gsz);
-#define GJ_H2(k)                                         \
-    atomicAdd(&sh_hist[((k).x >> shift) & mask], 1u);    \
-    atomicAdd(&sh_hist[((k).z >> shift) & mask], 1u);
+#define GJ_H2(k) GJ_HADD((k).x); GJ_HADD((k).z);
             GJ_H2(k0) GJ_H2(k1) GJ_H2(k2) GJ_H2(k3)
         }
         for (; i < nvec; i += gsz) {
@@ -108,13 +123,22 @@ hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bi
         }
 #undef GJ_H2
         const uint32_t tail0 = head + (nvec << 1);
-        if (gtid < head) atomicAdd(&sh_hist[(tp[gtid].x >> shift) & mask], 1u);
-        if (tail0 + gtid < n) atomicAdd(&sh_hist[(tp[tail0 + gtid].x >> shift) & mask], 1u);
+        if (gtid < head) GJ_HADD(tp[gtid].x);
+        if (tail0 + gtid < n) GJ_HADD(tp[tail0 + gtid].x);
     }
+#undef GJ_HADD
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
-        uint32_t c = sh_hist[i];
-        if (c) atomicAdd(&ghist[i], c);
+    if (!P16) {
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+            const uint32_t c = sh_hist[i];
+            if (c) atomicAdd(&ghist[i], c);
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) {
+            const uint32_t w = sh_hist[i];
+            if (w & 0xFFFFu) atomicAdd(&ghist[2 * i], w & 0xFFFFu);
+            if (w >> 16) atomicAdd(&ghist[2 * i + 1], w >> 16);
+        }
     }
 }
 

@@ -27,7 +27,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 
-def choose_radix_bits(n_build_local: int, part_target: int = 4096, max_bits: int = 15) -> int:
+def choose_radix_bits(n_build_local: int, part_target: int = 4096, max_bits: int = 16) -> int:
     """Mirror of choose_plan() in csrc/api.cu: smallest B with n >> B <= part_target."""
     b = 0
     while b < max_bits and (n_build_local >> b) > part_target:

@@ -111,4 +111,4 @@ def test_receive_layout_and_bits(gj):
     rc, ro, wa = d.receive_layout(counts, 0)
     assert wa.tolist() == [0, 0, 0]
     assert d.choose_radix_bits(128_000_000) == 15 and d.choose_radix_bits(1 << 20) == 8
-    assert d.choose_radix_bits(250_000_000) == 15 and d.choose_radix_bits(10) == 1
+    assert d.choose_radix_bits(250_000_000) == 16 and d.choose_radix_bits(10) == 1

@@ -40,7 +40,7 @@ def reset(eng):
 
 # ------------------------------------------------------------------------------- partitioner
 @pytest.mark.parametrize("n,bits", [(0, 4), (1, 1), (5, 3), (4096, 8), (4097, 8), (100_003, 0),
-                                    (1 << 20, 8), (300_000, 11), (1_000_000, 15), (777_777, 13)])
+                                    (1 << 20, 8), (300_000, 11), (1_000_000, 15), (777_777, 13), (2_000_003, 16)])
 def test_partition_matches_oracle(gj, orc, eng, torch_cuda, n, bits):
     reset(eng)
     rng = np.random.default_rng(n + bits)
@@ -80,16 +80,20 @@ def test_partition_every_scatter_variant(gj, orc, eng, torch_cuda, cfg):
 
 
 def test_partition_skewed_digit(gj, orc, eng, torch_cuda):
-    """Most of a tile falls into one digit (Zipf-like): stresses same-address shared atomics."""
+    """Most of a tile falls into one digit (Zipf-like): stresses same-address shared atomics; with
+    16 radix bits the histogram uses packed 16-bit counters and the hot bin overflows its field
+    (> 32768 hits per CTA) many times."""
     reset(eng)
     rng = np.random.default_rng(9)
-    n = 500_000
-    keys = np.where(rng.random(n) < 0.8, 77, rng.integers(0, 1 << 16, n)).astype(np.int32)
-    pays = np.arange(n, dtype=np.int32)
-    tup, off, B, _ = eng.partition(*dev(torch_cuda, keys, pays), 10)
-    c1, h1 = orc.partition_fingerprint(keys, pays, 0, B)
-    c2, h2 = orc.partition_fingerprint(np.ascontiguousarray(tup[:, 0]), np.ascontiguousarray(tup[:, 1]), 0, B)
-    assert np.array_equal(c1, c2) and np.array_equal(h1, h2)
+    for n, bits, slot in ((500_000, 10, 0), (8_000_000, 16, 1)):
+        keys = np.where(rng.random(n) < 0.8, 77, rng.integers(0, 1 << 20, n)).astype(np.int32)
+        pays = np.arange(n, dtype=np.int32)
+        tup, off, B, _ = eng.partition(*dev(torch_cuda, keys, pays), bits, slot=slot)
+        want_off, _, _ = orc.partition(keys, pays, 0, B)
+        assert np.array_equal(off, want_off.astype(np.int64))
+        c1, h1 = orc.partition_fingerprint(keys, pays, 0, B)
+        c2, h2 = orc.partition_fingerprint(np.ascontiguousarray(tup[:, 0]), np.ascontiguousarray(tup[:, 1]), 0, B)
+        assert np.array_equal(c1, c2) and np.array_equal(h1, h2)
 
 
 # ------------------------------------------------------------------------------- aggregate join
@@ -186,7 +190,7 @@ def test_every_radix_split_and_join_variant(gj, orc, eng, torch_cuda):
     Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
     want = orc.join_check(Rk, Rp, Sk, Sp)
     d = dev(torch_cuda, Rk, Rp, Sk, Sp)
-    for bits in (1, 5, 8, 9, 12, 15):
+    for bits in (1, 5, 8, 9, 12, 15, 16):
         eng.set_option("radix_bits", bits)
         got = eng.join_aggregate(*d)
         assert (got.matches, got.checksum) == (want.matches, want.checksum), bits
@@ -391,6 +395,6 @@ def test_error_behaviour(gj, eng, torch_cuda):
     with pytest.raises(gj.GJError):
         eng.set_option("no_such_option", 1)
     with pytest.raises(gj.GJError):
-        eng.set_option("radix_bits", 16)
+        eng.set_option("radix_bits", 17)
     with pytest.raises(gj.GJError):
         gj.JoinEngine(16, 16, device=99)
