@@ -52,6 +52,8 @@ WORKLOADS = {
     "small": (1 << 20, 1 << 20, "unique", 0.0),
     "zipf0.5": (128_000_000, 128_000_000, "zipf", 0.5),
     "zipf1.0": (128_000_000, 128_000_000, "zipf", 1.0),
+    # BASELINE config 5: 2e9 x 2e9 tuples in TOTAL, sharded over the GPUs (strong scaling)
+    "cfg5": (2_000_000_000, 2_000_000_000, "unique", 0.0),
 }
 
 
@@ -361,6 +363,57 @@ def single_gpu(args):
     print(json.dumps(line))
 
 
+def cfg5_single(args):
+    """BASELINE config 5 on ONE GPU (the strong-scaling denominator): 2e9 x 2e9 device-generated
+    tuples.  Build partitions are 30.5 K tuples at the 16-bit radix cap, so the join runs its
+    multi-chunk steps (8 build chunks x 8 probe chunks per partition) -- reported as measured."""
+    import torch
+    import __graft_entry__ as ge
+    gj = ge.load_package()
+    w = args.workload
+    n = WORKLOADS[w][0]
+    torch.cuda.set_device(0)
+    eng = gj.JoinEngine(n, n, 0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
+    stream = torch.cuda.Stream()
+    eng.use_torch_stream(stream)
+    cols = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(4)]
+    eng.generate_unique(cols[0], cols[1], 0, n, 4, 40)
+    eng.generate_unique(cols[2], cols[3], 0, n, 5, 50)
+    cols[1].fill_(1); cols[3].fill_(1)
+    torch.cuda.synchronize()
+    steps, warm = min(args.steps, 3), 1
+    for _ in range(warm):
+        res = eng.join_aggregate(*cols)
+    launches0 = gj.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    tms = []
+    for _ in range(steps):
+        res = eng.join_aggregate(*cols)
+        tms.append(res.timings.as_dict())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if res.matches != n or res.checksum != n:
+        raise SystemExit(f"WRONG RESULT: {res.matches} {res.checksum}, expected {n}")
+    ms_step = e0.elapsed_time(e1) / steps
+    peak, peak_src = measured_peak()
+    t = tms[-1]
+    line = base_line(args, w, 1)
+    line.update({"scaling": "strong", "steps": steps, "warmup": warm, "value": 2 * n / (ms_step * 1e-3), "ms_per_step": ms_step,
+                 "e2e": None, "gpu_launches": int(gj.kernel_launch_count() - launches0),
+                 "roofline": {"bound": "hbm", "kernel": "scatter_kernel", "achieved": 16.0 * 2 * n * 2 / (t["part_ms"] * 1e-3) / 1e9,
+                              "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                              "per_phase_ms": {k: t[k] for k in ("hist_ms", "part_ms", "join_ms", "total_ms")}},
+                 "plan": {"radix_bits": t["radix_bits"], "pass1_bits": t["pass1_bits"], "pass2_bits": t["pass2_bits"]},
+                 "checked": f"matches == checksum == {n}"})
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
+    print(json.dumps(line))
+    eng.close()
+
+
 def multi_gpu(args):
     import torch
     import torch.distributed as dist
@@ -373,7 +426,10 @@ def multi_gpu(args):
     w = args.workload
     nR, nS, kind, z = WORKLOADS[w]
     if kind != "unique":
-        raise SystemExit("multi-GPU bench supports the unique-key workloads (B, small)")
+        raise SystemExit("multi-GPU bench supports the unique-key workloads (B, small, cfg5)")
+    strong = (w == "cfg5")
+    if strong:                      # fixed total, per-GPU share shrinks with N
+        nR, nS = nR // world, nS // world
     NR, NS = nR * world, nS * world
     sj = gj.distributed.ShardedJoin(nR, nS, device=local, mode=args.shuffle, overlap=not args.no_overlap)
     for kv in args.opt:
@@ -388,7 +444,8 @@ def multi_gpu(args):
         raise SystemExit("unique workloads need |R| == |S|")
     cols[1].fill_(1); cols[3].fill_(1)
     expect = NS
-    host = [c.cpu().pin_memory() for c in cols]
+    do_e2e = nR + nS <= 600_000_000
+    host = [c.cpu().pin_memory() for c in cols] if do_e2e else None
     torch.cuda.synchronize()
 
     def step():
@@ -422,20 +479,25 @@ def multi_gpu(args):
             c.copy_(h, non_blocking=True)
         torch.cuda.synchronize()
         return step()
-    e2e_step()
-    torch.cuda.synchronize(); dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    e2 = torch.tensor([float("nan")], device=dev)
+    if do_e2e:
         e2e_step()
-    torch.cuda.synchronize(); dist.barrier()
-    e2 = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device=dev)
-    dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize(); dist.barrier()
+        e2 = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device=dev)
+        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
     if rank == 0:
         peak, peak_src = measured_peak()
         line = base_line(args, w, world)
+        if strong:
+            line["scaling"] = "strong"
+            line["config"].update({"per_gpu_R": nR, "per_gpu_S": nS})
         tm = r.phases_ms
         line.update({"value": (NR + NS) / (ms_step * 1e-3), "ms_per_step": ms_step,
-                     "e2e": {"value": (NR + NS) / (float(e2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(e2.item()),
+                     "e2e": None if not do_e2e else {"value": (NR + NS) / (float(e2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(e2.item()),
                              "h2d_bytes_per_step": 8 * (NR + NS), "d2h_bytes_per_step": 32 * world,
                              "api": "ShardedJoin.join_aggregate after per-rank H2D of pinned host shards"},
                      "gpu_launches": int(launches) * world, "clocks": clocks,
@@ -486,6 +548,8 @@ def main():
         print(json.dumps(line))
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus == 1 and args.workload == "cfg5":
+        return cfg5_single(args)
     if world > 1 or args.gpus > 1:
         if world == 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (see the module docstring)")
