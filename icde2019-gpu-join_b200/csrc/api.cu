@@ -48,8 +48,9 @@ static int fail(int code, const char* fmt, ...) {
 // kernel variant tables
 // ------------------------------------------------------------------------------------------
 typedef void (*scatter_fn)(ScatterArgs);
-struct ScatterCfg { int threads, ipt, mode, out; scatter_fn col, packed; };
-#define GJ_SC(T, I, M, O, B) { T, I, M, O, scatter_kernel<T, I, M, O, true, B>, scatter_kernel<T, I, M, O, false, B> }
+struct ScatterCfg { int threads, ipt, mode, out; scatter_fn col, packed, col_persist; };
+#define GJ_SC(T, I, M, O, B) { T, I, M, O, scatter_kernel<T, I, M, O, true, B>, scatter_kernel<T, I, M, O, false, B>, \
+                               scatter_kernel<T, I, M, O, true, B, true> }
 static const ScatterCfg kScatter[] = {
     GJ_SC(256, 16, 1, 0, 4),   // 0 default: two shared atomics, 8-byte stores, 4 CTAs/SM
     GJ_SC(256, 16, 0, 0, 3),   // 1 rank registers
@@ -104,10 +105,12 @@ struct RelMeta {
 };
 
 constexpr uint32_t FINE_MAX = 1u << MAX_RADIX_BITS;
+constexpr uint32_t MAX3_RADIX_BITS = 21;   // three passes: 8 + 8 + up to 5 bits
+constexpr uint32_t NB3_MAX = 1u << MAX3_RADIX_BITS;
 constexpr uint32_t SCAN_TILES_MAX = FINE_MAX / SCAN_TILE;
 constexpr int N_EVENTS = 64;
 
-struct Plan { uint32_t B, b1, b2; };
+struct Plan { uint32_t B = 0, b1 = 0, b2 = 0, b3 = 0; };   // b3 != 0: three passes, b1 + b2 == 16
 
 struct gj_ctx {
     int device = 0, sm_count = 0;
@@ -137,6 +140,19 @@ struct gj_ctx {
     uint32_t* shuf_cur[2] = {nullptr, nullptr};      // device: per-destination cursors of relation 0/1
     tup_t** shuf_bases[2] = {nullptr, nullptr};      // device: per-destination base pointers
     unsigned char* h_shuf = nullptr;                 // pinned staging for the two above
+    // third-pass state (allocated on first use: build sides beyond 2^28 tuples)
+    struct P3 {
+        uint32_t* ghist3[2] = {nullptr, nullptr};       // 2^MAX3 counters per relation (fully written by sub_hist)
+        uint32_t* off3[2] = {nullptr, nullptr};         // 2^MAX3 + 1 fine offsets
+        uint32_t* cur3[2] = {nullptr, nullptr};
+        uint32_t* tile_prefix[2] = {nullptr, nullptr};  // 65536 + 1
+        uint4* tiles[2] = {nullptr, nullptr};
+        uint32_t* unit_base = nullptr;
+        unsigned char* zero = nullptr; size_t zero_bytes = 0;
+        unsigned long long* desc[5] = {};               // off3 R, off3 S, units, tiles R, tiles S
+        uint32_t* ticket[5] = {};
+        unsigned char* block = nullptr;
+    } p3;
     unsigned char* zero_role[2] = {nullptr, nullptr};
     unsigned char* zero_common = nullptr;
     size_t zero_role_bytes = 0, zero_common_bytes = 0;
@@ -172,6 +188,7 @@ static int set_func_attrs(gj_ctx* ctx) {
         const int bytes = (int)scatter_smem(kScatter[i]);
         CK(cudaFuncSetAttribute(kScatter[i].col, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         CK(cudaFuncSetAttribute(kScatter[i].packed, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        CK(cudaFuncSetAttribute(kScatter[i].col_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
     for (int i = 0; i < kNumJoin; ++i) {
         CK(cudaFuncSetAttribute(kJoin[i].agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_agg));
@@ -193,6 +210,7 @@ extern "C" void gj_destroy(gj_ctx* ctx) {
     cudaFree(ctx->out[0]); cudaFree(ctx->out[1]); cudaFree(ctx->scratch);
     cudaFree(ctx->zero_block); cudaFree(ctx->meta_block); cudaFree(ctx->units);
     cudaFree(ctx->d_dst_bases); cudaFree(ctx->flush_buf); cudaFree(ctx->tiles_block);
+    cudaFree(ctx->p3.block); cudaFree(ctx->p3.zero);
     for (int i = 0; i < 4; ++i) cudaFree(ctx->d_in[i]);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -342,7 +360,7 @@ extern "C" int gj_set_option(gj_ctx* ctx, const char* name, int64_t v) {
     if ((p == &ctx->opt_scatter_cfg1 || p == &ctx->opt_scatter_cfg2) && v >= kNumScatter && v != 255)
         return fail(GJ_ERR_ARG, "%s %lld out of range [0,%d)", name, (long long)v, kNumScatter);
     if (p == &ctx->opt_join_cfg && v >= kNumJoin) return fail(GJ_ERR_ARG, "join_cfg out of range [0,%d)", kNumJoin);
-    if (p == &ctx->opt_radix_bits && v > MAX_RADIX_BITS) return fail(GJ_ERR_ARG, "radix_bits <= %d", MAX_RADIX_BITS);
+    if (p == &ctx->opt_radix_bits && v > MAX3_RADIX_BITS) return fail(GJ_ERR_ARG, "radix_bits <= %d", (int)MAX3_RADIX_BITS);
     if (p == &ctx->opt_pass1_bits && v > MAX_PASS_BITS) return fail(GJ_ERR_ARG, "pass1_bits <= %d", MAX_PASS_BITS);
     if (p == &ctx->opt_unit && v && v < 1024) return fail(GJ_ERR_ARG, "unit_tuples >= 1024");
     if (p == &ctx->opt_gpu_bits && v > 8) return fail(GJ_ERR_ARG, "gpu_bits <= 8");
@@ -370,14 +388,19 @@ extern "C" int gj_get_option(gj_ctx* ctx, const char* name, int64_t* v) {
 // (the reference freezes log_parts1 = 8, log_parts2 = 5 at compile time, common.h:51-52)
 // ------------------------------------------------------------------------------------------
 
-static Plan choose_plan(const gj_ctx* ctx, uint64_t n_build, uint32_t forced_bits) {
+static Plan choose_plan(const gj_ctx* ctx, uint64_t n_build, uint32_t forced_bits, bool allow3 = false) {
     Plan p;
     uint32_t B = forced_bits ? forced_bits : (uint32_t)ctx->opt_radix_bits;
+    const uint32_t cap = allow3 ? MAX3_RADIX_BITS : (uint32_t)MAX_RADIX_BITS;
     if (!B) {
         const uint64_t target = (uint64_t)ctx->opt_part_target;
-        while (B < (uint32_t)MAX_RADIX_BITS && (n_build >> B) > target) ++B;
+        while (B < cap && (n_build >> B) > target) ++B;
     }
-    B = std::min<uint32_t>(B, MAX_RADIX_BITS);
+    B = std::min<uint32_t>(B, cap);
+    if (B > (uint32_t)MAX_RADIX_BITS) {   // third pass on the low bits of every second-level partition
+        p.B = B; p.b1 = 8; p.b2 = 8; p.b3 = B - 16;
+        return p;
+    }
     if (B <= (uint32_t)MAX_PASS_BITS) { p.b1 = B; p.b2 = 0; }
     else {
         p.b1 = ctx->opt_pass1_bits ? (uint32_t)ctx->opt_pass1_bits : B / 2;   // measured: the smaller fan-out first
@@ -426,17 +449,14 @@ static int enqueue_scan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, u
     ScanArgs a;
     for (uint32_t r = 0; r < 2; ++r) {
         const RelMeta& m = ctx->meta[r < nrel ? first + (int)r : first];
-        a.seq[r].in = m.ghist; a.seq[r].out = m.off; a.seq[r].desc = m.desc; a.seq[r].ticket = m.ticket;
+        a.seq[r].in = m.ghist; a.seq[r].in2 = nullptr; a.seq[r].out = m.off; a.seq[r].desc = m.desc; a.seq[r].ticket = m.ticket;
+        a.seq[r].mode = SCAN_PLAIN; a.seq[r].param = 0;
     }
-    a.seq[2].in = nullptr; a.seq[2].out = ctx->unit_base; a.seq[2].desc = ctx->unit_desc; a.seq[2].ticket = ctx->unit_ticket;
-    a.nb = nb; a.unit = unit_tuples(ctx);
-    a.seq_base = 0;
-    if (nrel == 0) {           // unit sequence only; it reads the histograms of roles 0 and 1
-        for (uint32_t r = 0; r < 2; ++r) a.seq[r].in = ctx->meta[r].ghist;
-        a.seq_base = 2;
-    } else if (nrel == 1 && first == 1) {   // a single relation in role 1: sequence slot 0 carries it
-        a.seq_base = 0;
-    }
+    a.seq[2].in = ctx->meta[0].ghist; a.seq[2].in2 = ctx->meta[1].ghist; a.seq[2].out = ctx->unit_base;
+    a.seq[2].desc = ctx->unit_desc; a.seq[2].ticket = ctx->unit_ticket;
+    a.seq[2].mode = SCAN_UNITS; a.seq[2].param = unit_tuples(ctx);
+    a.nb = nb;
+    a.seq_base = nrel == 0 ? 2 : 0;   // nrel == 0: unit sequence only
     dim3 grid((nb + SCAN_TILE - 1) / SCAN_TILE, nrel == 0 ? 1 : (with_units ? 3 : nrel));
     scan_lookback_kernel<<<grid, SCAN_THREADS, 0, s>>>(a);
     LAUNCHED();
@@ -509,14 +529,15 @@ static int fill_pass_times(gj_ctx* ctx, gj_timings* t, const Plan& pl, int nrole
 }
 
 static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup_t* prb, const Plan& pl,
-                        uint64_t n_bld, uint64_t n_prb, bool mat, int32_t* out_b, int32_t* out_p, uint64_t cap) {
+                        uint64_t n_bld, uint64_t n_prb, bool mat, int32_t* out_b, int32_t* out_p, uint64_t cap,
+                        const uint32_t* num_units = nullptr) {
     (void)n_bld;
     int cfg = (int)ctx->opt_join_cfg;
     if (mat && kJoin[cfg].smem_mat > (size_t)227 * 1024) cfg = 2;   // pair staging needs 16 KB: smaller rings
     const JoinCfg& jc = kJoin[cfg];
     JoinArgs a;
     a.bld = bld; a.prb = prb;
-    a.units = ctx->units; a.num_units = ctx->unit_base + (1u << pl.B);
+    a.units = ctx->units; a.num_units = num_units ? num_units : ctx->unit_base + (1u << pl.B);
     a.hash_shift = pl.B + (uint32_t)ctx->opt_gpu_bits;
     a.result = ctx->result;
     a.out_bld_pay = out_b; a.out_prb_pay = out_p; a.cap = cap;
@@ -532,7 +553,141 @@ static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup
 
 static void fill_plan(gj_timings* t, const Plan& pl) {
     if (!t) return;
-    t->radix_bits = pl.B; t->pass1_bits = pl.b1; t->pass2_bits = pl.b2;
+    t->radix_bits = pl.B; t->pass1_bits = pl.b1; t->pass2_bits = pl.b2; t->pass3_bits = pl.b3;
+}
+
+// ------------------------------------------------------------------------------------------
+// three-pass partitioning (more than 16 radix bits)
+// ------------------------------------------------------------------------------------------
+static int ensure_pass3(gj_ctx* ctx) {
+    gj_ctx::P3& q = ctx->p3;
+    if (q.block) return GJ_OK;
+    const uint64_t mx = std::max(ctx->maxR, ctx->maxS);
+    const size_t tiles_cap = mx / 2048 + FINE_MAX + 16;
+    size_t b = 0;
+    size_t o_h[2], o_o[2], o_c[2], o_tp[2], o_t[2];
+    for (int r = 0; r < 2; ++r) {
+        o_h[r] = b; b += (size_t)NB3_MAX * 4;
+        o_o[r] = b; b += ((size_t)NB3_MAX + 4) * 4;
+        o_c[r] = b; b += (size_t)NB3_MAX * 4;
+        o_tp[r] = b; b += ((size_t)FINE_MAX + 4) * 4;
+        o_t[r] = b; b += tiles_cap * sizeof(uint4);
+    }
+    const size_t o_ub = b; b += ((size_t)NB3_MAX + 4) * 4;
+    if (cudaMalloc(&q.block, b) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "third-pass metadata (%.1f MB)", b * 1e-6); }
+    for (int r = 0; r < 2; ++r) {
+        q.ghist3[r] = reinterpret_cast<uint32_t*>(q.block + o_h[r]);
+        q.off3[r] = reinterpret_cast<uint32_t*>(q.block + o_o[r]);
+        q.cur3[r] = reinterpret_cast<uint32_t*>(q.block + o_c[r]);
+        q.tile_prefix[r] = reinterpret_cast<uint32_t*>(q.block + o_tp[r]);
+        q.tiles[r] = reinterpret_cast<uint4*>(q.block + o_t[r]);
+    }
+    q.unit_base = reinterpret_cast<uint32_t*>(q.block + o_ub);
+    // zeroed per call: scan descriptors + tickets of the five third-level scans
+    const size_t per = (size_t)(NB3_MAX / SCAN_TILE) * sizeof(unsigned long long) + 16;
+    q.zero_bytes = 5 * per;
+    CK(cudaMalloc(&q.zero, q.zero_bytes));
+    for (int i = 0; i < 5; ++i) {
+        q.desc[i] = reinterpret_cast<unsigned long long*>(q.zero + i * per);
+        q.ticket[i] = reinterpret_cast<uint32_t*>(q.zero + i * per + (size_t)(NB3_MAX / SCAN_TILE) * sizeof(unsigned long long));
+    }
+    // the unit list must cover 2^21 partitions
+    const uint64_t need = mx / 1024 + NB3_MAX + 16;
+    if (ctx->units_cap < need) {
+        CK(cudaFree(ctx->units));
+        ctx->units = nullptr;
+        CK(cudaMalloc(&ctx->units, need * sizeof(uint4)));
+        ctx->units_cap = need;
+    }
+    return GJ_OK;
+}
+
+static int enqueue_scan_one(gj_ctx* ctx, cudaStream_t s, const ScanSeq& seq, uint32_t nb) {
+    ScanArgs a;
+    a.seq[0] = a.seq[1] = a.seq[2] = seq;
+    a.nb = nb; a.seq_base = 0;
+    dim3 grid((nb + SCAN_TILE - 1) / SCAN_TILE, 1);
+    scan_lookback_kernel<<<grid, SCAN_THREADS, 0, s>>>(a);
+    LAUNCHED();
+    return GJ_OK;
+}
+
+// passes 1-3 of one relation; on return its tuples sit in `dst` grouped into 2^B partitions and
+// p3.off3[role] holds the offsets.  Level-2 (16-bit) histogram/offsets/cursors/tiles of both
+// relations were prepared by the caller with the two-pass machinery.
+static int enqueue_partition3(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int role, const Plan& pl, tup_t* dst) {
+    gj_ctx::P3& q = ctx->p3;
+    const RelMeta& m = ctx->meta[role];
+    const uint32_t nb3 = 1u << pl.B;
+    // pass 1: input -> dst on the top 8 bits; pass 2: dst -> scratch on the next 8
+    {
+        const ScatterCfg& c1 = scatter_cfg1(ctx);
+        const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
+        ScatterArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in_keys = rel.keys; a.in_pays = rel.pays; a.in_tup = rel.tup; a.n = (uint32_t)rel.n;
+        a.out = dst; a.shift = pl.b3 + pl.b2; a.bits = pl.b1;
+        a.cursors = m.cur1; a.cursor_stride = CUR1_STRIDE;
+        a.ntiles = (uint32_t)((rel.n + (rel.tup ? 1 : 0) + T1 - 1) / T1);
+        (rel.tup ? c1.packed : c1.col)<<<a.ntiles, c1.threads, scatter_smem(c1), s>>>(a);
+        LAUNCHED();
+    }
+    const ScatterCfg& c2 = scatter_cfg2(ctx, pl.b2);
+    const uint32_t T2 = (uint32_t)(c2.threads * c2.ipt);
+    {
+        ScatterArgs b;
+        memset(&b, 0, sizeof(b));
+        b.in_tup = dst; b.out = ctx->scratch; b.n = (uint32_t)rel.n;
+        b.shift = pl.b3; b.bits = pl.b2;
+        b.cursors = m.cur2; b.cursor_stride = 1; b.tiles = m.tiles; b.num_tiles = m.num_tiles;
+        c2.packed<<<(uint32_t)(rel.n / T2) + (1u << pl.b1) + 2, c2.threads, scatter_smem(c2), s>>>(b);
+        LAUNCHED();
+    }
+    // third level: count the low bits per second-level partition, scan, tile descriptors, scatter
+    sub_hist_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(ctx->scratch, m.off, FINE_MAX, pl.b3, q.ghist3[role]);
+    LAUNCHED();
+    int rc;
+    ScanSeq so;
+    so.in = q.ghist3[role]; so.in2 = nullptr; so.out = q.off3[role]; so.desc = q.desc[role]; so.ticket = q.ticket[role];
+    so.mode = SCAN_PLAIN; so.param = 0;
+    if ((rc = enqueue_scan_one(ctx, s, so, nb3))) return rc;
+    ScanSeq st;
+    st.in = m.off; st.in2 = nullptr; st.out = q.tile_prefix[role]; st.desc = q.desc[3 + role]; st.ticket = q.ticket[3 + role];
+    st.mode = SCAN_TILES; st.param = T2;
+    if ((rc = enqueue_scan_one(ctx, s, st, FINE_MAX))) return rc;
+    tiles3_kernel<<<FINE_MAX / 256, 256, 0, s>>>(m.off, q.tile_prefix[role], FINE_MAX, T2, pl.b3, q.tiles[role]);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(q.cur3[role], q.off3[role], (size_t)nb3 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    {
+        ScatterArgs c;
+        memset(&c, 0, sizeof(c));
+        c.in_tup = ctx->scratch; c.out = dst; c.n = (uint32_t)rel.n;
+        c.shift = 0; c.bits = pl.b3;
+        c.cursors = q.cur3[role]; c.cursor_stride = 1; c.tiles = q.tiles[role]; c.num_tiles = q.tile_prefix[role] + FINE_MAX;
+        c2.packed<<<(uint32_t)(rel.n / T2) + FINE_MAX + 2, c2.threads, scatter_smem(c2), s>>>(c);
+        LAUNCHED();
+    }
+    return GJ_OK;
+}
+
+// unit list over the 2^B third-level partitions (both relations partitioned)
+static int enqueue_units3(gj_ctx* ctx, cudaStream_t s, const Plan& pl) {
+    gj_ctx::P3& q = ctx->p3;
+    const uint32_t nb3 = 1u << pl.B;
+    ScanSeq su;
+    su.in = q.ghist3[0]; su.in2 = q.ghist3[1]; su.out = q.unit_base; su.desc = q.desc[2]; su.ticket = q.ticket[2];
+    su.mode = SCAN_UNITS; su.param = unit_tuples(ctx);
+    int rc;
+    if ((rc = enqueue_scan_one(ctx, s, su, nb3))) return rc;
+    PlanArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int r = 0; r < 2; ++r) { a.rel[r].off = q.off3[r]; a.rel[r].cur2 = q.cur3[r]; }
+    a.nrel = 0; a.with_units = 1; a.b1 = pl.B; a.b2 = 0;
+    a.tile = 4096; a.unit = unit_tuples(ctx);
+    a.unit_base = q.unit_base; a.units = ctx->units;
+    plan_kernel<<<128, PLAN_THREADS, 0, s>>>(a);
+    LAUNCHED();
+    return GJ_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -560,22 +715,39 @@ static int run_join(gj_ctx* ctx, Rel R, Rel S, bool mat, int32_t* out_Rp, int32_
     const bool swap = R.n > S.n;   // build on the smaller relation
     const Rel& bld = swap ? S : R;
     const Rel& prb = swap ? R : S;
-    const Plan pl = choose_plan(ctx, bld.n, 0);
+    const Plan pl = choose_plan(ctx, bld.n, 0, true);
     fill_plan(t, pl);
+    int rc;
+    if (pl.b3 && (rc = ensure_pass3(ctx))) return rc;
 
     CK(cudaMemsetAsync(ctx->zero_block, 0, ctx->zero_bytes, s));
+    if (pl.b3) CK(cudaMemsetAsync(ctx->p3.zero, 0, ctx->p3.zero_bytes, s));
     CK(cudaEventRecord(ctx->ev[0], s));
-    int rc;
-    if ((rc = enqueue_hist(ctx, s, bld.tup ? (const void*)bld.tup : (const void*)bld.keys, bld.tup != nullptr, bld.n, 0, pl.B, ctx->meta[0].ghist))) return rc;
-    if ((rc = enqueue_hist(ctx, s, prb.tup ? (const void*)prb.tup : (const void*)prb.keys, prb.tup != nullptr, prb.n, 0, pl.B, ctx->meta[1].ghist))) return rc;
-    if ((rc = enqueue_scan(ctx, s, 0, 2, 1u << pl.B, true))) return rc;
-    if ((rc = enqueue_plan(ctx, s, 0, 2, pl, true))) return rc;
-    CK(cudaEventRecord(ctx->ev[1], s));
-    if ((rc = enqueue_scatter(ctx, s, bld, 0, pl, ctx->out[bld.slot]))) return rc;
-    if ((rc = enqueue_scatter(ctx, s, prb, 1, pl, ctx->out[prb.slot]))) return rc;
+    const uint32_t* num_units = nullptr;
+    if (!pl.b3) {
+        if ((rc = enqueue_hist(ctx, s, bld.tup ? (const void*)bld.tup : (const void*)bld.keys, bld.tup != nullptr, bld.n, 0, pl.B, ctx->meta[0].ghist))) return rc;
+        if ((rc = enqueue_hist(ctx, s, prb.tup ? (const void*)prb.tup : (const void*)prb.keys, prb.tup != nullptr, prb.n, 0, pl.B, ctx->meta[1].ghist))) return rc;
+        if ((rc = enqueue_scan(ctx, s, 0, 2, 1u << pl.B, true))) return rc;
+        if ((rc = enqueue_plan(ctx, s, 0, 2, pl, true))) return rc;
+        CK(cudaEventRecord(ctx->ev[1], s));
+        if ((rc = enqueue_scatter(ctx, s, bld, 0, pl, ctx->out[bld.slot]))) return rc;
+        if ((rc = enqueue_scatter(ctx, s, prb, 1, pl, ctx->out[prb.slot]))) return rc;
+    } else {
+        // second-level (top 16 bits) histogram, offsets, cursors and pass-2 tiles with the two-pass machinery
+        Plan p2; p2.B = 16; p2.b1 = pl.b1; p2.b2 = pl.b2;
+        if ((rc = enqueue_hist(ctx, s, bld.tup ? (const void*)bld.tup : (const void*)bld.keys, bld.tup != nullptr, bld.n, pl.b3, 16, ctx->meta[0].ghist))) return rc;
+        if ((rc = enqueue_hist(ctx, s, prb.tup ? (const void*)prb.tup : (const void*)prb.keys, prb.tup != nullptr, prb.n, pl.b3, 16, ctx->meta[1].ghist))) return rc;
+        if ((rc = enqueue_scan(ctx, s, 0, 2, FINE_MAX, false))) return rc;
+        if ((rc = enqueue_plan(ctx, s, 0, 2, p2, false))) return rc;
+        CK(cudaEventRecord(ctx->ev[1], s));
+        if ((rc = enqueue_partition3(ctx, s, bld, 0, pl, ctx->out[bld.slot]))) return rc;
+        if ((rc = enqueue_partition3(ctx, s, prb, 1, pl, ctx->out[prb.slot]))) return rc;
+        if ((rc = enqueue_units3(ctx, s, pl))) return rc;
+        num_units = ctx->p3.unit_base + (1u << pl.B);
+    }
     CK(cudaEventRecord(ctx->ev[2], s));
     if ((rc = enqueue_join(ctx, s, ctx->out[bld.slot], ctx->out[prb.slot], pl, bld.n, prb.n, mat,
-                           swap ? out_Sp : out_Rp, swap ? out_Rp : out_Sp, cap))) return rc;
+                           swap ? out_Sp : out_Rp, swap ? out_Rp : out_Sp, cap, num_units))) return rc;
     CK(cudaEventRecord(ctx->ev[3], s));
     CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -587,7 +759,7 @@ static int run_join(gj_ctx* ctx, Rel R, Rel S, bool mat, int32_t* out_Rp, int32_
         CK(cudaEventElapsedTime(&t->part_ms, ctx->ev[1], ctx->ev[2]));
         CK(cudaEventElapsedTime(&t->join_ms, ctx->ev[2], ctx->ev[3]));
         CK(cudaEventElapsedTime(&t->total_ms, ctx->ev[0], ctx->ev[3]));
-        if ((rc = fill_pass_times(ctx, t, pl, 2, 0))) return rc;
+        if (!pl.b3 && (rc = fill_pass_times(ctx, t, pl, 2, 0))) return rc;
         t->kernel_launches = ctx->launches;
         t->wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
     }
@@ -866,7 +1038,7 @@ extern "C" int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, cons
         // to the local passes of the other relation running concurrently on another stream
         const uint32_t grid = ctx->opt_shuffle_grid ? std::min<uint32_t>((uint32_t)ctx->opt_shuffle_grid, a.ntiles) : a.ntiles;
         CK(cudaEventRecord(ctx->sev[0][0], s));
-        c1.col<<<grid, c1.threads, scatter_smem(c1), s>>>(a);
+        (grid < a.ntiles ? c1.col_persist : c1.col)<<<grid, c1.threads, scatter_smem(c1), s>>>(a);
         LAUNCHED();
         CK(cudaEventRecord(ctx->sev[0][1], s));
     }
@@ -914,7 +1086,7 @@ extern "C" int gj_shuffle_scatter_peers_async(gj_ctx* ctx, int which, const int3
         a.shift = gpu_shift; a.bits = bits; a.cursors = ctx->shuf_cur[which]; a.cursor_stride = 1;
         a.ntiles = (uint32_t)((n + T1 - 1) / T1);
         const uint32_t grid = ctx->opt_shuffle_grid ? std::min<uint32_t>((uint32_t)ctx->opt_shuffle_grid, a.ntiles) : a.ntiles;
-        c1.col<<<grid, c1.threads, scatter_smem(c1), s>>>(a);
+        (grid < a.ntiles ? c1.col_persist : c1.col)<<<grid, c1.threads, scatter_smem(c1), s>>>(a);
         LAUNCHED();
     }
     CK(cudaEventRecord(ctx->sev[which][1], s));

@@ -196,21 +196,28 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 // ------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_THREADS * SCAN_IPT;
 
+enum { SCAN_PLAIN = 0, SCAN_UNITS = 1, SCAN_TILES = 2 };
 struct ScanSeq {
-    const uint32_t* in;           // nb values (sequences 0/1)
+    const uint32_t* in;           // PLAIN: nb values; UNITS: build counts; TILES: nb + 1 offsets
+    const uint32_t* in2;          // UNITS: probe counts
     uint32_t* out;                // nb + 1 exclusive prefix sums
     unsigned long long* desc;     // one word per tile, zeroed
     uint32_t* ticket;             // zeroed
+    uint32_t mode;                // SCAN_*
+    uint32_t param;               // UNITS: probe tuples per unit; TILES: tuples per scatter tile
 };
 struct ScanArgs {
     ScanSeq seq[3];
     uint32_t nb;
-    uint32_t unit;                // probe tuples per join unit (sequence 2)
     uint32_t seq_base;            // blockIdx.y + seq_base selects the sequence
 };
 
 __device__ __forceinline__ uint32_t units_of(uint32_t n_bld, uint32_t n_prb, uint32_t unit) {
     return (n_bld && n_prb) ? (n_prb + unit - 1) / unit : 0u;
+}
+// scatter tiles of a parent partition [lo, hi): tiles start on even slots
+__device__ __forceinline__ uint32_t tiles_of(uint32_t lo, uint32_t hi, uint32_t tile) {
+    return hi > lo ? (hi - (lo & ~1u) + tile - 1) / tile : 0u;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -229,8 +236,9 @@ scan_lookback_kernel(ScanArgs a) {
     for (int j = 0; j < SCAN_IPT; ++j) {
         v[j] = 0;
         if (base + j < a.nb) {
-            if (which < 2) v[j] = r.in[base + j];
-            else v[j] = units_of(a.seq[0].in[base + j], a.seq[1].in[base + j], a.unit);
+            if (r.mode == SCAN_PLAIN) v[j] = r.in[base + j];
+            else if (r.mode == SCAN_UNITS) v[j] = units_of(r.in[base + j], r.in2[base + j], r.param);
+            else v[j] = tiles_of(r.in[base + j], r.in[base + j + 1], r.param);
         }
         tsum += v[j];
     }
@@ -374,6 +382,47 @@ plan_kernel(PlanArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// 3b. Third-pass support (more than 16 radix bits: build sides beyond 2^28 tuples).  After two
+//     passes on the top 16 bits the data is grouped into 65536 second-level partitions; the third
+//     pass splits each of them on the low b3 bits.  sub_hist_kernel counts those bits per
+//     partition (one CTA per partition, plain stores: every counter is written, nothing needs
+//     zeroing); tiles3_kernel writes the third pass's tile descriptors from the scanned tile
+//     counts.  Extra traffic of the third level: 8 B/tuple (count) + 16 B/tuple (scatter).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sub_hist_kernel(const tup_t* __restrict__ data, const uint32_t* __restrict__ off2, uint32_t nparents,
+                uint32_t b3, uint32_t* __restrict__ ghist3) {
+    __shared__ uint32_t sh[32];
+    const uint32_t m3 = (1u << b3) - 1u;
+    for (uint32_t p = blockIdx.x; p < nparents; p += gridDim.x) {
+        if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t lo = off2[p], hi = off2[p + 1];
+        uint32_t i = lo + threadIdx.x;
+        for (; i + 3 * 256 < hi; i += 4 * 256) {
+            const tup_t t0 = __ldg(data + i), t1 = __ldg(data + i + 256), t2 = __ldg(data + i + 512), t3 = __ldg(data + i + 768);
+            atomicAdd(&sh[t0.x & m3], 1u); atomicAdd(&sh[t1.x & m3], 1u);
+            atomicAdd(&sh[t2.x & m3], 1u); atomicAdd(&sh[t3.x & m3], 1u);
+        }
+        for (; i < hi; i += 256) atomicAdd(&sh[__ldg(data + i).x & m3], 1u);
+        __syncthreads();
+        if (threadIdx.x <= m3) ghist3[((size_t)p << b3) + threadIdx.x] = sh[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tiles3_kernel(const uint32_t* __restrict__ off2, const uint32_t* __restrict__ tile_prefix, uint32_t nparents,
+              uint32_t tile, uint32_t b3, uint4* __restrict__ tiles) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nparents; p += gridDim.x * blockDim.x) {
+        const uint32_t lo = off2[p], hi = off2[p + 1];
+        uint32_t at = tile_prefix[p];
+        for (uint32_t a0 = lo & ~1u; hi > lo && a0 < hi; a0 += tile)
+            tiles[at++] = make_uint4(a0, max(a0, lo), min(a0 + tile, hi), p << b3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // 4. Radix scatter pass.  One tile of THREADS*IPT tuples per CTA:
 //      load (16-byte loads, registers) -> shared-memory histogram that also yields each tuple's
 //      rank inside its digit -> block scan of the 2^bits counts + ONE global ticket per
@@ -409,7 +458,7 @@ struct ScatterArgs {
     const uint32_t* num_tiles;   // pass 2 only
 };
 
-template <int THREADS, int IPT, int MODE, int OUT, bool COLUMNAR, int MINB>
+template <int THREADS, int IPT, int MODE, int OUT, bool COLUMNAR, int MINB, bool PERSIST = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 scatter_kernel(ScatterArgs a) {
     constexpr uint32_t T = THREADS * IPT;
@@ -425,8 +474,9 @@ scatter_kernel(ScatterArgs a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t nb = 1u << a.bits, mask = nb - 1u;
 
-    // One tile per CTA when the grid covers all tiles; a smaller (persistent) grid loops -- used by
-    // the multi-GPU peer scatter so that it leaves SM resources to concurrently running kernels.
+    // One tile per CTA (the grid covers all tiles).  PERSIST: a smaller grid loops over the tiles
+    // -- the multi-GPU peer scatter can leave SM resources to concurrently running kernels.  (As a
+    // run-time loop in every variant it cost the one-tile launches ~1.5 %, hence the template.)
     const uint32_t ntiles_total = (a.tiles == nullptr) ? a.ntiles : *a.num_tiles;
     for (uint32_t tile_id = blockIdx.x; tile_id < ntiles_total; tile_id += gridDim.x) {
     // ---- which slots does this tile cover ----
@@ -446,7 +496,7 @@ scatter_kernel(ScatterArgs a) {
         const uint4 td = __ldg(a.tiles + tile_id);
         a0 = td.x; lo = td.y; hi = td.z; cbase = td.w;
     }
-    if (hi <= lo) continue;
+    if (hi <= lo) { if (PERSIST) continue; else return; }
     if (tid < NB_MAX) s_hist[tid] = 0;
     __syncthreads();
     const bool full = (lo == a0) && (hi - a0 == T);
@@ -581,6 +631,7 @@ scatter_kernel(ScatterArgs a) {
             bulk_wait_read0();   // shared memory must stay valid until the engine has read it
         }
     }
+    if (!PERSIST) break;
     }   // tile loop (the barrier at the top of the next iteration orders the reuse of shared memory)
 }
 

@@ -40,6 +40,7 @@ class Timings(C.Structure):
                 ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("wall_ms", C.c_float),
                 ("pass_ms", C.c_float * 4),
                 ("radix_bits", C.c_uint32), ("pass1_bits", C.c_uint32), ("pass2_bits", C.c_uint32),
+                ("pass3_bits", C.c_uint32),
                 ("kernel_launches", C.c_uint32)]
 
     def as_dict(self):

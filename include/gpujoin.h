@@ -53,6 +53,7 @@ typedef struct gj_timings {
     uint32_t radix_bits;     /* total radix bits B used (2^B partitions) */
     uint32_t pass1_bits;     /* bits of the first pass (== radix_bits when single pass) */
     uint32_t pass2_bits;     /* bits of the second pass (0 when single pass) */
+    uint32_t pass3_bits;     /* bits of the third pass (0 unless the build side exceeds 2^28 tuples) */
     uint32_t kernel_launches;/* kernels launched inside the timed window */
 } gj_timings;
 

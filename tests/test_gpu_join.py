@@ -211,6 +211,33 @@ def test_every_radix_split_and_join_variant(gj, orc, eng, torch_cuda):
     reset(eng)
 
 
+@pytest.mark.parametrize("bits", [17, 19, 21])
+def test_three_pass_partitioning(gj, orc, eng, torch_cuda, bits):
+    """More than 16 radix bits (what build sides beyond 2^28 tuples get): third pass on the low bits
+    of every second-level partition.  Forced here on small inputs, incl. skew and both input layouts."""
+    reset(eng)
+    rng = np.random.default_rng(bits)
+    nR, nS = 1_500_000, 3_000_000
+    Rk = rnd(rng, nR, -2**31, 2**31)
+    Sk = np.concatenate([Rk[rng.integers(0, nR, nS // 2)], rnd(rng, nS - nS // 2, -2**31, 2**31)])
+    Sk[: 200_000] = Rk[7]                        # one hot key
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    eng.set_option("radix_bits", bits)
+    got = eng.join_aggregate(*dev(torch_cuda, Rk, Rp, Sk, Sp))
+    assert (got.matches, got.checksum) == (want.matches, want.checksum)
+    assert (got.timings.radix_bits, got.timings.pass1_bits, got.timings.pass2_bits, got.timings.pass3_bits) == (bits, 8, 8, bits - 16)
+    Rt = torch_cuda.from_numpy(np.stack([Rk, Rp], axis=1).copy()).cuda()
+    St = torch_cuda.from_numpy(np.stack([Sk, Sp], axis=1).copy()).cuda()
+    got = eng.join_aggregate_tuples(Rt, nR, St, nS)
+    assert (got.matches, got.checksum) == (want.matches, want.checksum)
+    out_r = torch_cuda.empty(int(want.matches), dtype=torch_cuda.int32, device="cuda")
+    out_s = torch_cuda.empty(int(want.matches), dtype=torch_cuda.int32, device="cuda")
+    n, res = eng.join_materialize(*dev(torch_cuda, Rk, Rp, Sk, Sp), out_r, out_s)
+    assert n == want.matches and orc.pairs_hash(out_r.cpu().numpy(), out_s.cpu().numpy()) == want.pairhash
+    reset(eng)
+
+
 def test_packed_tuple_entry(gj, orc, eng, torch_cuda):
     reset(eng)
     rng = np.random.default_rng(12)
@@ -395,6 +422,6 @@ def test_error_behaviour(gj, eng, torch_cuda):
     with pytest.raises(gj.GJError):
         eng.set_option("no_such_option", 1)
     with pytest.raises(gj.GJError):
-        eng.set_option("radix_bits", 17)
+        eng.set_option("radix_bits", 22)
     with pytest.raises(gj.GJError):
         gj.JoinEngine(16, 16, device=99)
