@@ -509,7 +509,7 @@ def multi_gpu(args):
                                  "scatter_kernel_ms": tm.get("shuffle_scatter_ms"),
                                  "nvlink_out_GBs_per_gpu": (8.0 * (nR + nS) * (world - 1) / world / (tm["shuffle_scatter_ms"] * 1e-3) / 1e9)
                                  if tm.get("shuffle_scatter_ms") else None,
-                                 "nvlink_peak_GBs": 770.0, "host_ms_rank0": tm.get("host_ms"),
+                                 "nvlink_peak_GBs": 770.0, "host_ms_rank0": tm.get("host_ms"), "trace_ms_rank0": tm.get("trace_ms"),
                                  "note": "peer-store scatter: one kernel reads the local shard (8 B/tuple HBM) and stores each run into the destination GPU's HBM over NVLink"},
                      "checked": f"matches == checksum == {expect} every step"})
         if line["roofline"]["achieved"]:

@@ -98,29 +98,50 @@ class GpuOps:
         """Shuffle R -> [all ranks done] -> local passes of R  ||  shuffle S -> [done] -> local passes
         of S -> join.  The cross-rank "done" points are 1-element NCCL all-reduces enqueued on the
         streams, so nothing blocks the host until the final result read-back."""
+        import os
         torch, eng = self.torch, self.engine
         sA, sB = self.stream_local, self.stream_shuffle
         cur = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_tok"):
+            self._tok = [torch.zeros(1, dtype=torch.int32, device=self.dev) for _ in range(2)]
+        tok = self._tok
         sA.wait_stream(cur); sB.wait_stream(cur)
-        tok = [torch.zeros(1, dtype=torch.int32, device=self.dev) for _ in range(2)]
+        trace = [] if os.environ.get("GJ_TRACE") else None
+
+        def mark(name, stream):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                trace.append((name, e))
+        mark("start", sA)
         eng.stage_begin(n_in[0], n_in[1], sA)
         (Rk, Rp), (Sk, Sp) = rels
         eng.shuffle_scatter_peers_async(0, Rk, Rp, G, shift, peers[0], write_at[0], sA)
         r_sent = torch.cuda.Event()
         r_sent.record(sA)
+        mark("R shuffled (local kernel end)", sA)
         with torch.cuda.stream(sA):
             dist.all_reduce(tok[0], group=group)          # every rank's R stores have landed
+        mark("R token", sA)
         eng.stage_partition(0, own_ptrs[0], sA)
+        mark("R partitioned", sA)
         sB.wait_event(r_sent)                             # one relation on NVLink at a time
         eng.shuffle_scatter_peers_async(1, Sk, Sp, G, shift, peers[1], write_at[1], sB)
+        mark("S shuffled (local kernel end)", sB)
         with torch.cuda.stream(sB):
             dist.all_reduce(tok[1], group=group)          # every rank's S stores have landed
+        mark("S token", sB)
         eng.stage_partition(1, own_ptrs[1], sB)
+        mark("S partitioned", sB)
         eng.stage_join(sB)
+        mark("joined", sB)
         m, c = eng.stage_finish()
         sA.synchronize()
         ms = eng.shuffle_scatter_ms(0) + eng.shuffle_scatter_ms(1)
-        return m, c, {"shuffle_scatter_ms": ms}
+        out = {"shuffle_scatter_ms": ms}
+        if trace is not None:
+            out["trace_ms"] = {n: round(trace[0][1].elapsed_time(e), 3) for n, e in trace[1:]}
+        return m, c, out
 
     def exchange_counts(self, dist, group, mine):
         """All ranks' count vectors in ONE small NCCL all-gather (doubles as a barrier)."""
