@@ -528,7 +528,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--shuffle", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--shuffle", default="p2p", choices=["p2p", "nccl", "dma"])
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: shuffle and local passes back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1093,6 +1093,12 @@ extern "C" int gj_shuffle_scatter_peers_async(gj_ctx* ctx, int which, const int3
     return GJ_OK;
 }
 
+extern "C" int gj_memcpy_d2d_async(void* dst, const void* src, uint64_t bytes, void* cuda_stream) {
+    if (bytes && (!dst || !src)) return fail(GJ_ERR_ARG, "NULL argument");
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+    return GJ_OK;
+}
+
 extern "C" int gj_shuffle_scatter_ms(gj_ctx* ctx, int which, float* ms) {
     if (!ctx || !ms || (which != 0 && which != 1)) return fail(GJ_ERR_ARG, "bad argument");
     CK(cudaEventSynchronize(ctx->sev[which][1]));

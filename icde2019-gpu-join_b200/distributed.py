@@ -143,6 +143,60 @@ class GpuOps:
             out["trace_ms"] = {n: round(trace[0][1].elapsed_time(e), 3) for n, e in trace[1:]}
         return m, c, out
 
+    def dma_shuffle(self, dist, group, rank, rels, G, shift, peers, counts, write_at, n_in, own_ptrs):
+        """Shuffle variant "dma": ONE kernel per relation splits the shard by destination -- this
+        rank's own share goes straight into its receive buffer, the other shares into a send
+        buffer -- and the copy engines move the groups to the peers over NVLink (one stream per
+        destination) while the SMs already run the next kernels: split of S, local passes of R
+        (after its token), local passes of S, join."""
+        torch, eng = self.torch, self.engine
+        sK, sT = self.stream_local, self.stream_shuffle
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = [torch.cuda.Stream(self.device) for _ in range(max(G - 1, 1))]
+            self._tok = [torch.zeros(1, dtype=torch.int32, device=self.dev) for _ in range(2)]
+        cur = torch.cuda.current_stream(self.device)
+        sK.wait_stream(cur); sT.wait_stream(cur)
+        eng.stage_begin(n_in[0], n_in[1], sK)
+        split_done, copies_done = [], []
+        for which, (k, p) in enumerate(rels):
+            cnt = counts[which][rank]                        # what this rank sends to each destination
+            send_off = np.concatenate(([0], np.cumsum(cnt)[:-1]))
+            bases = [self.send[which].data_ptr()] * G
+            offs = [int(x) for x in send_off]
+            bases[rank] = own_ptrs[which]
+            offs[rank] = int(write_at[which][rank])
+            eng.shuffle_scatter_peers_async(which, k, p, G, shift, bases, offs, sK)
+            ev = torch.cuda.Event()
+            ev.record(sK)
+            split_done.append((ev, cnt, send_off))
+        for which in range(2):
+            ev, cnt, send_off = split_done[which]
+            evs = []
+            for j, g in enumerate(x for x in range(G) if x != rank):
+                cs = self._copy_streams[j]
+                cs.wait_event(ev)
+                eng.memcpy_d2d_async(peers[which][g] + int(write_at[which][g]) * 8,
+                                     self.send[which].data_ptr() + int(send_off[g]) * 8, int(cnt[g]) * 8, cs)
+                e2 = torch.cuda.Event()
+                e2.record(cs)
+                evs.append(e2)
+            copies_done.append(evs)
+        for which in range(2):
+            for e2 in copies_done[which]:
+                sT.wait_event(e2)
+            sT.wait_event(split_done[which][0])
+            with torch.cuda.stream(sT):
+                dist.all_reduce(self._tok[which], group=group)     # every rank's copies have landed
+            tok_ev = torch.cuda.Event()
+            tok_ev.record(sT)
+            sK.wait_event(tok_ev)
+            eng.stage_partition(which, own_ptrs[which], sK)
+        eng.stage_join(sK)
+        m, c = eng.stage_finish()
+        for cs in self._copy_streams:
+            cs.synchronize()
+        return m, c, {"shuffle_scatter_ms": eng.shuffle_scatter_ms(0) + eng.shuffle_scatter_ms(1)}
+
     def exchange_counts(self, dist, group, mine):
         """All ranks' count vectors in ONE small NCCL all-gather (doubles as a barrier)."""
         t = self.torch.tensor([int(x) for x in mine], dtype=self.torch.int64, device=self.dev)
@@ -183,13 +237,13 @@ class ShardedJoin:
         self.overlap = overlap
         self.part_target = part_target
         self.ops = ops if ops is not None else GpuOps(max_local_R, max_local_S, device,
-                                                      with_send_buffers=(mode == "nccl"))
+                                                      with_send_buffers=(mode in ("nccl", "dma")))
         self.max_local = (max_local_R, max_local_S)
         self._peers = None
-        if mode == "p2p":
+        if mode in ("p2p", "dma"):
             self._setup_peers()
         elif mode != "nccl":
-            raise ValueError("mode must be 'nccl' or 'p2p'")
+            raise ValueError("mode must be 'nccl', 'p2p' or 'dma'")
 
     # -- CUDA IPC mapping of every rank's receive buffers (p2p mode) -------------------------
     def _setup_peers(self):
@@ -290,7 +344,10 @@ class ShardedJoin:
                     raise RuntimeError(f"rank {rank}: receives {n_in} tuples, capacity {cap}")
                 write_ats.append(write_at)
                 local_n[which] = n_in
-            if self.overlap and hasattr(ops, "overlapped_p2p"):
+            if self.mode == "dma":
+                m, c, tm = ops.dma_shuffle(dist, self.group, rank, rels, G, shift, self._peers, all_counts, write_ats,
+                                           local_n, self._own)
+            elif self.overlap and hasattr(ops, "overlapped_p2p"):
                 m, c, tm = ops.overlapped_p2p(dist, self.group, rels, G, shift, self._peers, write_ats, local_n, self._own)
             else:
                 for which, (k, p) in enumerate(rels):
@@ -298,14 +355,14 @@ class ShardedJoin:
                 dist.barrier(group=self.group)   # every rank's stores have landed
                 m, c, tm = ops.local_join_ptrs(self._own[0], local_n[0], self._own[1], local_n[1])
                 tm = dict(tm, shuffle_scatter_ms=shuffle_ms)
-        if self.mode != "p2p":
+        if self.mode == "nccl":
             m, c, tm = ops.local_join(local_n[0], local_n[1])
         lap()
         res = ops.result_tensor(m, c)
         dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
         vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
         lap()
-        if self.mode == "p2p" and len(t_host) == 5:
+        if self.mode != "nccl" and len(t_host) == 5:
             d = [1e3 * (b - a) for a, b in zip(t_host, t_host[1:])]
             tm = dict(tm, host_ms={"count": d[0], "exchange": d[1], "shuffle+local": d[2], "reduce": d[3]})
         return ShardedResult(vals[0], vals[1], local_n[0], local_n[1], tm)

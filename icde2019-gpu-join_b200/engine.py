@@ -21,7 +21,7 @@ C_ABI_SYMBOLS = [
     "gj_create", "gj_destroy", "gj_last_error", "gj_version", "gj_set_stream", "gj_set_option",
     "gj_get_option", "gj_join_aggregate", "gj_join_aggregate_tuples", "gj_join_aggregate_host",
     "gj_join_materialize", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
-    "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_stage_begin",
+    "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
     "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
     "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_device_synchronize", "gj_flush_l2",
@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
     L.gj_shuffle_count.argtypes = [vp, i32p, u64, u32, u32, C.POINTER(u64)]
     L.gj_shuffle_scatter_peers_async.argtypes = [vp, C.c_int, i32p, i32p, u64, u32, u32, C.POINTER(vp), C.POINTER(u64), vp]
     L.gj_shuffle_scatter_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    L.gj_memcpy_d2d_async.argtypes = [vp, vp, u64, vp]
     L.gj_stage_begin.argtypes = [vp, u64, u64, vp]
     L.gj_stage_partition.argtypes = [vp, C.c_int, vp, vp]
     L.gj_stage_join.argtypes = [vp, vp]
@@ -314,6 +315,9 @@ class JoinEngine:
         ms = C.c_float()
         _check(self._L.gj_shuffle_scatter_ms(self._ctx, which, C.byref(ms)))
         return float(ms.value)
+
+    def memcpy_d2d_async(self, dst: int, src: int, nbytes: int, stream):
+        _check(self._L.gj_memcpy_d2d_async(C.c_void_p(dst), C.c_void_p(src), nbytes, C.c_void_p(stream.cuda_stream)))
 
     def stage_begin(self, nR: int, nS: int, stream):
         _check(self._L.gj_stage_begin(self._ctx, nR, nS, C.c_void_p(stream.cuda_stream)))

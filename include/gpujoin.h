@@ -154,6 +154,9 @@ int gj_shuffle_scatter_peers_async(gj_ctx* ctx, int which, const int32_t* d_keys
                                    void* const* d_peer_bases, const uint64_t* h_peer_offsets,
                                    void* cuda_stream);
 int gj_shuffle_scatter_ms(gj_ctx* ctx, int which, float* ms);
+/* Device-to-device (also peer / IPC-mapped) copy on a stream: runs on the copy engines, so the
+ * "dma" shuffle variant moves tuples over NVLink without occupying SMs. */
+int gj_memcpy_d2d_async(void* dst, const void* src, uint64_t bytes, void* cuda_stream);
 
 /* Staged form of gj_join_aggregate_tuples for overlapping with the shuffle: begin fixes the plan
  * from (nR, nS); partition(side) enqueues histogram + scan + radix passes of one relation's

@@ -48,7 +48,7 @@ def _worker(rank, world, port, n_local, mode, overlap, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,overlap", [("nccl", False), ("p2p", False), ("p2p", True)])
+@pytest.mark.parametrize("mode,overlap", [("nccl", False), ("p2p", False), ("p2p", True), ("dma", True)])
 def test_sharded_join_on_real_gpus(mode, overlap):
     import torch
     import torch.multiprocessing as mp
