@@ -125,7 +125,8 @@ class GpuOps:
         mark("R token", sA)
         eng.stage_partition(0, own_ptrs[0], sA)
         mark("R partitioned", sA)
-        sB.wait_event(r_sent)                             # one relation on NVLink at a time
+        if not os.environ.get("GJ_CONCURRENT_SHUFFLE"):
+            sB.wait_event(r_sent)                         # one relation on NVLink at a time
         eng.shuffle_scatter_peers_async(1, Sk, Sp, G, shift, peers[1], write_at[1], sB)
         mark("S shuffled (local kernel end)", sB)
         with torch.cuda.stream(sB):
