@@ -1,0 +1,50 @@
+"""Differential test against the REFERENCE's own CUDA kernels rebuilt for sm_100a
+(oracle/_ref/bench_ref, built by oracle/Makefile from the sources where they lie): identical
+key files go to both engines (`--file -k -l`, main.cu:186-189); the reference prints
+`%d results` = int32 SUM(Pr*Ps) with Pr=Ps=1 (hash_join_clustered_probe.cu:984-986,1994-1999),
+which must equal our match count / checksum and the oracle's."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BENCH_REF = os.path.join(ROOT, "oracle", "_ref", "bench_ref")
+OUR_BENCH = os.path.join(ROOT, "icde2019-gpu-join_b200", "bin", "bench")
+
+
+def _run(exe, nR, nS, fr, fs, cwd):
+    out = subprocess.run([exe, "-b", "7", "-a", "HJC", "-R", str(nR), "-S", str(nS), "--file", "-k", fr, "-l", fs],
+                         capture_output=True, text=True, timeout=300, cwd=cwd)
+    m = re.search(r"(-?\d+) results", out.stdout)
+    assert m, out.stdout[-500:] + out.stderr[-500:]
+    return int(m.group(1)), out.stdout
+
+
+@pytest.mark.parametrize("nR,nS,kind", [(1 << 20, 1 << 20, "unique"), (1 << 18, 1 << 21, "fk"), (1 << 19, 1 << 20, "zipf")])
+def test_same_key_files_same_results(gj, orc, tmp_path, nR, nS, kind):
+    if not os.path.exists(BENCH_REF):
+        pytest.skip("oracle/_ref/bench_ref not built (reference sources absent at build time)")
+    g = gj.generator
+    R = g.create_relation_unique(nR, nR, 11)
+    if kind == "unique":
+        S = g.create_relation_unique(nS, nS, 12)
+    elif kind == "fk":
+        S = g.create_relation_unique(nS, nR, 13)
+    else:
+        S = g.create_relation_zipf_parallel(nS, nR, 1.0, 14)
+    fr, fs = str(tmp_path / "R.bin"), str(tmp_path / "S.bin")
+    g.write_relation(fr, R)
+    g.write_relation(fs, S)
+    want = orc.join_check(R, np.ones(nR, np.int32), S, np.ones(nS, np.int32))
+    ref_results, ref_out = _run(BENCH_REF, nR, nS, fr, fs, str(tmp_path))
+    our_results, our_out = _run(OUR_BENCH, nR, nS, fr, fs, str(tmp_path))
+    assert ref_results == want.ref_results_int32 == our_results
+    m = re.search(r"matches (\d+) checksum (\d+)", our_out)
+    assert m and int(m.group(1)) == want.matches and int(m.group(2)) == want.checksum
+    # both binaries print the reference's throughput lines
+    for text in (ref_out, our_out):
+        assert "Without materialization" in text and "Partition Throughput" in text and "Total Throughput" in text

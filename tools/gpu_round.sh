@@ -13,6 +13,8 @@ has() { [[ " $STAGES " == *" $1 "* ]]; }
 if has sanity; then
   (cd /tmp && timeout 300 $REPO/icde2019-gpu-join_b200/bin/bench -b 7 -a HJC -R 1048576 -S 1048576 --parallel-gen) > $OUT/driver_small.log 2>&1
   echo "exit $?" >> $OUT/driver_small.log
+  (cd /tmp && timeout 300 $REPO/icde2019-gpu-join_b200/bin/bench -b 7 -a HJC -R 1000000 -S 4000000 -s 1.0 --payload rowid) > $OUT/driver_zipf.log 2>&1
+  echo "exit $?" >> $OUT/driver_zipf.log
   (cd /tmp && timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 $REPO/icde2019-gpu-join_b200/bin/bench -b 7 -a HJC -R 300000 -S 700000 --parallel-gen) > $OUT/memcheck.log 2>&1
   echo "exit $?" >> $OUT/memcheck.log
   (cd /tmp && timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 $REPO/icde2019-gpu-join_b200/bin/bench -b 7 -a HJC -R 100000 -S 200000 --parallel-gen) > $OUT/racecheck.log 2>&1
@@ -21,7 +23,7 @@ if has sanity; then
   echo "exit $?" >> $OUT/smoke.log
 fi
 if has tests; then
-  timeout 2400 python -m pytest tests/test_gpu_join.py -m gpu -q --timeout 600 -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1
+  timeout 2400 python -m pytest tests/test_gpu_join.py tests/test_gpu_reference_differential.py -m gpu -q --timeout 600 -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1
   echo "exit $?" >> $OUT/pytest_gpu.log
 fi
 if has full; then
