@@ -512,10 +512,23 @@ def multi_gpu(args):
                                  "nvlink_peak_GBs": 770.0, "host_ms_rank0": tm.get("host_ms"), "trace_ms_rank0": tm.get("trace_ms"),
                                  "note": "peer-store scatter: one kernel reads the local shard (8 B/tuple HBM) and stores each run into the destination GPU's HBM over NVLink"},
                      "checked": f"matches == checksum == {expect} every step"})
+        if args.shuffle == "pp" and tm.get("local_R_ms"):
+            # dominant HBM-bound kernels of the sharded pipeline: the local phase of one relation =
+            # coarse histogram (4 B) + first pass (16 B) + fine counts (8 B) per tuple
+            line["roofline"].update({"kernel": "pp local phase of R (hist + first radix pass + fine counts), rank 0",
+                                     "achieved": 28.0 * nR / (tm["local_R_ms"] * 1e-3) / 1e9,
+                                     "algorithmic_bytes_per_launch": 28.0 * nR,
+                                     "local_phases_ms": {k: tm.get(k) for k in ("local_R_ms", "push_R_ms", "local_S_ms", "push_S_ms", "join_ms")}})
+            line["plan"] = {"gpu_bits": world.bit_length() - 1, "local_bits": tm.get("radix_bits"),
+                            "pass1_bits": tm.get("pass1_bits"), "pass2_bits": tm.get("pass2_bits")}
+            line["shuffle"]["note"] = ("partition-then-push: every GPU partitions its own shard on [gpu|local] bits; the last radix pass "
+                                       "stores its runs into the destination GPU's final partition buffer over NVLink; "
+                                       "scatter_kernel_ms = cursor kernel + pushing pass of R and S")
         if line["roofline"]["achieved"]:
             line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
         line["config"].update({"global_R": NR, "global_S": NS, "parallelism": f"radix-sharded over {world} GPUs, {args.shuffle} shuffle"
-                               + ("" if args.no_overlap or args.shuffle != "p2p" else ", S shuffle overlapped with R's local passes")})
+                               + (", R's push overlapped with S's local pass" if args.shuffle == "pp" else
+                                  "" if args.no_overlap or args.shuffle != "p2p" else ", S shuffle overlapped with R's local passes")})
         print(json.dumps(line))
     sj.close()
     dist.destroy_process_group()
@@ -528,7 +541,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--shuffle", default="p2p", choices=["p2p", "nccl", "dma"])
+    ap.add_argument("--shuffle", default="p2p", choices=["p2p", "nccl", "dma", "pp"])
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: shuffle and local passes back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -74,6 +74,26 @@ static size_t scatter_smem(const ScatterCfg& c) {
     return ((size_t)c.threads * c.ipt + (c.out ? 2 * NB_MAX : 0)) * sizeof(tup_t);
 }
 
+// Sharded "partition, then push" pipeline: first pass (columnar input, local) and last pass
+// (packed input, runs pushed into the destination GPU's partition buffer) by fan-out.
+struct PPCfg { int threads, ipt, out, nbt; scatter_fn fn; };
+static size_t pp_smem(const PPCfg& c) { return ((size_t)c.threads * c.ipt + (c.out ? 2 * c.nbt : 0)) * sizeof(tup_t); }
+static const PPCfg kPPFirst[] = {   // indexed by max(bits, 8) - 8
+    { 256, 16, 0, 256, scatter_kernel<256, 16, 1, 0, true, 4> },
+    { 512, 16, 0, 512, scatter_kernel<512, 16, 1, 0, true, 2, false, 512> },
+    { 1024, 8, 0, 1024, scatter_kernel<1024, 8, 1, 0, true, 1, false, 1024> },
+};
+static const PPCfg kPPPush[2][3] = {   // [8-byte stores | TMA bulk stores][max(bits, 8) - 8]
+    { { 256, 16, 0, 256, scatter_kernel<256, 16, 1, 0, false, 4, false, 256, true> },
+      { 512, 16, 0, 512, scatter_kernel<512, 16, 1, 0, false, 2, false, 512, true> },
+      { 1024, 8, 0, 1024, scatter_kernel<1024, 8, 1, 0, false, 1, false, 1024, true> } },
+    { { 512, 16, 1, 256, scatter_kernel<512, 16, 1, 1, false, 2, false, 256, true> },
+      { 512, 16, 1, 512, scatter_kernel<512, 16, 1, 1, false, 2, false, 512, true> },
+      { 1024, 8, 1, 1024, scatter_kernel<1024, 8, 1, 1, false, 1, false, 1024, true> } },
+};
+constexpr uint32_t PP_MAX_PASS_BITS = 10;
+constexpr uint32_t PP_MAX_BITS = 2 * PP_MAX_PASS_BITS;
+
 typedef void (*join_fn)(JoinArgs);
 struct JoinCfg { int threads, cap, u; join_fn agg, mat; size_t smem_agg, smem_mat; };
 // <threads, build chunk, probe chunk, R ring slots, S ring slots>
@@ -153,6 +173,25 @@ struct gj_ctx {
         uint32_t* ticket[5] = {};
         unsigned char* block = nullptr;
     } p3;
+    // sharded "partition, then push" pipeline (gj_pp_*), allocated on first use
+    struct PP {
+        bool active = false;
+        uint32_t G = 0, rank = 0, g = 0, B = 0, Btot = 0, b1 = 0, b2 = 0, out = 0;
+        int role_of_side[2] = {0, 1};
+        uint64_t n_glob[2] = {0, 0};
+        unsigned char* block = nullptr;
+        uint32_t* cur_fine[2] = {nullptr, nullptr};      // 2^PP_MAX_BITS write cursors (this source's)
+        uint32_t* tile_prefix[2] = {nullptr, nullptr};   // 2^b1 + 1, last = number of pass-2 tiles
+        tup_t** bases[2] = {nullptr, nullptr};           // destination partition buffers
+        unsigned char* zero[2] = {nullptr, nullptr};     // zeroed per call: tile-scan descriptor, ticket, status
+        size_t zero_bytes = 0;
+        unsigned long long* tdesc[2] = {nullptr, nullptr};
+        uint32_t* tticket[2] = {nullptr, nullptr};
+        uint32_t* status[2] = {nullptr, nullptr};        // [0] abort, [1] tuples received
+        unsigned char* h_pin = nullptr;                  // pinned: bases staging [2][256 ptrs] + status read-back [2][4]
+        cudaEvent_t ev[2][4] = {};                       // per relation: local begin, local end, push begin, push end
+        cudaEvent_t jev[2] = {};                         // join begin, end
+    } pp;
     unsigned char* zero_role[2] = {nullptr, nullptr};
     unsigned char* zero_common = nullptr;
     size_t zero_role_bytes = 0, zero_common_bytes = 0;
@@ -165,7 +204,7 @@ struct gj_ctx {
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
-            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0;
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 0;
     bool attrs_set = false;
 };
 
@@ -190,6 +229,9 @@ static int set_func_attrs(gj_ctx* ctx) {
         CK(cudaFuncSetAttribute(kScatter[i].packed, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         CK(cudaFuncSetAttribute(kScatter[i].col_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
+    for (const PPCfg& c : kPPFirst) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
+    for (const auto& row : kPPPush)
+        for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (int i = 0; i < kNumJoin; ++i) {
         CK(cudaFuncSetAttribute(kJoin[i].agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_agg));
         if (kJoin[i].smem_mat <= (size_t)227 * 1024)
@@ -211,6 +253,10 @@ extern "C" void gj_destroy(gj_ctx* ctx) {
     cudaFree(ctx->zero_block); cudaFree(ctx->meta_block); cudaFree(ctx->units);
     cudaFree(ctx->d_dst_bases); cudaFree(ctx->flush_buf); cudaFree(ctx->tiles_block);
     cudaFree(ctx->p3.block); cudaFree(ctx->p3.zero);
+    cudaFree(ctx->pp.block);
+    if (ctx->pp.h_pin) cudaFreeHost(ctx->pp.h_pin);
+    for (auto& r : ctx->pp.ev) for (auto& e : r) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->pp.jev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 4; ++i) cudaFree(ctx->d_in[i]);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -280,7 +326,7 @@ static int create_impl(gj_ctx* ctx, int device, uint64_t max_R, uint64_t max_S) 
     const size_t o_ub = mb;     mb += (FINE_MAX + 4) * sizeof(uint32_t);
     CK(cudaMalloc(&ctx->meta_block, mb));
     // pass-2 tile descriptors: smallest tile is 2048 tuples, one extra tile per first-pass partition
-    ctx->tiles_cap = mx / 2048 + NB_MAX + 16;
+    ctx->tiles_cap = mx / 2048 + (1u << PP_MAX_PASS_BITS) + 16;
     CK(cudaMalloc(&ctx->tiles_block, 2 * ctx->tiles_cap * sizeof(uint4)));
     for (int r = 0; r < 2; ++r) {
         RelMeta& m = ctx->meta[r];
@@ -341,7 +387,7 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
         {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
         {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
         {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
-        {"shuffle_grid", &ctx->opt_shuffle_grid},
+        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out},
     };
     for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
     return nullptr;
@@ -361,7 +407,8 @@ extern "C" int gj_set_option(gj_ctx* ctx, const char* name, int64_t v) {
         return fail(GJ_ERR_ARG, "%s %lld out of range [0,%d)", name, (long long)v, kNumScatter);
     if (p == &ctx->opt_join_cfg && v >= kNumJoin) return fail(GJ_ERR_ARG, "join_cfg out of range [0,%d)", kNumJoin);
     if (p == &ctx->opt_radix_bits && v > MAX3_RADIX_BITS) return fail(GJ_ERR_ARG, "radix_bits <= %d", (int)MAX3_RADIX_BITS);
-    if (p == &ctx->opt_pass1_bits && v > MAX_PASS_BITS) return fail(GJ_ERR_ARG, "pass1_bits <= %d", MAX_PASS_BITS);
+    if (p == &ctx->opt_pass1_bits && v > PP_MAX_PASS_BITS) return fail(GJ_ERR_ARG, "pass1_bits <= %d", (int)PP_MAX_PASS_BITS);
+    if (p == &ctx->opt_pp_out && v > 1) return fail(GJ_ERR_ARG, "pp_out is 0 (8-byte stores) or 1 (TMA bulk stores)");
     if (p == &ctx->opt_unit && v && v < 1024) return fail(GJ_ERR_ARG, "unit_tuples >= 1024");
     if (p == &ctx->opt_gpu_bits && v > 8) return fail(GJ_ERR_ARG, "gpu_bits <= 8");
     if (p == &ctx->opt_part_target && v < 32) return fail(GJ_ERR_ARG, "part_target >= 32");
@@ -530,7 +577,7 @@ static int fill_pass_times(gj_ctx* ctx, gj_timings* t, const Plan& pl, int nrole
 
 static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup_t* prb, const Plan& pl,
                         uint64_t n_bld, uint64_t n_prb, bool mat, int32_t* out_b, int32_t* out_p, uint64_t cap,
-                        const uint32_t* num_units = nullptr) {
+                        const uint32_t* num_units = nullptr, int gpu_bits = -1) {
     (void)n_bld;
     int cfg = (int)ctx->opt_join_cfg;
     if (mat && kJoin[cfg].smem_mat > (size_t)227 * 1024) cfg = 2;   // pair staging needs 16 KB: smaller rings
@@ -538,7 +585,7 @@ static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup
     JoinArgs a;
     a.bld = bld; a.prb = prb;
     a.units = ctx->units; a.num_units = num_units ? num_units : ctx->unit_base + (1u << pl.B);
-    a.hash_shift = pl.B + (uint32_t)ctx->opt_gpu_bits;
+    a.hash_shift = pl.B + (gpu_bits >= 0 ? (uint32_t)gpu_bits : (uint32_t)ctx->opt_gpu_bits);
     a.result = ctx->result;
     a.out_bld_pay = out_b; a.out_prb_pay = out_p; a.cap = cap;
     const size_t smem = mat ? jc.smem_mat : jc.smem_agg;
@@ -1177,6 +1224,235 @@ extern "C" int gj_stage_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksu
     ctx->stage.active = false;
     if (matches) *matches = ctx->h_result[0];
     if (checksum) *checksum = ctx->h_result[1];
+    return GJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Sharded "partition, then push" pipeline (multi-GPU; kernels.cuh section 3c).  Per relation:
+//   gj_pp_local : coarse histogram -> scan -> cursors -> pass 1 (local) -> pass-2 tile list ->
+//                 fine histogram of this shard (2^(gpu bits + local bits) counters)
+//   [caller: all-gather of the fine histograms, e.g. ncclAllGather on the same stream]
+//   gj_pp_push  : write cursors from the gathered histograms -> pass 2, runs stored into the
+//                 destination GPUs' partition buffers (local or peer-mapped)
+//   [caller: a cross-rank "all pushes have landed" point, e.g. a 1-element all-reduce]
+//   gj_pp_join  : unit planning + join over what this GPU received (already fully partitioned)
+// Nothing synchronises with the host before gj_pp_finish.  ctx->out[] serve as first-pass buffers.
+// ------------------------------------------------------------------------------------------
+static int ensure_pp(gj_ctx* ctx) {
+    gj_ctx::PP& q = ctx->pp;
+    if (q.block) return GJ_OK;
+    const size_t NQ = (size_t)1 << PP_MAX_BITS, NC = (size_t)1 << PP_MAX_PASS_BITS;
+    size_t b = 0, o_cur[2], o_tp[2], o_bs[2], o_z[2];
+    for (int r = 0; r < 2; ++r) {
+        o_cur[r] = b; b += NQ * sizeof(uint32_t);
+        o_tp[r] = b;  b += (NC + 4) * sizeof(uint32_t);
+        o_bs[r] = b;  b += NB_MAX * sizeof(tup_t*);
+    }
+    q.zero_bytes = 64;   // [tile-scan descriptor u64 x 2][ticket u32 .. pad][status u32 x 4]
+    for (int r = 0; r < 2; ++r) { o_z[r] = b; b += q.zero_bytes; }
+    if (cudaMalloc(&q.block, b) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "sharded-pipeline metadata (%.1f MB)", b * 1e-6); }
+    for (int r = 0; r < 2; ++r) {
+        q.cur_fine[r] = reinterpret_cast<uint32_t*>(q.block + o_cur[r]);
+        q.tile_prefix[r] = reinterpret_cast<uint32_t*>(q.block + o_tp[r]);
+        q.bases[r] = reinterpret_cast<tup_t**>(q.block + o_bs[r]);
+        q.zero[r] = q.block + o_z[r];
+        q.tdesc[r] = reinterpret_cast<unsigned long long*>(q.zero[r]);
+        q.tticket[r] = reinterpret_cast<uint32_t*>(q.zero[r] + 16);
+        q.status[r] = reinterpret_cast<uint32_t*>(q.zero[r] + 32);
+    }
+    CK(cudaHostAlloc(&q.h_pin, 2 * NB_MAX * sizeof(void*) + 64, cudaHostAllocDefault));
+    for (auto& r : q.ev) for (auto& e : r) CK(cudaEventCreate(&e));
+    for (auto& e : q.jev) CK(cudaEventCreate(&e));
+    return GJ_OK;
+}
+
+static const PPCfg& pp_first_cfg(uint32_t bits) { return kPPFirst[std::max(bits, 8u) - 8u]; }
+static const PPCfg& pp_push_cfg(const gj_ctx* ctx, uint32_t bits) { return kPPPush[ctx->pp.out ? 1 : 0][std::max(bits, 8u) - 8u]; }
+
+extern "C" int gj_pp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
+                           uint32_t local_bits, void* cuda_stream) {
+    if (!ctx) return fail(GJ_ERR_ARG, "ctx is NULL");
+    if (n_gpus == 0 || n_gpus > (uint32_t)NB_MAX || (n_gpus & (n_gpus - 1))) return fail(GJ_ERR_ARG, "n_gpus must be a power of two <= %d", NB_MAX);
+    if (rank >= n_gpus) return fail(GJ_ERR_ARG, "rank %u out of range", rank);
+    uint32_t g = 0;
+    while ((1u << g) < n_gpus) ++g;
+    if (local_bits < 1 || local_bits > (uint32_t)MAX_RADIX_BITS) return fail(GJ_ERR_ARG, "local_bits must be in [1, %d]", MAX_RADIX_BITS);
+    const uint32_t Btot = g + local_bits;
+    if (Btot < 2 || Btot > PP_MAX_BITS) return fail(GJ_ERR_ARG, "gpu bits + local bits = %u outside [2, %u]", Btot, PP_MAX_BITS);
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_pp(ctx))) return rc;
+    gj_ctx::PP& q = ctx->pp;
+    q.G = n_gpus; q.rank = rank; q.g = g; q.B = local_bits; q.Btot = Btot;
+    // the first pass must cover the GPU bits (a first-pass partition belongs to ONE destination)
+    uint32_t b1 = ctx->opt_pass1_bits ? (uint32_t)ctx->opt_pass1_bits : Btot / 2;
+    b1 = std::max(b1, std::max(g, 1u));
+    if (Btot - b1 > PP_MAX_PASS_BITS) b1 = Btot - PP_MAX_PASS_BITS;
+    b1 = std::min(b1, std::min(PP_MAX_PASS_BITS, Btot - 1));
+    if (b1 < g) return fail(GJ_ERR_ARG, "%u GPU bits do not fit the first pass", g);
+    q.b1 = b1; q.b2 = Btot - b1; q.out = (uint32_t)ctx->opt_pp_out;
+    const bool swap = n_R_global > n_S_global;   // build on the smaller relation -- same choice on every rank
+    q.role_of_side[0] = swap ? 1 : 0;
+    q.role_of_side[1] = swap ? 0 : 1;
+    q.n_glob[0] = n_R_global; q.n_glob[1] = n_S_global;
+    q.active = true;
+    ctx->launches = 0;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaMemsetAsync(ctx->zero_common, 0, ctx->zero_common_bytes, s));
+    CK(cudaEventRecord(ctx->stage_ev[3], s));   // "common block ready"
+    return GJ_OK;
+}
+
+extern "C" int gj_pp_local(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays, uint64_t n,
+                           uint32_t* d_fine_hist, void* cuda_stream) {
+    if (!ctx || !ctx->pp.active) return fail(GJ_ERR_STATE, "gj_pp_begin first");
+    if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
+    if (n > (which ? ctx->maxS : ctx->maxR)) return fail(GJ_ERR_ARG, "n exceeds the context capacity");
+    if (!d_fine_hist || (n && (!d_keys || !d_pays))) return fail(GJ_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    gj_ctx::PP& q = ctx->pp;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const int role = q.role_of_side[which];
+    const RelMeta& m = ctx->meta[role];
+    int rc;
+    CK(cudaMemsetAsync(ctx->zero_role[role], 0, ctx->zero_role_bytes, s));
+    CK(cudaMemsetAsync(q.zero[which], 0, q.zero_bytes, s));
+    CK(cudaMemsetAsync(d_fine_hist, 0, sizeof(uint32_t) << q.Btot, s));
+    CK(cudaEventRecord(q.ev[which][0], s));
+    // coarse (first-pass) histogram -> offsets -> cursors
+    const uint32_t n1 = 1u << q.b1;
+    if ((rc = enqueue_hist(ctx, s, d_keys, false, n, q.b2, q.b1, m.ghist))) return rc;
+    if ((rc = enqueue_scan(ctx, s, role, 1, n1, false))) return rc;
+    Plan p1; p1.B = q.b1; p1.b1 = q.b1; p1.b2 = 0;
+    if ((rc = enqueue_plan(ctx, s, role, 1, p1, false))) return rc;
+    tup_t* first_out = ctx->out[which];
+    if (n) {
+        const PPCfg& c1 = pp_first_cfg(q.b1);
+        const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
+        ScatterArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = first_out;
+        a.shift = q.b2; a.bits = q.b1; a.cursors = m.cur2; a.cursor_stride = 1;
+        a.ntiles = (uint32_t)((n + T1 - 1) / T1);
+        c1.fn<<<a.ntiles, c1.threads, pp_smem(c1), s>>>(a);
+        LAUNCHED();
+    }
+    // pass-2 tile list (tiles never straddle a first-pass partition) and the fine counts per tile
+    const PPCfg& c2 = pp_push_cfg(ctx, q.b2);
+    const uint32_t T2 = (uint32_t)(c2.threads * c2.ipt);
+    ScanSeq st;
+    st.in = m.off; st.in2 = nullptr; st.out = q.tile_prefix[which]; st.desc = q.tdesc[which]; st.ticket = q.tticket[which];
+    st.mode = SCAN_TILES; st.param = T2;
+    if ((rc = enqueue_scan_one(ctx, s, st, n1))) return rc;
+    tiles3_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(m.off, q.tile_prefix[which], n1, T2, q.b2, m.tiles);
+    LAUNCHED();
+    if (n) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n / T2 + n1 + 2, (uint64_t)ctx->sm_count * 8);
+        subhist_tiles_kernel<512><<<grid, 512, 0, s>>>(first_out, m.tiles, q.tile_prefix[which] + n1, q.b2, T2, d_fine_hist);
+        LAUNCHED();
+    }
+    CK(cudaEventRecord(q.ev[which][1], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_pp_push(gj_ctx* ctx, int which, const uint32_t* d_all_hist, void* const* peer_bases,
+                          uint64_t cap_tuples, uint64_t n, void* cuda_stream) {
+    if (!ctx || !ctx->pp.active) return fail(GJ_ERR_STATE, "gj_pp_begin first");
+    if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
+    if (!d_all_hist || !peer_bases) return fail(GJ_ERR_ARG, "NULL argument");
+    if (cap_tuples > 0xFFFFFFFFull) return fail(GJ_ERR_ARG, "destination capacity exceeds 2^32 tuples");
+    CK(cudaSetDevice(ctx->device));
+    gj_ctx::PP& q = ctx->pp;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const int role = q.role_of_side[which];
+    const RelMeta& m = ctx->meta[role];
+    void** hb = reinterpret_cast<void**>(q.h_pin) + (size_t)which * NB_MAX;
+    for (uint32_t g = 0; g < q.G; ++g) {
+        if (!peer_bases[g] || ((size_t)peer_bases[g] & 15u)) return fail(GJ_ERR_ARG, "destination buffer %u must be non-NULL and 16-byte aligned", g);
+        hb[g] = peer_bases[g];
+    }
+    CK(cudaMemcpyAsync(q.bases[which], hb, q.G * sizeof(void*), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(q.ev[which][2], s));
+    // this GPU's own counts / offsets land in the role's histogram + offset arrays (join planning)
+    pp_cursor_kernel<<<q.G, PPC_THREADS, 0, s>>>(d_all_hist, q.G, q.rank, q.B, (uint32_t)cap_tuples, q.cur_fine[which],
+                                                 m.ghist, m.off, q.status[which]);
+    LAUNCHED();
+    if (n) {
+        const PPCfg& c2 = pp_push_cfg(ctx, q.b2);
+        const uint32_t T2 = (uint32_t)(c2.threads * c2.ipt);
+        const uint32_t n1 = 1u << q.b1;
+        ScatterArgs b;
+        memset(&b, 0, sizeof(b));
+        b.in_tup = ctx->out[which]; b.out = nullptr; b.n = (uint32_t)n;
+        b.shift = 0; b.bits = q.b2;
+        b.cursors = q.cur_fine[which]; b.cursor_stride = 1;
+        b.tiles = m.tiles; b.num_tiles = q.tile_prefix[which] + n1;
+        b.part_bases = q.bases[which]; b.part_shift = q.B; b.n_dest = q.G; b.abort_flag = q.status[which];
+        const uint32_t grid = (uint32_t)(n / T2) + n1 + 2;   // upper bound on tiles
+        c2.fn<<<grid, c2.threads, pp_smem(c2), s>>>(b);
+        LAUNCHED();
+    }
+    CK(cudaEventRecord(q.ev[which][3], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_pp_join(gj_ctx* ctx, const void* d_own_R, const void* d_own_S, uint64_t cap_R, uint64_t cap_S,
+                          void* cuda_stream) {
+    if (!ctx || !ctx->pp.active) return fail(GJ_ERR_STATE, "gj_pp_begin first");
+    if (!d_own_R || !d_own_S) return fail(GJ_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    gj_ctx::PP& q = ctx->pp;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaStreamWaitEvent(s, ctx->stage_ev[3], 0));
+    Plan pl; pl.B = q.B; pl.b1 = q.B; pl.b2 = 0;
+    const bool r_builds = q.role_of_side[0] == 0;
+    const tup_t* bld = (const tup_t*)(r_builds ? d_own_R : d_own_S);
+    const tup_t* prb = (const tup_t*)(r_builds ? d_own_S : d_own_R);
+    int rc;
+    CK(cudaEventRecord(q.jev[0], s));
+    if (q.n_glob[0] && q.n_glob[1]) {
+        if ((rc = enqueue_scan(ctx, s, 0, 0, 1u << pl.B, true))) return rc;
+        if ((rc = enqueue_plan(ctx, s, 0, 0, pl, true))) return rc;
+        if ((rc = enqueue_join(ctx, s, bld, prb, pl, r_builds ? cap_R : cap_S, r_builds ? cap_S : cap_R, false,
+                               nullptr, nullptr, 0, nullptr, (int)q.g))) return rc;
+    }
+    CK(cudaEventRecord(q.jev[1], s));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    uint32_t* hs = reinterpret_cast<uint32_t*>(q.h_pin + 2 * NB_MAX * sizeof(void*));
+    for (int w = 0; w < 2; ++w) CK(cudaMemcpyAsync(hs + 4 * w, q.status[w], 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[3], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_pp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
+                            uint64_t* n_local_S, float* phase_ms) {
+    if (!ctx || !ctx->pp.active) return fail(GJ_ERR_STATE, "gj_pp_begin first");
+    gj_ctx::PP& q = ctx->pp;
+    CK(cudaEventSynchronize(ctx->ev[3]));
+    q.active = false;
+    const uint32_t* hs = reinterpret_cast<const uint32_t*>(q.h_pin + 2 * NB_MAX * sizeof(void*));
+    if (n_local_R) *n_local_R = hs[1];
+    if (n_local_S) *n_local_S = hs[5];
+    if (hs[0] || hs[4])
+        return fail(GJ_ERR_ARG, "sharded join: a destination GPU would receive more tuples than its buffer holds "
+                                "(this GPU: %u R, %u S tuples) -- raise the receive-buffer slack", hs[1], hs[5]);
+    if (matches) *matches = ctx->h_result[0];
+    if (checksum) *checksum = ctx->h_result[1];
+    if (phase_ms) {   // [local R, push R, local S, push S, join]; the events of a relation sit on its stream
+        for (int w = 0; w < 2; ++w) {
+            CK(cudaEventSynchronize(q.ev[w][3]));
+            CK(cudaEventElapsedTime(&phase_ms[2 * w], q.ev[w][0], q.ev[w][1]));
+            CK(cudaEventElapsedTime(&phase_ms[2 * w + 1], q.ev[w][2], q.ev[w][3]));
+        }
+        CK(cudaEventElapsedTime(&phase_ms[4], q.jev[0], q.jev[1]));
+    }
+    return GJ_OK;
+}
+
+extern "C" int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bits) {
+    if (!ctx || !ctx->pp.block) return fail(GJ_ERR_STATE, "gj_pp_begin first");
+    if (pass1_bits) *pass1_bits = ctx->pp.b1;
+    if (pass2_bits) *pass2_bits = ctx->pp.b2;
     return GJ_OK;
 }
 

@@ -423,6 +423,118 @@ tiles3_kernel(const uint32_t* __restrict__ off2, const uint32_t* __restrict__ ti
 }
 
 // ------------------------------------------------------------------------------------------
+// 3c. Sharded "partition, then push" pipeline (multi-GPU, no reference counterpart).
+//     Every GPU partitions its own shard on ALL radix bits [gpu bits | local bits]: pass 1 on
+//     the high b1 bits (local), then the fine counts of the low b2 bits inside every first-pass
+//     partition (subhist_tiles_kernel, one pass-2 tile per step, 8 B/tuple read), an all-gather
+//     of those fine histograms (host: NCCL), and pass 2 whose runs go straight into the
+//     DESTINATION GPU's final partition buffer over NVLink (scatter_kernel<..., PUSH>): the
+//     all-to-all is the last radix pass and the receiver joins what arrives without another pass.
+//     pp_cursor_kernel turns the gathered histograms into this GPU's write cursors: destination
+//     d lays partition p out at  sum_{p' < p} C[d][p']  (C = counts summed over all sources) and
+//     source r writes its share at  + sum_{s < r} H[s][d][p]  -- every rank computes the same
+//     layout from the same numbers, no further communication.  The CTA of d == rank also writes
+//     this GPU's own partition counts / offsets for the join's unit planning.
+// ------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+subhist_tiles_kernel(const tup_t* __restrict__ data, const uint4* __restrict__ tiles,
+                     const uint32_t* __restrict__ num_tiles, uint32_t bits, uint32_t tile_tuples,
+                     uint32_t* __restrict__ fine_hist) {
+    __shared__ uint32_t sh[1024];
+    const uint32_t nb = 1u << bits, mask = nb - 1u, nt = *num_tiles;
+    for (uint32_t t = blockIdx.x; t < nt; t += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < nb; i += THREADS) sh[i] = 0;
+        __syncthreads();
+        const uint4 td = __ldg(tiles + t);
+        const uint32_t a0 = td.x, lo = td.y, hi = td.z;
+        const uint4* v = reinterpret_cast<const uint4*>(data + a0);   // a0 even, buffer 16-byte aligned
+        const bool full = (lo == a0) && (hi - a0 == tile_tuples);
+        for (uint32_t pi = threadIdx.x; 2u * pi < tile_tuples; pi += THREADS) {
+            const uint32_t s0 = a0 + 2u * pi;
+            if (full || (s0 >= lo && s0 + 1u < hi)) {
+                const uint4 x = __ldg(v + pi);
+                atomicAdd(&sh[x.x & mask], 1u);
+                atomicAdd(&sh[x.z & mask], 1u);
+            } else {
+                if (s0 >= lo && s0 < hi) atomicAdd(&sh[__ldg(data + s0).x & mask], 1u);
+                if (s0 + 1u >= lo && s0 + 1u < hi) atomicAdd(&sh[__ldg(data + s0 + 1u).x & mask], 1u);
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nb; i += THREADS) {
+            const uint32_t c = sh[i];
+            if (c) atomicAdd(&fine_hist[(size_t)td.w + i], c);
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int PPC_THREADS = 1024, PPC_IPT = 4;
+// status words: [0] abort (some destination would overflow its buffer), [1] tuples this GPU receives
+__global__ void __launch_bounds__(PPC_THREADS)
+pp_cursor_kernel(const uint32_t* __restrict__ all_hist, uint32_t n_gpus, uint32_t rank, uint32_t local_bits,
+                 uint32_t cap_tuples, uint32_t* __restrict__ cur_fine, uint32_t* __restrict__ loc_cnt,
+                 uint32_t* __restrict__ loc_off, uint32_t* __restrict__ status) {
+    __shared__ uint32_t s_warp[PPC_THREADS / 32];
+    __shared__ uint32_t s_run;
+    const uint32_t d = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t np = 1u << local_bits;
+    const size_t nq = (size_t)n_gpus << local_bits;
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < np; base += PPC_THREADS * PPC_IPT) {
+        uint32_t c[PPC_IPT], pre[PPC_IPT], tsum = 0;
+#pragma unroll
+        for (int j = 0; j < PPC_IPT; ++j) {
+            const uint32_t p = base + tid * PPC_IPT + j;
+            c[j] = 0; pre[j] = 0;
+            if (p < np) {
+                const size_t q = ((size_t)d << local_bits) + p;
+                for (uint32_t s = 0; s < n_gpus; ++s) {
+                    const uint32_t h = __ldg(all_hist + (size_t)s * nq + q);
+                    c[j] += h;
+                    if (s < rank) pre[j] += h;
+                }
+            }
+            tsum += c[j];
+        }
+        const uint32_t incl = warp_incl_scan(tsum, lane);
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        uint32_t woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < PPC_THREADS / 32; ++w) {
+            const uint32_t x = s_warp[w];
+            if ((uint32_t)w < wid) woff += x;
+            tot += x;
+        }
+        uint32_t run = s_run + woff + incl - tsum;
+#pragma unroll
+        for (int j = 0; j < PPC_IPT; ++j) {
+            const uint32_t p = base + tid * PPC_IPT + j;
+            if (p < np) {
+                cur_fine[((size_t)d << local_bits) + p] = run + pre[j];
+                if (d == rank) { loc_cnt[p] = c[j]; loc_off[p] = run; }
+            }
+            run += c[j];
+        }
+        __syncthreads();              // everyone has read s_run / s_warp
+        if (tid == 0) s_run += tot;
+        __syncthreads();
+    }
+    const uint32_t total = s_run;
+    // +16: bulk copies and 16-byte loads of the join round partition ends out to tuple pairs
+    const bool overflow = (unsigned long long)total + 16ull > (unsigned long long)cap_tuples;
+    if (overflow && tid == 0) atomicExch(&status[0], 1u);
+    if (d == rank) {
+        if (tid == 0) { status[1] = total; loc_off[np] = overflow ? 0u : total; }
+        if (overflow)   // nothing will arrive: give the join an empty relation
+            for (uint32_t p = tid; p < np; p += PPC_THREADS) { loc_cnt[p] = 0; loc_off[p] = 0; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // 4. Radix scatter pass.  One tile of THREADS*IPT tuples per CTA:
 //      load (16-byte loads, registers) -> shared-memory histogram that also yields each tuple's
 //      rank inside its digit -> block scan of the 2^bits counts + ONE global ticket per
@@ -456,20 +568,34 @@ struct ScatterArgs {
     uint32_t ntiles;             // pass 1: number of tiles (the grid may be smaller: CTAs loop)
     const uint4* tiles;          // pass 2 only
     const uint32_t* num_tiles;   // pass 2 only
+    // PUSH (last pass of the sharded "partition, then push" pipeline): the output base is chosen
+    // per TILE -- the tile's first-pass partition belongs to one destination GPU, whose final
+    // partition buffer (local or mapped over NVLink) receives the runs -- and tiles are taken in
+    // an order that spreads consecutive CTAs over all destinations.
+    tup_t* const* part_bases;    // [n_dest] final partition buffers
+    uint32_t part_shift;         // destination = cursor base >> part_shift
+    uint32_t n_dest;
+    const uint32_t* abort_flag;  // non-zero: a destination would overflow, nothing is written
 };
 
-template <int THREADS, int IPT, int MODE, int OUT, bool COLUMNAR, int MINB, bool PERSIST = false>
+__device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b) {
+    while (b) { const uint32_t t = a % b; a = b; b = t; }
+    return a;
+}
+
+template <int THREADS, int IPT, int MODE, int OUT, bool COLUMNAR, int MINB, bool PERSIST = false, int NBT = NB_MAX, bool PUSH = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 scatter_kernel(ScatterArgs a) {
     constexpr uint32_t T = THREADS * IPT;
-    static_assert(THREADS >= NB_MAX, "one thread per digit in the scan step");
+    static_assert(THREADS >= NBT, "one thread per digit in the scan step");
     static_assert(IPT % 4 == 0, "vector loads");
+    static_assert(!PUSH || (!COLUMNAR && !PERSIST), "the push pass reads first-pass output, one tile per CTA");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    tup_t* tile = reinterpret_cast<tup_t*>(smem_raw);   // T (+ 2*NB_MAX padding slots for OUT 1)
-    __shared__ uint32_t s_hist[NB_MAX];
-    __shared__ uint32_t s_lbase[NB_MAX];
-    __shared__ tup_t* s_dst[NB_MAX];
-    __shared__ uint32_t s_warp[NB_MAX / 32];
+    tup_t* tile = reinterpret_cast<tup_t*>(smem_raw);   // T (+ 2*NBT padding slots for OUT 1)
+    __shared__ uint32_t s_hist[NBT];                    // NBT = largest fan-out of this variant (256, 512 or 1024)
+    __shared__ uint32_t s_lbase[MODE == 0 ? NBT : 1];
+    __shared__ tup_t* s_dst[NBT];
+    __shared__ uint32_t s_warp[NBT / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t nb = 1u << a.bits, mask = nb - 1u;
@@ -478,7 +604,17 @@ scatter_kernel(ScatterArgs a) {
     // -- the multi-GPU peer scatter can leave SM resources to concurrently running kernels.  (As a
     // run-time loop in every variant it cost the one-tile launches ~1.5 %, hence the template.)
     const uint32_t ntiles_total = (a.tiles == nullptr) ? a.ntiles : *a.num_tiles;
-    for (uint32_t tile_id = blockIdx.x; tile_id < ntiles_total; tile_id += gridDim.x) {
+    uint32_t first_tile = blockIdx.x;
+    if (PUSH) {
+        // tiles are sorted by destination; CTA b takes tile (b * stride) mod N with stride ~ N / n_dest
+        // coprime to N: a bijection under which any window of resident CTAs covers all destinations
+        // in proportion to their share (no NVLink ingress hot spot, whatever the skew)
+        if (blockIdx.x >= ntiles_total || *a.abort_flag) return;
+        uint32_t stride = ntiles_total / a.n_dest + 1u;
+        while (gcd_u32(stride, ntiles_total) != 1u) ++stride;
+        first_tile = (uint32_t)(((unsigned long long)blockIdx.x * stride) % ntiles_total);
+    }
+    for (uint32_t tile_id = first_tile; tile_id < ntiles_total; tile_id += gridDim.x) {
     // ---- which slots does this tile cover ----
     uint32_t a0, lo, hi, cbase;
     const tup_t* in_tup = a.in_tup;
@@ -497,7 +633,7 @@ scatter_kernel(ScatterArgs a) {
         a0 = td.x; lo = td.y; hi = td.z; cbase = td.w;
     }
     if (hi <= lo) { if (PERSIST) continue; else return; }
-    if (tid < NB_MAX) s_hist[tid] = 0;
+    if (tid < NBT) s_hist[tid] = 0;
     __syncthreads();
     const bool full = (lo == a0) && (hi - a0 == T);
 
@@ -567,7 +703,7 @@ scatter_kernel(ScatterArgs a) {
     // OUT 1 pads every digit's region to an even number of slots (+ room for a 1-slot phase
     // shift) so that region starts are 16-byte aligned in shared memory.
     uint32_t cnt = 0, sz = 0, incl = 0;
-    if (tid < NB_MAX) {
+    if (tid < NBT) {
         cnt = (tid < nb) ? s_hist[tid] : 0u;
         sz = (OUT == 1) ? ((cnt + 2u) & ~1u) : cnt;
         incl = warp_incl_scan(sz, lane);
@@ -579,11 +715,11 @@ scatter_kernel(ScatterArgs a) {
     if (tid < nb) {
         uint32_t woff = 0;
 #pragma unroll
-        for (uint32_t w = 0; w < NB_MAX / 32; ++w)
+        for (uint32_t w = 0; w < NBT / 32; ++w)
             if (w < wid) woff += s_warp[w];
         const uint32_t excl = incl - sz + woff;
         if (cnt) gb = atomicAdd(&a.cursors[(size_t)(cbase + tid) * a.cursor_stride], cnt);
-        dbase = a.dst_bases ? a.dst_bases[tid] : a.out;
+        dbase = PUSH ? a.part_bases[cbase >> a.part_shift] : (a.dst_bases ? a.dst_bases[tid] : a.out);
         sbeg = (OUT == 1) ? excl + (gb & 1u) : excl;   // same 16-byte phase as the destination
         // tile slot i (i >= sbeg for this digit) goes to dbase[gb + (i - sbeg)]
         s_dst[tid] = reinterpret_cast<tup_t*>(reinterpret_cast<unsigned long long>(dbase) +

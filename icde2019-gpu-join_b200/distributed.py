@@ -15,6 +15,13 @@ cudaSetDevice(1), hash_join_clustered_probe.cu:1001,1685).  Design:
     4. local      partition + build + probe on the received tuples (gj_join_aggregate_tuples)
     5. reduce     all_reduce(SUM) of {matches, checksum} (int64 wrap-around == mod 2^64)
 
+  mode "pp" ("partition, then push") turns the order around: every GPU first partitions its OWN
+  shard on all [gpu | local] bits (pass 1 local), the ranks all-gather their fine histograms
+  (2^(g+B) counters each -- every rank then derives the same global layout, `pp_layout`), and the
+  LAST radix pass stores its runs straight into the destination GPU's final partition buffer over
+  NVLink.  The receiver joins what arrives without touching it again, R's push overlaps S's local
+  pass, and the shuffle costs no extra pass over the data.
+
 `ops` abstracts the three device steps so the host logic (counts, offsets, split sizes,
 collectives, reduction) is testable on CPU with the gloo backend and a stand-in `ops`.
 """
@@ -43,6 +50,22 @@ def receive_layout(counts: np.ndarray, rank: int):
     recv_offsets = np.concatenate(([0], np.cumsum(recv_counts)[:-1]))
     write_at = np.array([counts[:rank, d].sum() for d in range(counts.shape[1])], dtype=np.int64)
     return recv_counts, recv_offsets, write_at
+
+
+def pp_layout(all_hist: np.ndarray, rank: int, local_bits: int):
+    """numpy model of pp_cursor_kernel (csrc/kernels.cuh): all_hist[s][q] = tuples of source s in
+    global partition q = (dest << local_bits) | p.  Destination d lays partition p out at
+    sum_{p' < p} C[d][p'] (C = counts over all sources); source `rank` writes its share at
+    + sum_{s < rank} H[s][d][p].  Returns (write cursors of `rank` [G << B], own offsets [2^B + 1],
+    own counts [2^B])."""
+    all_hist = np.asarray(all_hist)
+    G = all_hist.shape[0]
+    n_p = 1 << local_bits
+    H = all_hist.astype(np.int64).reshape(G, G, n_p)          # [source][dest][partition]
+    Cn = H.sum(axis=0)                                        # [dest][partition]
+    off = np.concatenate((np.zeros((G, 1), dtype=np.int64), np.cumsum(Cn, axis=1)), axis=1)
+    cur = (off[:, :-1] + H[:rank].sum(axis=0)).reshape(-1)
+    return cur, off[rank], Cn[rank]
 
 
 @dataclass
@@ -198,6 +221,48 @@ class GpuOps:
             cs.synchronize()
         return m, c, {"shuffle_scatter_ms": eng.shuffle_scatter_ms(0) + eng.shuffle_scatter_ms(1)}
 
+    def pp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob):
+        """Mode "pp": local passes -> all-gather of the fine histograms -> pushing last pass ->
+        join.  R runs on a normal-priority stream, S on the high-priority one: while R's
+        (NVLink-bound) push is in flight, S's local pass gets the SM slots it asks for.  The
+        cross-rank points are NCCL collectives enqueued on those streams; the host blocks only
+        in pp_finish."""
+        import os
+        torch, eng = self.torch, self.engine
+        streams = (self.stream_shuffle, self.stream_local)      # R: normal priority, S: high
+        nq = G << B
+        if getattr(self, "_pp_nq", None) != (G, nq):
+            self._pp_hist = [torch.empty(nq, dtype=torch.int32, device=self.dev) for _ in range(2)]
+            self._pp_all = [torch.empty(G * nq, dtype=torch.int32, device=self.dev) for _ in range(2)]
+            self._pp_tok = [torch.zeros(1, dtype=torch.int32, device=self.dev) for _ in range(2)]
+            self._pp_nq = (G, nq)
+        cur = torch.cuda.current_stream(self.device)
+        for s in streams:
+            s.wait_stream(cur)
+        eng.pp_begin(n_glob[0], n_glob[1], G, rank, B, streams[0])
+        caps = (self.cap_R, self.cap_S)
+        for which, (k, p) in enumerate(rels):
+            eng.pp_local(which, k, p, self._pp_hist[which], streams[which])
+            with torch.cuda.stream(streams[which]):
+                dist.all_gather_into_tensor(self._pp_all[which], self._pp_hist[which], group=group)
+        pushed = None
+        for which, (k, p) in enumerate(rels):
+            s = streams[which]
+            if pushed is not None and not os.environ.get("GJ_CONCURRENT_SHUFFLE"):
+                s.wait_event(pushed)                              # one relation on NVLink at a time
+            eng.pp_push(which, self._pp_all[which], peers[which], caps[which], k.numel(), s)
+            pushed = torch.cuda.Event()
+            pushed.record(s)
+            with torch.cuda.stream(s):
+                dist.all_reduce(self._pp_tok[which], group=group)   # every rank's pushes have landed
+        streams[1].wait_stream(streams[0])
+        eng.pp_join(own_ptrs[0], own_ptrs[1], caps[0], caps[1], streams[1])
+        m, c, n_r, n_s, ph = eng.pp_finish()
+        streams[0].synchronize()
+        b1, b2 = eng.pp_plan()
+        ph = dict(ph, shuffle_scatter_ms=ph["push_R_ms"] + ph["push_S_ms"], pass1_bits=b1, pass2_bits=b2, radix_bits=B)
+        return m, c, (n_r, n_s), ph
+
     def exchange_counts(self, dist, group, mine):
         """All ranks' count vectors in ONE small NCCL all-gather (doubles as a barrier)."""
         t = self.torch.tensor([int(x) for x in mine], dtype=self.torch.int64, device=self.dev)
@@ -241,10 +306,15 @@ class ShardedJoin:
                                                       with_send_buffers=(mode in ("nccl", "dma")))
         self.max_local = (max_local_R, max_local_S)
         self._peers = None
-        if mode in ("p2p", "dma"):
-            self._setup_peers()
+        self._own = [0, 0]
+        if mode in ("p2p", "dma", "pp"):
+            if ops is None:
+                self._setup_peers()
+            else:                      # test stand-in: no device buffers to map
+                self._peers = [[0] * self.world, [0] * self.world]
+                self._opened = []
         elif mode != "nccl":
-            raise ValueError("mode must be 'nccl', 'p2p' or 'dma'")
+            raise ValueError("mode must be 'nccl', 'p2p', 'dma' or 'pp'")
 
     # -- CUDA IPC mapping of every rank's receive buffers (p2p mode) -------------------------
     def _setup_peers(self):
@@ -280,7 +350,7 @@ class ShardedJoin:
         self._L = L
 
     def close(self):
-        if self._peers is not None:
+        if self._peers is not None and self._opened is not None and any(self._own):
             for q in self._opened:
                 self._L.gj_ipc_close(C.c_void_p(q))
             self.dist.barrier(group=self.group)
@@ -310,7 +380,11 @@ class ShardedJoin:
         shift = B
         rels = ((Rk, Rp), (Sk, Sp))
         local_n = [0, 0]
-        if self.mode == "nccl":
+        if self.mode == "pp":
+            m, c, local_n, tm = ops.pp_join(dist, self.group, rank, rels, G, B, self._peers, self._own,
+                                            (n_R_global, n_S_global))
+            lap()
+        elif self.mode == "nccl":
             import torch
             for which, (k, p) in enumerate(rels):
                 cnt = ops.split(which, k, p, G, shift)
@@ -358,12 +432,16 @@ class ShardedJoin:
                 tm = dict(tm, shuffle_scatter_ms=shuffle_ms)
         if self.mode == "nccl":
             m, c, tm = ops.local_join(local_n[0], local_n[1])
-        lap()
+        if self.mode != "pp":
+            lap()
         res = ops.result_tensor(m, c)
         dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
         vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
         lap()
-        if self.mode != "nccl" and len(t_host) == 5:
+        if self.mode == "pp":
+            d = [1e3 * (b - a) for a, b in zip(t_host, t_host[1:])]
+            tm = dict(tm, host_ms={"pipeline": d[0], "reduce": d[1]})
+        elif self.mode != "nccl" and len(t_host) == 5:
             d = [1e3 * (b - a) for a, b in zip(t_host, t_host[1:])]
             tm = dict(tm, host_ms={"count": d[0], "exchange": d[1], "shuffle+local": d[2], "reduce": d[3]})
         return ShardedResult(vals[0], vals[1], local_n[0], local_n[1], tm)

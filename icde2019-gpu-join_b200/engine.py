@@ -22,7 +22,8 @@ C_ABI_SYMBOLS = [
     "gj_get_option", "gj_join_aggregate", "gj_join_aggregate_tuples", "gj_join_aggregate_host",
     "gj_join_materialize", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
-    "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
+    "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
+    "gj_pp_finish", "gj_pp_plan", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
     "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_device_synchronize", "gj_flush_l2",
     "gj_kernel_launch_count",
@@ -100,6 +101,12 @@ def lib() -> C.CDLL:
     L.gj_stage_partition.argtypes = [vp, C.c_int, vp, vp]
     L.gj_stage_join.argtypes = [vp, vp]
     L.gj_stage_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.gj_pp_begin.argtypes = [vp, u64, u64, u32, u32, u32, vp]
+    L.gj_pp_local.argtypes = [vp, C.c_int, i32p, i32p, u64, vp, vp]
+    L.gj_pp_push.argtypes = [vp, C.c_int, vp, C.POINTER(vp), u64, u64, vp]
+    L.gj_pp_join.argtypes = [vp, vp, vp, u64, u64, vp]
+    L.gj_pp_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float)]
+    L.gj_pp_plan.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     L.gj_generate_unique.argtypes = [vp, i32p, i32p, u64, u64, u64, u32, u32]
     L.gj_bijection.argtypes = [u64, u64, u32]
     L.gj_bijection.restype = u32
@@ -332,6 +339,40 @@ class JoinEngine:
         m, c = C.c_uint64(), C.c_uint64()
         _check(self._L.gj_stage_finish(self._ctx, C.byref(m), C.byref(c)))
         return int(m.value), int(c.value)
+
+    # -- sharded "partition, then push" pipeline (gj_pp_*) -----------------------------------
+    @staticmethod
+    def _sptr(stream):
+        return C.c_void_p(stream.cuda_stream if stream is not None else 0)
+
+    def pp_begin(self, n_R_global: int, n_S_global: int, n_gpus: int, rank: int, local_bits: int, stream=None):
+        _check(self._L.gj_pp_begin(self._ctx, n_R_global, n_S_global, n_gpus, rank, local_bits, self._sptr(stream)))
+
+    def pp_local(self, which: int, keys, pays, fine_hist, stream=None):
+        """fine_hist: int32/uint32 CUDA tensor of 2^(gpu bits + local bits) counters (overwritten)."""
+        n = keys.numel()
+        _check(self._L.gj_pp_local(self._ctx, which, _dev_ptr(keys, n, "keys"), _dev_ptr(pays, n, "pays"), n,
+                                   C.c_void_p(fine_hist.data_ptr()), self._sptr(stream)))
+
+    def pp_push(self, which: int, all_hist, peer_ptrs, cap_tuples: int, n: int, stream=None):
+        bases = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        _check(self._L.gj_pp_push(self._ctx, which, C.c_void_p(all_hist.data_ptr()), bases, cap_tuples, n, self._sptr(stream)))
+
+    def pp_join(self, own_R: int, own_S: int, cap_R: int, cap_S: int, stream=None):
+        _check(self._L.gj_pp_join(self._ctx, C.c_void_p(own_R), C.c_void_p(own_S), cap_R, cap_S, self._sptr(stream)))
+
+    def pp_finish(self):
+        """Returns (matches, checksum, tuples received of R, of S, phase_ms dict)."""
+        m, c, a, b = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        ph = (C.c_float * 5)()
+        _check(self._L.gj_pp_finish(self._ctx, C.byref(m), C.byref(c), C.byref(a), C.byref(b), ph))
+        names = ("local_R_ms", "push_R_ms", "local_S_ms", "push_S_ms", "join_ms")
+        return int(m.value), int(c.value), int(a.value), int(b.value), dict(zip(names, (float(x) for x in ph)))
+
+    def pp_plan(self):
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(self._L.gj_pp_plan(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     # -- synthetic data ---------------------------------------------------------------------
     def generate_unique(self, keys, pays, row_begin: int, n_total: int, seed: int, pay_seed: int):

@@ -78,7 +78,8 @@ int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
  *   "scatter_cfg1"/"scatter_cfg2" per-pass variants; 255 = measured best per fan-out (default)
  *   "join_cfg"     join kernel shape variant (0 = default)
  *   "gpu_bits"     number of key bits above the radix field consumed by the multi-GPU shuffle
- *   "shuffle_grid" persistent CTA count of the peer-store scatter (0 = one tile per CTA) */
+ *   "shuffle_grid" persistent CTA count of the peer-store scatter (0 = one tile per CTA)
+ *   "pp_out"       sharded pipeline: pushed runs leave the SM as 8-byte stores (0) or TMA bulk stores (1) */
 int gj_set_option(gj_ctx* ctx, const char* name, int64_t value);
 int gj_get_option(gj_ctx* ctx, const char* name, int64_t* value);
 
@@ -168,6 +169,38 @@ int gj_stage_begin(gj_ctx* ctx, uint64_t nR, uint64_t nS, void* cuda_stream);
 int gj_stage_partition(gj_ctx* ctx, int side, const void* d_tuples, void* cuda_stream);
 int gj_stage_join(gj_ctx* ctx, void* cuda_stream);
 int gj_stage_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum);
+
+/* ---- sharded "partition, then push" pipeline (multi-GPU, default) -------
+ * Radix field = [gpu bits | local bits] (destination = (key >> local_bits) & (n_gpus-1), as above).
+ * Every GPU partitions its OWN shard on all gpu+local bits in two passes; the second pass stores
+ * its runs straight into the destination GPU's final partition buffer (local or peer-mapped over
+ * NVLink), so the all-to-all IS the last radix pass and the receiver joins what arrives without
+ * another pass over it.  Per relation (`which` 0 = R, 1 = S), each on a stream of the caller's:
+ *   gj_pp_local  histogram + first pass (local) + this shard's fine histogram into d_fine_hist
+ *                (2^(gpu bits + local bits) uint32, device);
+ *   -- the caller all-gathers the fine histograms of all ranks into d_all_hist
+ *      ([n_gpus][2^(gpu bits + local bits)] uint32, rank-major) on the same stream --
+ *   gj_pp_push   derives this rank's write cursors from d_all_hist (every rank computes the same
+ *                layout, no further exchange) and runs the pushing pass; peer_bases[g] = GPU g's
+ *                partition buffer for this relation (16-byte aligned, cap_tuples + 16 tuples);
+ *   -- the caller makes sure every rank's push has completed (e.g. a 1-element all-reduce) --
+ *   gj_pp_join   unit planning + build/probe over this GPU's received partitions;
+ *   gj_pp_finish synchronises; returns the local aggregate, the tuples this GPU received and
+ *                (phase_ms[5], optional) the device time of local R, push R, local S, push S, join.
+ * gj_pp_finish fails with GJ_ERR_ARG when some destination would have overflowed cap_tuples (then
+ * nothing was pushed on any rank).  Options: "pass1_bits" (first-pass bits, 0 = half of the field),
+ * "pp_out" (0 = 8-byte stores, 1 = TMA bulk stores for the pushed runs). */
+int gj_pp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
+                uint32_t local_bits, void* cuda_stream);
+int gj_pp_local(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays, uint64_t n,
+                uint32_t* d_fine_hist, void* cuda_stream);
+int gj_pp_push(gj_ctx* ctx, int which, const uint32_t* d_all_hist, void* const* peer_bases,
+               uint64_t cap_tuples, uint64_t n, void* cuda_stream);
+int gj_pp_join(gj_ctx* ctx, const void* d_own_R, const void* d_own_S, uint64_t cap_R, uint64_t cap_S,
+               void* cuda_stream);
+int gj_pp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
+                 uint64_t* n_local_S, float* phase_ms);
+int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bits);
 
 /* CUDA IPC plumbing for the peer-store variant when every GPU is driven by its own process:
  * export a gj_malloc_device allocation as a 64-byte handle, open a peer's handle (peer access is

@@ -54,12 +54,56 @@ class NumpyOps:
         res = oracle.join_check(rk, rp, sk, sp, 1)
         return res.matches, res.checksum, {}
 
+    def pp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob):
+        """Mode "pp" without a GPU: fine histograms with numpy, the real all-gather, the layout of
+        distributed.pp_layout (the numpy model of pp_cursor_kernel), and the push emulated by an
+        all-to-all of (slot, tuple) pairs -- the receiver checks that the slots every source computed
+        on its own tile [0, total) exactly and that every partition range holds only its keys."""
+        from oracle import oracle
+        import __graft_entry__ as ge
+        pp_layout = ge.load_package().distributed.pp_layout
+        torch = self.torch
+        nq, mask = G << B, (G << B) - 1
+        cols, local_n = [], []
+        for k, p in rels:
+            kk, pv = k.numpy(), p.numpy()
+            q = (kk.view(np.uint32) & mask).astype(np.int64)
+            hist = torch.from_numpy(np.bincount(q, minlength=nq).astype(np.int32))
+            allh = torch.empty(G * nq, dtype=torch.int32)
+            dist.all_gather_into_tensor(allh, hist, group=group)
+            ah = allh.numpy().reshape(G, nq)
+            cur, off, cnt = pp_layout(ah, rank, B)
+            order = np.argsort(q, kind="stable")
+            qs = q[order]
+            start = np.concatenate(([0], np.cumsum(np.bincount(qs, minlength=nq))[:-1]))
+            slot = cur[qs] + (np.arange(qs.size) - start[qs])
+            packed = (kk[order].view(np.uint32).astype(np.uint64) | (pv[order].view(np.uint32).astype(np.uint64) << 32)).view(np.int64)
+            send = torch.from_numpy(np.ascontiguousarray(np.stack([slot, packed], axis=1)))
+            n_to = np.bincount(qs >> B, minlength=G)
+            n_from = ah.reshape(G, G, -1)[:, rank].sum(axis=1)
+            recv = torch.empty((int(n_from.sum()), 2), dtype=torch.int64)
+            dist.all_to_all_single(recv, send, output_split_sizes=[int(x) for x in n_from],
+                                   input_split_sizes=[int(x) for x in n_to], group=group)
+            r = recv.numpy()
+            tot = int(off[-1])
+            assert r.shape[0] == tot and np.array_equal(np.sort(r[:, 0]), np.arange(tot))
+            buf = np.empty(tot, dtype=np.int64)
+            buf[r[:, 0]] = r[:, 1]
+            u = buf.view(np.uint64)
+            keys = (u & 0xFFFFFFFF).astype(np.uint32)
+            pid = np.repeat(np.arange(1 << B, dtype=np.int64) + (rank << B), cnt)
+            assert np.array_equal((keys & mask).astype(np.int64), pid)
+            cols.append((keys.view(np.int32), (u >> 32).astype(np.uint32).view(np.int32)))
+            local_n.append(tot)
+        res = oracle.join_check(cols[0][0], cols[0][1], cols[1][0], cols[1][1], 1)
+        return res.matches, res.checksum, local_n, {}
+
     def result_tensor(self, m, c):
         to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v  # noqa: E731
         return self.torch.tensor([to_i64(m), to_i64(c)], dtype=self.torch.int64)
 
 
-def _worker(rank, world, port, nR, nS, q):
+def _worker(rank, world, port, nR, nS, q, mode="nccl"):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch
@@ -77,7 +121,7 @@ def _worker(rank, world, port, nR, nS, q):
         Sp = rng.integers(-2**31, 2**31, nS, dtype=np.int64).astype(np.int32)
         want = oracle.join_check(Rk, Rp, Sk, Sp, 1)
         sl = lambda a: torch.from_numpy(a[len(a) * rank // world: len(a) * (rank + 1) // world].copy())  # noqa: E731
-        sj = gj.distributed.ShardedJoin(nR, nS, group=None, mode="nccl", ops=NumpyOps(nR + nS, rank, world))
+        sj = gj.distributed.ShardedJoin(nR, nS, group=None, mode=mode, ops=NumpyOps(nR + nS, rank, world))
         got = sj.join_aggregate(sl(Rk), sl(Rp), sl(Sk), sl(Sp), nR, nS)
         tot = torch.tensor([got.local_R, got.local_S])
         dist.all_reduce(tot)
@@ -87,13 +131,14 @@ def _worker(rank, world, port, nR, nS, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nR,nS", [(2, 20_000, 50_000), (4, 30_000, 30_001), (2, 7, 0)])
-def test_sharded_join_host_logic_gloo(world, nR, nS):
+@pytest.mark.parametrize("world,nR,nS,mode", [(2, 20_000, 50_000, "nccl"), (4, 30_000, 30_001, "nccl"), (2, 7, 0, "nccl"),
+                                              (2, 20_000, 50_000, "pp"), (4, 30_000, 30_001, "pp"), (2, 7, 0, "pp")])
+def test_sharded_join_host_logic_gloo(world, nR, nS, mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nR, nS, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nR, nS, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=180) for _ in range(world)]
@@ -112,3 +157,26 @@ def test_receive_layout_and_bits(gj):
     assert wa.tolist() == [0, 0, 0]
     assert d.choose_radix_bits(128_000_000) == 15 and d.choose_radix_bits(1 << 20) == 8
     assert d.choose_radix_bits(250_000_000) == 16 and d.choose_radix_bits(10) == 1
+
+
+def test_pp_layout_tiles_every_destination(gj):
+    """The write cursors every source derives from the gathered histograms partition each
+    destination's buffer exactly: partition p of destination d is [off_d[p], off_d[p+1]) and the
+    sources' shares follow each other in rank order."""
+    d = gj.distributed
+    rng = np.random.default_rng(3)
+    G, B = 4, 3
+    H = rng.integers(0, 7, size=(G, G << B))
+    H[:, 5] = 0                                    # an empty partition
+    cur = [d.pp_layout(H, r, B)[0] for r in range(G)]
+    for dest in range(G):
+        _, off, cnt = d.pp_layout(H, dest, B)
+        assert off[0] == 0 and np.array_equal(np.diff(off), cnt)
+        assert np.array_equal(cnt, H[:, dest << B:(dest + 1) << B].sum(axis=0))
+        for p in range(1 << B):
+            q = (dest << B) | p
+            at = off[p]
+            for r in range(G):
+                assert cur[r][q] == at
+                at += H[r, q]
+            assert at == off[p + 1]

@@ -392,6 +392,146 @@ def test_peer_store_scatter_into_local_buffers(gj, orc, eng, torch_cuda):
         assert c[g] == cnt[g] == c_all[g] and h[g] == h_all[g] and c.sum() == c[g]
 
 
+# ------------------------------------------------------------------------------- sharded "partition, then push"
+def _pp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, opts=None, check_layout=True):
+    """Runs the gj_pp_* pipeline with G virtual ranks on ONE GPU (one engine context per rank, every
+    'peer' buffer local): same kernels, same cursor arithmetic, same call sequence as over NVLink;
+    the all-gather of the fine histograms is a torch.stack."""
+    rels = [(Rk, Rp), (Sk, Sp)]
+    n = [len(Rk), len(Sk)]
+    if splits is None:
+        splits = [np.linspace(0, n[w], G + 1).astype(np.int64) for w in range(2)]
+    shard_n = [[int(splits[w][r + 1] - splits[w][r]) for r in range(G)] for w in range(2)]
+    nq = G << B
+    mask = nq - 1
+    # worst destination decides the buffer size (all ranks must agree on it)
+    caps = []
+    for w in range(2):
+        d = ((rels[w][0].view(np.uint32) >> B) & (G - 1)) if n[w] else np.zeros(0, dtype=np.int64)
+        caps.append(int(max(np.bincount(d, minlength=G).max() if n[w] else 0, 1) * slack) + 64)
+    engs = [gj.JoinEngine(max(max(shard_n[0]), 1), max(max(shard_n[1]), 1), 0, **(opts or {})) for _ in range(G)]
+    try:
+        own = [[torch.zeros(caps[w] + 16, dtype=torch.int64, device="cuda") for _ in range(G)] for w in range(2)]
+        cols = [[dev(torch, rels[w][0][splits[w][r]:splits[w][r + 1]], rels[w][1][splits[w][r]:splits[w][r + 1]])
+                 for r in range(G)] for w in range(2)]
+        hist = [[torch.empty(nq, dtype=torch.int32, device="cuda") for _ in range(G)] for w in range(2)]
+        torch.cuda.synchronize()
+        for r in range(G):
+            engs[r].pp_begin(n[0], n[1], G, r, B)
+            for w in range(2):
+                engs[r].pp_local(w, cols[w][r][0], cols[w][r][1], hist[w][r])
+        torch.cuda.synchronize()
+        allh = [torch.stack(hist[w]).contiguous() for w in range(2)]
+        for w in range(2):      # the fine histogram of every shard is exact
+            for r in range(G):
+                k = rels[w][0][splits[w][r]:splits[w][r + 1]].view(np.uint32)
+                assert np.array_equal(hist[w][r].cpu().numpy(), np.bincount(k & mask, minlength=nq))
+        for r in range(G):
+            for w in range(2):
+                engs[r].pp_push(w, allh[w], [t.data_ptr() for t in own[w]], caps[w], shard_n[w][r])
+        torch.cuda.synchronize()
+        if check_layout:
+            for w in range(2):
+                ah = allh[w].cpu().numpy()
+                c_all, h_all = orc.partition_fingerprint(rels[w][0], rels[w][1], 0, G.bit_length() - 1 + B) if n[w] else (None, None)
+                for d in range(G):
+                    _, off, cnt = gj.distributed.pp_layout(ah, d, B)
+                    tot = int(off[-1])
+                    got = own[w][d].cpu().numpy()
+                    assert not got[tot:].any()                    # nothing beyond the received tuples
+                    t = got[:tot].view(np.int32).reshape(-1, 2)
+                    keys = np.ascontiguousarray(t[:, 0])
+                    pid = np.repeat(np.arange(1 << B, dtype=np.int64) + (d << B), cnt)
+                    assert np.array_equal((keys.view(np.uint32) & mask).astype(np.int64), pid)
+                    if tot:
+                        c, h = orc.partition_fingerprint(keys, np.ascontiguousarray(t[:, 1]), 0, G.bit_length() - 1 + B)
+                        sl = slice(d << B, (d + 1) << B)
+                        assert np.array_equal(c[sl], c_all[sl]) and np.array_equal(h[sl], h_all[sl])
+        m = c = 0
+        got_n = [0, 0]
+        for r in range(G):
+            engs[r].pp_join(own[0][r].data_ptr(), own[1][r].data_ptr(), caps[0], caps[1])
+            mm, cc, a, b, ph = engs[r].pp_finish()
+            m += mm
+            c = (c + cc) % 2**64
+            got_n[0] += a
+            got_n[1] += b
+        assert got_n == n
+        return m, c, engs[0].pp_plan()
+    finally:
+        for e in engs:
+            e.close()
+
+
+@pytest.mark.parametrize("G,B", [(1, 6), (2, 7), (4, 9), (8, 8), (8, 13)])
+def test_pp_virtual_shards(gj, orc, torch_cuda, G, B):
+    """gpu bits + local bits <= 16: 8-bit (or smaller) passes."""
+    rng = np.random.default_rng(100 * G + B)
+    nR, nS = 600_000, 1_100_000
+    Rk, Sk = rnd(rng, nR, 0, 1 << 19), rnd(rng, nS, 0, 1 << 19)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    m, c, _ = _pp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp)
+    assert (m, c) == (want.matches, want.checksum)
+
+
+@pytest.mark.parametrize("G,B,p1,out", [(8, 15, 0, 0), (8, 15, 0, 1), (4, 16, 0, 0), (16, 16, 0, 0), (16, 16, 0, 1),
+                                        (2, 12, 4, 0), (2, 12, 4, 1), (8, 11, 6, 1), (8, 14, 10, 0)])
+def test_pp_wide_passes_and_tma_output(gj, orc, torch_cuda, G, B, p1, out):
+    """9- and 10-bit passes (512 / 1024-way tiles), explicit first-pass bits, TMA bulk-store runs;
+    signed keys, N:M matches, ragged shards (one of them empty)."""
+    rng = np.random.default_rng(7 * G + B + p1 + out)
+    nR, nS = 1_500_000, 2_500_000
+    Rk = rnd(rng, nR, -(1 << 21), 1 << 21)
+    Sk = rnd(rng, nS, -(1 << 21), 1 << 21)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    splits = []
+    for n in (nR, nS):
+        cuts = np.sort(rng.integers(0, n, size=G - 1)) if G > 1 else np.zeros(0, dtype=np.int64)
+        if G > 2:
+            cuts[1] = cuts[0]                   # an empty shard
+        splits.append(np.concatenate(([0], cuts, [n])).astype(np.int64))
+    opts = {"pp_out": out}
+    if p1:
+        opts["pass1_bits"] = p1
+    m, c, plan = _pp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, splits=splits, opts=opts)
+    assert (m, c) == (want.matches, want.checksum)
+    g = G.bit_length() - 1
+    assert sum(plan) == g + B and plan[0] >= g and max(plan) <= 10
+    if p1:
+        assert plan[0] == max(p1, g)
+
+
+def test_pp_skew_and_empty_relation(gj, orc, torch_cuda):
+    """Zipf-like probe side (one destination and one partition far heavier than the rest) and an
+    empty relation."""
+    rng = np.random.default_rng(5)
+    nR, nS, G, B = 400_000, 1_600_000, 4, 8
+    Rk = rng.permutation(nR).astype(np.int32)
+    hot = rng.integers(0, 50, size=nS // 2)
+    Sk = np.concatenate((hot, rng.integers(0, nR, size=nS - nS // 2))).astype(np.int32)
+    rng.shuffle(Sk)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    m, c, _ = _pp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, slack=1.2)
+    assert (m, c) == (want.matches, want.checksum)
+    e = np.zeros(0, dtype=np.int32)
+    assert _pp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, e, e)[:2] == (0, 0)
+    assert _pp_virtual(gj, orc, torch_cuda, G, B, e, e, Sk, Sp)[:2] == (0, 0)
+
+
+def test_pp_destination_overflow_is_reported(gj, orc, torch_cuda):
+    """A destination that would receive more than its buffer holds: nothing is pushed anywhere and
+    gj_pp_finish fails (every rank computes the same totals from the gathered histograms)."""
+    rng = np.random.default_rng(9)
+    n, G, B = 300_000, 4, 8
+    k = (rng.integers(0, 1 << 8, size=n) | (2 << 8)).astype(np.int32)     # every key goes to GPU 2
+    p = rnd(rng, n, -2**31, 2**31)
+    with pytest.raises(gj.GJError):
+        _pp_virtual(gj, orc, torch_cuda, G, B, k, p, k, p, slack=0.5, check_layout=False)
+
+
 # ------------------------------------------------------------------------------- device generator
 def test_device_generator_is_the_host_bijection(gj, orc, eng, torch_cuda):
     n = 1_000_003

@@ -1,5 +1,6 @@
 """Multi-GPU parity (needs >= 2 GPUs on the box; `gpurun --gpus N`): the radix-sharded join with
-both shuffle variants (NCCL all-to-all, fused peer-store scatter over NVLink) against the oracle's
+every shuffle variant (NCCL all-to-all, fused peer-store scatter over NVLink, copy-engine transfers,
+and the default "partition, then push" pipeline whose last radix pass stores into the peers) against the oracle's
 closed form for the device-generated unique relations."""
 import os
 import socket
@@ -48,7 +49,7 @@ def _worker(rank, world, port, n_local, mode, overlap, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,overlap", [("nccl", False), ("p2p", False), ("p2p", True), ("dma", True)])
+@pytest.mark.parametrize("mode,overlap", [("nccl", False), ("p2p", False), ("p2p", True), ("dma", True), ("pp", True)])
 def test_sharded_join_on_real_gpus(mode, overlap):
     import torch
     import torch.multiprocessing as mp
