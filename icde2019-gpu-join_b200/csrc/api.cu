@@ -91,6 +91,17 @@ static const PPCfg kPPPush[2][3] = {   // [8-byte stores | TMA bulk stores][max(
       { 512, 16, 1, 512, scatter_kernel<512, 16, 1, 1, false, 2, false, 512, true> },
       { 1024, 8, 1, 1024, scatter_kernel<1024, 8, 1, 1, false, 1, false, 1024, true> } },
 };
+// 16 K-tuple tiles (one 1024-thread CTA per SM): twice / four times longer runs per destination
+// partition -- NVLink moves long runs far better than short ones (2 GPUs, TMA stores: 128 B runs
+// 422 GB/s, 16 KB runs 689 GB/s)
+static const PPCfg kPPPushBig[2][3] = {
+    { { 1024, 16, 0, 256, scatter_kernel<1024, 16, 1, 0, false, 1, false, 256, true> },
+      { 1024, 16, 0, 512, scatter_kernel<1024, 16, 1, 0, false, 1, false, 512, true> },
+      { 1024, 16, 0, 1024, scatter_kernel<1024, 16, 1, 0, false, 1, false, 1024, true> } },
+    { { 1024, 16, 1, 256, scatter_kernel<1024, 16, 1, 1, false, 1, false, 256, true> },
+      { 1024, 16, 1, 512, scatter_kernel<1024, 16, 1, 1, false, 1, false, 512, true> },
+      { 1024, 16, 1, 1024, scatter_kernel<1024, 16, 1, 1, false, 1, false, 1024, true> } },
+};
 constexpr uint32_t PP_MAX_PASS_BITS = 10;
 constexpr uint32_t PP_MAX_BITS = 2 * PP_MAX_PASS_BITS;
 
@@ -176,7 +187,7 @@ struct gj_ctx {
     // sharded "partition, then push" pipeline (gj_pp_*), allocated on first use
     struct PP {
         bool active = false;
-        uint32_t G = 0, rank = 0, g = 0, B = 0, Btot = 0, b1 = 0, b2 = 0, out = 0;
+        uint32_t G = 0, rank = 0, g = 0, B = 0, Btot = 0, b1 = 0, b2 = 0, out = 0, big = 0;
         int role_of_side[2] = {0, 1};
         uint64_t n_glob[2] = {0, 0};
         unsigned char* block = nullptr;
@@ -204,7 +215,7 @@ struct gj_ctx {
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
-            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 0;
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1;
     bool attrs_set = false;
 };
 
@@ -231,6 +242,8 @@ static int set_func_attrs(gj_ctx* ctx) {
     }
     for (const PPCfg& c : kPPFirst) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (const auto& row : kPPPush)
+        for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
+    for (const auto& row : kPPPushBig)
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (int i = 0; i < kNumJoin; ++i) {
         CK(cudaFuncSetAttribute(kJoin[i].agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_agg));
@@ -387,7 +400,7 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
         {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
         {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
         {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
-        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out},
+        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k},
     };
     for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
     return nullptr;
@@ -409,6 +422,7 @@ extern "C" int gj_set_option(gj_ctx* ctx, const char* name, int64_t v) {
     if (p == &ctx->opt_radix_bits && v > MAX3_RADIX_BITS) return fail(GJ_ERR_ARG, "radix_bits <= %d", (int)MAX3_RADIX_BITS);
     if (p == &ctx->opt_pass1_bits && v > PP_MAX_PASS_BITS) return fail(GJ_ERR_ARG, "pass1_bits <= %d", (int)PP_MAX_PASS_BITS);
     if (p == &ctx->opt_pp_out && v > 1) return fail(GJ_ERR_ARG, "pp_out is 0 (8-byte stores) or 1 (TMA bulk stores)");
+    if (p == &ctx->opt_pp_tile16k && v > 1) return fail(GJ_ERR_ARG, "pp_tile16k is 0 or 1");
     if (p == &ctx->opt_unit && v && v < 1024) return fail(GJ_ERR_ARG, "unit_tuples >= 1024");
     if (p == &ctx->opt_gpu_bits && v > 8) return fail(GJ_ERR_ARG, "gpu_bits <= 8");
     if (p == &ctx->opt_part_target && v < 32) return fail(GJ_ERR_ARG, "part_target >= 32");
@@ -488,6 +502,12 @@ static const ScatterCfg& scatter_cfg2(const gj_ctx* ctx, uint32_t b2) {
     return kScatter[ctx->opt_scatter_cfg2 == 255 ? (b2 <= 7 ? 4 : 6) : ctx->opt_scatter_cfg2];
 }
 
+// peer-store shuffle: TMA bulk stores of the (long) per-destination runs -- measured over NVLink on
+// 2 GPUs: 689 GB/s against 581 GB/s with 8-byte stores
+static const ScatterCfg& scatter_cfg_shuffle(const gj_ctx* ctx) {
+    return kScatter[ctx->opt_scatter_cfg1 == 255 ? 4 : ctx->opt_scatter_cfg1];
+}
+
 static uint32_t unit_tuples(const gj_ctx* ctx) { return ctx->opt_unit ? (uint32_t)ctx->opt_unit : 8192u; }
 
 // scan of the fine histogram(s) of roles [first, first+nrel) and, for a join, of the unit counts
@@ -497,11 +517,11 @@ static int enqueue_scan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, u
     for (uint32_t r = 0; r < 2; ++r) {
         const RelMeta& m = ctx->meta[r < nrel ? first + (int)r : first];
         a.seq[r].in = m.ghist; a.seq[r].in2 = nullptr; a.seq[r].out = m.off; a.seq[r].desc = m.desc; a.seq[r].ticket = m.ticket;
-        a.seq[r].mode = SCAN_PLAIN; a.seq[r].param = 0;
+        a.seq[r].mode = SCAN_PLAIN; a.seq[r].param = 0; a.seq[r].param2 = 0;
     }
     a.seq[2].in = ctx->meta[0].ghist; a.seq[2].in2 = ctx->meta[1].ghist; a.seq[2].out = ctx->unit_base;
     a.seq[2].desc = ctx->unit_desc; a.seq[2].ticket = ctx->unit_ticket;
-    a.seq[2].mode = SCAN_UNITS; a.seq[2].param = unit_tuples(ctx);
+    a.seq[2].mode = SCAN_UNITS; a.seq[2].param = unit_tuples(ctx); a.seq[2].param2 = 0;
     a.nb = nb;
     a.seq_base = nrel == 0 ? 2 : 0;   // nrel == 0: unit sequence only
     dim3 grid((nb + SCAN_TILE - 1) / SCAN_TILE, nrel == 0 ? 1 : (with_units ? 3 : nrel));
@@ -696,11 +716,11 @@ static int enqueue_partition3(gj_ctx* ctx, cudaStream_t s, const Rel& rel, int r
     int rc;
     ScanSeq so;
     so.in = q.ghist3[role]; so.in2 = nullptr; so.out = q.off3[role]; so.desc = q.desc[role]; so.ticket = q.ticket[role];
-    so.mode = SCAN_PLAIN; so.param = 0;
+    so.mode = SCAN_PLAIN; so.param = 0; so.param2 = 0;
     if ((rc = enqueue_scan_one(ctx, s, so, nb3))) return rc;
     ScanSeq st;
     st.in = m.off; st.in2 = nullptr; st.out = q.tile_prefix[role]; st.desc = q.desc[3 + role]; st.ticket = q.ticket[3 + role];
-    st.mode = SCAN_TILES; st.param = T2;
+    st.mode = SCAN_TILES; st.param = T2; st.param2 = 0;
     if ((rc = enqueue_scan_one(ctx, s, st, FINE_MAX))) return rc;
     tiles3_kernel<<<FINE_MAX / 256, 256, 0, s>>>(m.off, q.tile_prefix[role], FINE_MAX, T2, pl.b3, q.tiles[role]);
     LAUNCHED();
@@ -723,7 +743,7 @@ static int enqueue_units3(gj_ctx* ctx, cudaStream_t s, const Plan& pl) {
     const uint32_t nb3 = 1u << pl.B;
     ScanSeq su;
     su.in = q.ghist3[0]; su.in2 = q.ghist3[1]; su.out = q.unit_base; su.desc = q.desc[2]; su.ticket = q.ticket[2];
-    su.mode = SCAN_UNITS; su.param = unit_tuples(ctx);
+    su.mode = SCAN_UNITS; su.param = unit_tuples(ctx); su.param2 = 0;
     int rc;
     if ((rc = enqueue_scan_one(ctx, s, su, nb3))) return rc;
     PlanArgs a;
@@ -1073,7 +1093,7 @@ extern "C" int gj_shuffle_scatter_peers(gj_ctx* ctx, const int32_t* d_keys, cons
     CK(cudaMemcpyAsync(ctx->meta[0].cur2, cur, n_gpus * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_dst_bases, d_peer_bases, n_gpus * sizeof(void*), cudaMemcpyHostToDevice, s));
     if (n) {
-        const ScatterCfg& c1 = scatter_cfg1(ctx);
+        const ScatterCfg& c1 = scatter_cfg_shuffle(ctx);
         const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
         ScatterArgs a;
         memset(&a, 0, sizeof(a));
@@ -1124,7 +1144,7 @@ extern "C" int gj_shuffle_scatter_peers_async(gj_ctx* ctx, int which, const int3
     CK(cudaMemcpyAsync(ctx->shuf_bases[which], hbase, n_gpus * sizeof(void*), cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(ctx->sev[which][0], s));
     if (n) {
-        const ScatterCfg& c1 = scatter_cfg1(ctx);
+        const ScatterCfg& c1 = scatter_cfg_shuffle(ctx);
         const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
         ScatterArgs a;
         memset(&a, 0, sizeof(a));
@@ -1266,8 +1286,11 @@ static int ensure_pp(gj_ctx* ctx) {
     return GJ_OK;
 }
 
-static const PPCfg& pp_first_cfg(uint32_t bits) { return kPPFirst[std::max(bits, 8u) - 8u]; }
-static const PPCfg& pp_push_cfg(const gj_ctx* ctx, uint32_t bits) { return kPPPush[ctx->pp.out ? 1 : 0][std::max(bits, 8u) - 8u]; }
+static const PPCfg& pp_first_cfg(uint32_t bits) { return kPPFirst[bits > 8u ? bits - 8u : 0u]; }
+static const PPCfg& pp_push_cfg(const gj_ctx* ctx, uint32_t bits) {
+    const uint32_t i = bits > 8u ? bits - 8u : 0u;
+    return (ctx->pp.big ? kPPPushBig : kPPPush)[ctx->pp.out ? 1 : 0][i];
+}
 
 extern "C" int gj_pp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
                            uint32_t local_bits, void* cuda_stream) {
@@ -1285,12 +1308,13 @@ extern "C" int gj_pp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global
     gj_ctx::PP& q = ctx->pp;
     q.G = n_gpus; q.rank = rank; q.g = g; q.B = local_bits; q.Btot = Btot;
     // the first pass must cover the GPU bits (a first-pass partition belongs to ONE destination)
-    uint32_t b1 = ctx->opt_pass1_bits ? (uint32_t)ctx->opt_pass1_bits : Btot / 2;
+    // default: the pushing pass gets the smaller half -- its runs (tile / 2^b2 tuples) cross NVLink
+    uint32_t b1 = ctx->opt_pass1_bits ? (uint32_t)ctx->opt_pass1_bits : (Btot + 1) / 2;
     b1 = std::max(b1, std::max(g, 1u));
     if (Btot - b1 > PP_MAX_PASS_BITS) b1 = Btot - PP_MAX_PASS_BITS;
     b1 = std::min(b1, std::min(PP_MAX_PASS_BITS, Btot - 1));
     if (b1 < g) return fail(GJ_ERR_ARG, "%u GPU bits do not fit the first pass", g);
-    q.b1 = b1; q.b2 = Btot - b1; q.out = (uint32_t)ctx->opt_pp_out;
+    q.b1 = b1; q.b2 = Btot - b1; q.out = (uint32_t)ctx->opt_pp_out; q.big = (uint32_t)ctx->opt_pp_tile16k;
     const bool swap = n_R_global > n_S_global;   // build on the smaller relation -- same choice on every rank
     q.role_of_side[0] = swap ? 1 : 0;
     q.role_of_side[1] = swap ? 0 : 1;
@@ -1343,8 +1367,10 @@ extern "C" int gj_pp_local(gj_ctx* ctx, int which, const int32_t* d_keys, const 
     ScanSeq st;
     st.in = m.off; st.in2 = nullptr; st.out = q.tile_prefix[which]; st.desc = q.tdesc[which]; st.ticket = q.tticket[which];
     st.mode = SCAN_TILES; st.param = T2;
+    const uint32_t perm = q.g ? ((q.b1 << 8) | q.g) : 0u;   // destination-interleaved partition order
+    st.param2 = perm;
     if ((rc = enqueue_scan_one(ctx, s, st, n1))) return rc;
-    tiles3_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(m.off, q.tile_prefix[which], n1, T2, q.b2, m.tiles);
+    tiles3_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(m.off, q.tile_prefix[which], n1, T2, q.b2, m.tiles, perm);
     LAUNCHED();
     if (n) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>(n / T2 + n1 + 2, (uint64_t)ctx->sm_count * 8);

@@ -205,6 +205,7 @@ struct ScanSeq {
     uint32_t* ticket;             // zeroed
     uint32_t mode;                // SCAN_*
     uint32_t param;               // UNITS: probe tuples per unit; TILES: tuples per scatter tile
+    uint32_t param2;              // TILES: parent order (tile_perm), 0 = identity
 };
 struct ScanArgs {
     ScanSeq seq[3];
@@ -214,6 +215,16 @@ struct ScanArgs {
 
 __device__ __forceinline__ uint32_t units_of(uint32_t n_bld, uint32_t n_prb, uint32_t unit) {
     return (n_bld && n_prb) ? (n_prb + unit - 1) / unit : 0u;
+}
+// Order in which the pushing pass of the sharded pipeline visits its first-pass partitions: the
+// top g bits of a partition id name the destination GPU, so position k takes partition
+// (k mod 2^g, k div 2^g) -- consecutive positions go to different destinations (no NVLink ingress
+// hot spot) while all tiles of one partition stay adjacent (their runs complete cache lines in L2
+// together).  pm = (b1 << 8) | g, 0 = identity.
+__host__ __device__ __forceinline__ uint32_t tile_perm(uint32_t k, uint32_t pm) {
+    if (!pm) return k;
+    const uint32_t g = pm & 0xFFu, b1 = pm >> 8;
+    return ((k & ((1u << g) - 1u)) << (b1 - g)) | (k >> g);
 }
 // scatter tiles of a parent partition [lo, hi): tiles start on even slots
 __device__ __forceinline__ uint32_t tiles_of(uint32_t lo, uint32_t hi, uint32_t tile) {
@@ -238,7 +249,7 @@ scan_lookback_kernel(ScanArgs a) {
         if (base + j < a.nb) {
             if (r.mode == SCAN_PLAIN) v[j] = r.in[base + j];
             else if (r.mode == SCAN_UNITS) v[j] = units_of(r.in[base + j], r.in2[base + j], r.param);
-            else v[j] = tiles_of(r.in[base + j], r.in[base + j + 1], r.param);
+            else { const uint32_t c = tile_perm(base + j, r.param2); v[j] = tiles_of(r.in[c], r.in[c + 1], r.param); }
         }
         tsum += v[j];
     }
@@ -413,10 +424,11 @@ sub_hist_kernel(const tup_t* __restrict__ data, const uint32_t* __restrict__ off
 
 __global__ void __launch_bounds__(256)
 tiles3_kernel(const uint32_t* __restrict__ off2, const uint32_t* __restrict__ tile_prefix, uint32_t nparents,
-              uint32_t tile, uint32_t b3, uint4* __restrict__ tiles) {
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nparents; p += gridDim.x * blockDim.x) {
+              uint32_t tile, uint32_t b3, uint4* __restrict__ tiles, uint32_t perm = 0) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nparents; k += gridDim.x * blockDim.x) {
+        const uint32_t p = tile_perm(k, perm);     // tile_prefix is indexed by position, offsets by partition
         const uint32_t lo = off2[p], hi = off2[p + 1];
-        uint32_t at = tile_prefix[p];
+        uint32_t at = tile_prefix[k];
         for (uint32_t a0 = lo & ~1u; hi > lo && a0 < hi; a0 += tile)
             tiles[at++] = make_uint4(a0, max(a0, lo), min(a0 + tile, hi), p << b3);
     }
@@ -450,13 +462,25 @@ subhist_tiles_kernel(const tup_t* __restrict__ data, const uint4* __restrict__ t
         const uint32_t a0 = td.x, lo = td.y, hi = td.z;
         const uint4* v = reinterpret_cast<const uint4*>(data + a0);   // a0 even, buffer 16-byte aligned
         const bool full = (lo == a0) && (hi - a0 == tile_tuples);
-        for (uint32_t pi = threadIdx.x; 2u * pi < tile_tuples; pi += THREADS) {
+        const uint32_t npairs = tile_tuples >> 1;
+        uint32_t pi = threadIdx.x;
+        if (full) {   // four independent 16-byte loads in flight per thread
+            for (; pi + 3u * THREADS < npairs; pi += 4u * THREADS) {
+                const uint4 x0 = __ldg(v + pi), x1 = __ldg(v + pi + THREADS), x2 = __ldg(v + pi + 2 * THREADS),
+                            x3 = __ldg(v + pi + 3 * THREADS);
+                atomicAdd(&sh[x0.x & mask], 1u); atomicAdd(&sh[x0.z & mask], 1u);
+                atomicAdd(&sh[x1.x & mask], 1u); atomicAdd(&sh[x1.z & mask], 1u);
+                atomicAdd(&sh[x2.x & mask], 1u); atomicAdd(&sh[x2.z & mask], 1u);
+                atomicAdd(&sh[x3.x & mask], 1u); atomicAdd(&sh[x3.z & mask], 1u);
+            }
+        }
+        for (; pi < npairs; pi += THREADS) {
             const uint32_t s0 = a0 + 2u * pi;
             if (full || (s0 >= lo && s0 + 1u < hi)) {
                 const uint4 x = __ldg(v + pi);
                 atomicAdd(&sh[x.x & mask], 1u);
                 atomicAdd(&sh[x.z & mask], 1u);
-            } else {
+            } else {   // tile edge: never touch a tuple outside [lo, hi)
                 if (s0 >= lo && s0 < hi) atomicAdd(&sh[__ldg(data + s0).x & mask], 1u);
                 if (s0 + 1u >= lo && s0 + 1u < hi) atomicAdd(&sh[__ldg(data + s0 + 1u).x & mask], 1u);
             }
@@ -570,18 +594,12 @@ struct ScatterArgs {
     const uint32_t* num_tiles;   // pass 2 only
     // PUSH (last pass of the sharded "partition, then push" pipeline): the output base is chosen
     // per TILE -- the tile's first-pass partition belongs to one destination GPU, whose final
-    // partition buffer (local or mapped over NVLink) receives the runs -- and tiles are taken in
-    // an order that spreads consecutive CTAs over all destinations.
+    // partition buffer (local or mapped over NVLink) receives the runs.
     tup_t* const* part_bases;    // [n_dest] final partition buffers
     uint32_t part_shift;         // destination = cursor base >> part_shift
     uint32_t n_dest;
     const uint32_t* abort_flag;  // non-zero: a destination would overflow, nothing is written
 };
-
-__device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b) {
-    while (b) { const uint32_t t = a % b; a = b; b = t; }
-    return a;
-}
 
 template <int THREADS, int IPT, int MODE, int OUT, bool COLUMNAR, int MINB, bool PERSIST = false, int NBT = NB_MAX, bool PUSH = false>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -604,15 +622,9 @@ scatter_kernel(ScatterArgs a) {
     // -- the multi-GPU peer scatter can leave SM resources to concurrently running kernels.  (As a
     // run-time loop in every variant it cost the one-tile launches ~1.5 %, hence the template.)
     const uint32_t ntiles_total = (a.tiles == nullptr) ? a.ntiles : *a.num_tiles;
-    uint32_t first_tile = blockIdx.x;
-    if (PUSH) {
-        // tiles are sorted by destination; CTA b takes tile (b * stride) mod N with stride ~ N / n_dest
-        // coprime to N: a bijection under which any window of resident CTAs covers all destinations
-        // in proportion to their share (no NVLink ingress hot spot, whatever the skew)
+    const uint32_t first_tile = blockIdx.x;
+    if (PUSH) {   // (the tile list is already ordered destination-interleaved, see tile_perm)
         if (blockIdx.x >= ntiles_total || *a.abort_flag) return;
-        uint32_t stride = ntiles_total / a.n_dest + 1u;
-        while (gcd_u32(stride, ntiles_total) != 1u) ++stride;
-        first_tile = (uint32_t)(((unsigned long long)blockIdx.x * stride) % ntiles_total);
     }
     for (uint32_t tile_id = first_tile; tile_id < ntiles_total; tile_id += gridDim.x) {
     // ---- which slots does this tile cover ----

@@ -243,6 +243,10 @@ class GpuOps:
         caps = (self.cap_R, self.cap_S)
         for which, (k, p) in enumerate(rels):
             eng.pp_local(which, k, p, self._pp_hist[which], streams[which])
+            if which == 0:       # S's local pass starts when R's is done: it then runs under R's push
+                local_done = torch.cuda.Event()
+                local_done.record(streams[0])
+                streams[1].wait_event(local_done)
             with torch.cuda.stream(streams[which]):
                 dist.all_gather_into_tensor(self._pp_all[which], self._pp_hist[which], group=group)
         pushed = None

@@ -79,7 +79,7 @@ int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
  *   "join_cfg"     join kernel shape variant (0 = default)
  *   "gpu_bits"     number of key bits above the radix field consumed by the multi-GPU shuffle
  *   "shuffle_grid" persistent CTA count of the peer-store scatter (0 = one tile per CTA)
- *   "pp_out"       sharded pipeline: pushed runs leave the SM as 8-byte stores (0) or TMA bulk stores (1) */
+ *   "pp_out", "pp_tile16k"  sharded pipeline, see gj_pp_begin */
 int gj_set_option(gj_ctx* ctx, const char* name, int64_t value);
 int gj_get_option(gj_ctx* ctx, const char* name, int64_t* value);
 
@@ -188,8 +188,10 @@ int gj_stage_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum);
  *   gj_pp_finish synchronises; returns the local aggregate, the tuples this GPU received and
  *                (phase_ms[5], optional) the device time of local R, push R, local S, push S, join.
  * gj_pp_finish fails with GJ_ERR_ARG when some destination would have overflowed cap_tuples (then
- * nothing was pushed on any rank).  Options: "pass1_bits" (first-pass bits, 0 = half of the field),
- * "pp_out" (0 = 8-byte stores, 1 = TMA bulk stores for the pushed runs). */
+ * nothing was pushed on any rank).  Options: "pass1_bits" (first-pass bits, 0 = the larger half of
+ * the field), "pp_out" (pushed runs leave the SM as 8-byte stores (0) or TMA bulk stores (1,
+ * default)), "pp_tile16k" (16 K-tuple push tiles (1, default) or 4-8 K (0): longer runs cross
+ * NVLink faster). */
 int gj_pp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
                 uint32_t local_bits, void* cuda_stream);
 int gj_pp_local(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays, uint64_t n,

@@ -475,12 +475,14 @@ def test_pp_virtual_shards(gj, orc, torch_cuda, G, B):
     assert (m, c) == (want.matches, want.checksum)
 
 
-@pytest.mark.parametrize("G,B,p1,out", [(8, 15, 0, 0), (8, 15, 0, 1), (4, 16, 0, 0), (16, 16, 0, 0), (16, 16, 0, 1),
-                                        (2, 12, 4, 0), (2, 12, 4, 1), (8, 11, 6, 1), (8, 14, 10, 0)])
-def test_pp_wide_passes_and_tma_output(gj, orc, torch_cuda, G, B, p1, out):
-    """9- and 10-bit passes (512 / 1024-way tiles), explicit first-pass bits, TMA bulk-store runs;
+@pytest.mark.parametrize("G,B,p1,out,big", [(8, 15, 0, 0, 0), (8, 15, 0, 1, 0), (4, 16, 0, 0, 0), (16, 16, 0, 0, 0), (16, 16, 0, 1, 0),
+                                            (2, 12, 4, 0, 0), (2, 12, 4, 1, 0), (8, 11, 6, 1, 0), (8, 14, 10, 0, 0),
+                                            (8, 15, 0, 1, 1), (8, 15, 10, 0, 1), (16, 16, 0, 1, 1), (16, 16, 0, 0, 1), (2, 9, 0, 1, 1)])
+def test_pp_wide_passes_and_tma_output(gj, orc, torch_cuda, G, B, p1, out, big):
+    """9- and 10-bit passes (512 / 1024-way tiles), explicit first-pass bits, 8-byte-store and TMA
+    bulk-store runs, 8 K and 16 K-tuple push tiles;
     signed keys, N:M matches, ragged shards (one of them empty)."""
-    rng = np.random.default_rng(7 * G + B + p1 + out)
+    rng = np.random.default_rng(7 * G + B + p1 + out + 3 * big)
     nR, nS = 1_500_000, 2_500_000
     Rk = rnd(rng, nR, -(1 << 21), 1 << 21)
     Sk = rnd(rng, nS, -(1 << 21), 1 << 21)
@@ -492,7 +494,7 @@ def test_pp_wide_passes_and_tma_output(gj, orc, torch_cuda, G, B, p1, out):
         if G > 2:
             cuts[1] = cuts[0]                   # an empty shard
         splits.append(np.concatenate(([0], cuts, [n])).astype(np.int64))
-    opts = {"pp_out": out}
+    opts = {"pp_out": out, "pp_tile16k": big}
     if p1:
         opts["pass1_bits"] = p1
     m, c, plan = _pp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, splits=splits, opts=opts)

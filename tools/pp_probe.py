@@ -35,14 +35,15 @@ def main():
     allh = [torch.zeros(G * nq, dtype=torch.int32, device="cuda") for _ in range(2)]
     torch.cuda.synchronize()
     for p1 in ([0] + [b for b in range(max(g, (g + B) - 10), min(10, g + B - 1) + 1)]):
-        for out in (0, 1):
+        for out, big in ((0, 0), (1, 0), (1, 1)):
             eng.set_option("pass1_bits", p1)
-            eng.set_option("pp_out", out)
+            eng.set_option("pp_out", out); eng.set_option("pp_tile16k", big)
             best = None
             for _ in range(args.reps):
                 eng.pp_begin(N, N, G, 0, B)
                 for w in range(2):
                     eng.pp_local(w, cols[2 * w], cols[2 * w + 1], hist[w])
+                    torch.cuda.synchronize()                          # the engine runs on its own stream
                     allh[w][:nq].copy_(hist[w])                       # only rank 0 contributes
                     torch.cuda.synchronize()
                     eng.pp_push(w, allh[w], [t.data_ptr() for t in own[w]], cap, n)
@@ -54,7 +55,7 @@ def main():
             b1, b2 = eng.pp_plan()
             ph = best[1]
             gbs = lambda ms, bytes_per: bytes_per * n / (ms * 1e-3) / 1e9  # noqa: E731
-            print(json.dumps({"b1": b1, "b2": b2, "out": out, **{k: round(v, 3) for k, v in ph.items()},
+            print(json.dumps({"b1": b1, "b2": b2, "out": out, "big": big, **{k: round(v, 3) for k, v in ph.items()},
                               "local_GBs(4+16+8 B/tuple)": round(gbs(ph["local_R_ms"], 28), 1),
                               "push_GBs(16 B/tuple)": round(gbs(ph["push_R_ms"], 16), 1),
                               "check(matches,recvR,recvS)": best[2]}), flush=True)
