@@ -427,6 +427,10 @@ def multi_gpu(args):
     nR, nS, kind, z = WORKLOADS[w]
     if kind != "unique":
         raise SystemExit("multi-GPU bench supports the unique-key workloads (B, small, cfg5)")
+    if args.shuffle == "auto":
+        # short pushed runs cross NVLink slower the more destinations share a tile: measured
+        # 2 GPUs 124.8 (pp) vs 111.6 (p2p), 4 GPUs 198.0 vs 192.5, 8 GPUs 315.0 vs 352.8 G tuples/s
+        args.shuffle = "pp" if world <= 4 else "p2p"
     strong = (w == "cfg5")
     if strong:                      # fixed total, per-GPU share shrinks with N
         nR, nS = nR // world, nS // world
@@ -512,6 +516,14 @@ def multi_gpu(args):
                                  "nvlink_peak_GBs": 770.0, "host_ms_rank0": tm.get("host_ms"), "trace_ms_rank0": tm.get("trace_ms"),
                                  "note": "peer-store scatter: one kernel reads the local shard (8 B/tuple HBM) and stores each run into the destination GPU's HBM over NVLink"},
                      "checked": f"matches == checksum == {expect} every step"})
+        if tm.get("pass_ms") and any(tm["pass_ms"][2:]):
+            # the receiver's radix passes over S run alone (R's overlap S's shuffle): 16 B/tuple per launch
+            ps = [x for x in tm["pass_ms"][2:] if x > 0]
+            line["roofline"].update({"kernel": "scatter_kernel (receiver's radix passes over S, rank 0)",
+                                     "achieved": 16.0 * r.local_S / (sum(ps) / len(ps) * 1e-3) / 1e9,
+                                     "algorithmic_bytes_per_launch": 16.0 * r.local_S, "avg_launch_ms": sum(ps) / len(ps),
+                                     "local_phases_ms": {"scatter_R_pass1": tm["pass_ms"][0], "scatter_R_pass2": tm["pass_ms"][1],
+                                                         "scatter_S_pass1": tm["pass_ms"][2], "scatter_S_pass2": tm["pass_ms"][3]}})
         if args.shuffle == "pp" and tm.get("local_R_ms"):
             # dominant HBM-bound kernels of the sharded pipeline: the local phase of one relation =
             # coarse histogram (4 B) + first pass (16 B) + fine counts (8 B) per tuple
@@ -541,7 +553,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--shuffle", default="p2p", choices=["p2p", "nccl", "dma", "pp"])
+    ap.add_argument("--shuffle", default="auto", choices=["auto", "p2p", "nccl", "dma", "pp"],
+                    help="multi-GPU exchange: pp = partition locally, last radix pass pushes into the peers; p2p = peer-store "
+                         "shuffle first, local passes at the receiver; auto = pp up to 4 GPUs, p2p beyond (measured, profiles/README.md)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: shuffle and local passes back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1247,6 +1247,21 @@ extern "C" int gj_stage_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksu
     return GJ_OK;
 }
 
+extern "C" int gj_stage_pass_ms(gj_ctx* ctx, float pass_ms[4]) {
+    if (!ctx || !pass_ms) return fail(GJ_ERR_ARG, "NULL argument");
+    if (ctx->stage.active) return fail(GJ_ERR_STATE, "gj_stage_finish first");
+    for (int i = 0; i < 4; ++i) pass_ms[i] = 0.f;
+    const Plan& pl = ctx->stage.pl;
+    for (int side = 0; side < 2; ++side) {   // [R pass 1, R pass 2, S pass 1, S pass 2]
+        if (!ctx->stage.n_side[side]) continue;
+        const int role = ctx->stage.role_of_side[side];
+        CK(cudaEventSynchronize(ctx->pev[role][pl.b2 ? 2 : 1]));
+        CK(cudaEventElapsedTime(&pass_ms[2 * side], ctx->pev[role][0], ctx->pev[role][1]));
+        if (pl.b2) CK(cudaEventElapsedTime(&pass_ms[2 * side + 1], ctx->pev[role][1], ctx->pev[role][2]));
+    }
+    return GJ_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Sharded "partition, then push" pipeline (multi-GPU; kernels.cuh section 3c).  Per relation:
 //   gj_pp_local : coarse histogram -> scan -> cursors -> pass 1 (local) -> pass-2 tile list ->

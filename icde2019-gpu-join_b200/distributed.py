@@ -162,7 +162,7 @@ class GpuOps:
         m, c = eng.stage_finish()
         sA.synchronize()
         ms = eng.shuffle_scatter_ms(0) + eng.shuffle_scatter_ms(1)
-        out = {"shuffle_scatter_ms": ms}
+        out = {"shuffle_scatter_ms": ms, "pass_ms": eng.stage_pass_ms()}
         if trace is not None:
             out["trace_ms"] = {n: round(trace[0][1].elapsed_time(e), 3) for n, e in trace[1:]}
         return m, c, out
@@ -294,7 +294,7 @@ class ShardedJoin:
     with its local shard (device int32 columns) and all ranks get the global result."""
 
     def __init__(self, max_local_R: int, max_local_S: int, device: int | None = None, group=None,
-                 mode: str = "nccl", ops=None, part_target: int = 4096, overlap: bool = True):
+                 mode: str = "auto", ops=None, part_target: int = 4096, overlap: bool = True):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -303,6 +303,8 @@ class ShardedJoin:
         if self.world & (self.world - 1):
             raise ValueError("world size must be a power of two (GPU id = radix bits)")
         self.gpu_bits = int(math.log2(self.world))
+        if mode == "auto":     # measured on B200 / NVLink 5 (profiles/README.md): pushed runs get shorter
+            mode = "pp" if self.world <= 4 else "p2p"   # with more destinations and cross NVLink slower
         self.mode = mode
         self.overlap = overlap
         self.part_target = part_target

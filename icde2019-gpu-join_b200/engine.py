@@ -22,7 +22,7 @@ C_ABI_SYMBOLS = [
     "gj_get_option", "gj_join_aggregate", "gj_join_aggregate_tuples", "gj_join_aggregate_host",
     "gj_join_materialize", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
-    "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
+    "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_stage_pass_ms", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
     "gj_pp_finish", "gj_pp_plan", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
     "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_device_synchronize", "gj_flush_l2",
@@ -101,6 +101,7 @@ def lib() -> C.CDLL:
     L.gj_stage_partition.argtypes = [vp, C.c_int, vp, vp]
     L.gj_stage_join.argtypes = [vp, vp]
     L.gj_stage_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.gj_stage_pass_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.gj_pp_begin.argtypes = [vp, u64, u64, u32, u32, u32, vp]
     L.gj_pp_local.argtypes = [vp, C.c_int, i32p, i32p, u64, vp, vp]
     L.gj_pp_push.argtypes = [vp, C.c_int, vp, C.POINTER(vp), u64, u64, vp]
@@ -339,6 +340,11 @@ class JoinEngine:
         m, c = C.c_uint64(), C.c_uint64()
         _check(self._L.gj_stage_finish(self._ctx, C.byref(m), C.byref(c)))
         return int(m.value), int(c.value)
+
+    def stage_pass_ms(self):
+        ms = (C.c_float * 4)()
+        _check(self._L.gj_stage_pass_ms(self._ctx, ms))
+        return [float(x) for x in ms]
 
     # -- sharded "partition, then push" pipeline (gj_pp_*) -----------------------------------
     @staticmethod

@@ -169,6 +169,9 @@ int gj_stage_begin(gj_ctx* ctx, uint64_t nR, uint64_t nS, void* cuda_stream);
 int gj_stage_partition(gj_ctx* ctx, int side, const void* d_tuples, void* cuda_stream);
 int gj_stage_join(gj_ctx* ctx, void* cuda_stream);
 int gj_stage_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum);
+/* Durations of the local scatter launches of the last staged join: R pass 1, R pass 2, S pass 1,
+ * S pass 2 (CUDA events on the streams they ran on; 0 where a pass did not run). */
+int gj_stage_pass_ms(gj_ctx* ctx, float pass_ms[4]);
 
 /* ---- sharded "partition, then push" pipeline (multi-GPU, default) -------
  * Radix field = [gpu bits | local bits] (destination = (key >> local_bits) & (n_gpus-1), as above).
