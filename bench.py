@@ -524,6 +524,15 @@ def multi_gpu(args):
                                      "algorithmic_bytes_per_launch": 16.0 * r.local_S, "avg_launch_ms": sum(ps) / len(ps),
                                      "local_phases_ms": {"scatter_R_pass1": tm["pass_ms"][0], "scatter_R_pass2": tm["pass_ms"][1],
                                                          "scatter_S_pass1": tm["pass_ms"][2], "scatter_S_pass2": tm["pass_ms"][3]}})
+        if args.shuffle == "pcp" and tm.get("part_R_ms"):
+            line["roofline"].update({"kernel": "pcp source-side radix pass of R (layout + first pass, 16 B/tuple), rank 0",
+                                     "achieved": 16.0 * nR / (tm["part_R_ms"] * 1e-3) / 1e9, "algorithmic_bytes_per_launch": 16.0 * nR,
+                                     "local_phases_ms": {k: tm.get(k) for k in ("part_R_ms", "copy_R_ms", "recv_R_ms", "part_S_ms", "copy_S_ms", "recv_S_ms", "join_ms")}})
+            line["plan"] = {"gpu_bits": world.bit_length() - 1, "local_bits": tm.get("radix_bits"),
+                            "source_pass_bits": tm.get("pass1_bits"), "receiver_pass_bits": tm.get("pass2_bits")}
+            line["shuffle"]["note"] = ("partition-copy-partition: first radix pass at the source on [gpu | top local bits], whole first-pass "
+                                       "partitions bulk-copied (TMA, global->shared->peer global) into the receiver's layout, last pass + join "
+                                       "at the receiver; scatter_kernel_ms = the copy kernels of R and S")
         if args.shuffle == "pp" and tm.get("local_R_ms"):
             # dominant HBM-bound kernels of the sharded pipeline: the local phase of one relation =
             # coarse histogram (4 B) + first pass (16 B) + fine counts (8 B) per tuple
@@ -540,6 +549,7 @@ def multi_gpu(args):
             line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
         line["config"].update({"global_R": NR, "global_S": NS, "parallelism": f"radix-sharded over {world} GPUs, {args.shuffle} shuffle"
                                + (", R's push overlapped with S's local pass" if args.shuffle == "pp" else
+                                  ", R's copy under S's first pass, S's copy under R's last pass" if args.shuffle == "pcp" else
                                   "" if args.no_overlap or args.shuffle != "p2p" else ", S shuffle overlapped with R's local passes")})
         print(json.dumps(line))
     sj.close()
@@ -553,7 +563,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--shuffle", default="auto", choices=["auto", "p2p", "nccl", "dma", "pp"],
+    ap.add_argument("--shuffle", default="auto", choices=["auto", "p2p", "nccl", "dma", "pp", "pcp"],
                     help="multi-GPU exchange: pp = partition locally, last radix pass pushes into the peers; p2p = peer-store "
                          "shuffle first, local passes at the receiver; auto = pp up to 4 GPUs, p2p beyond (measured, profiles/README.md)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")

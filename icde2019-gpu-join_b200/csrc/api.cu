@@ -102,6 +102,15 @@ static const PPCfg kPPPushBig[2][3] = {
       { 1024, 16, 1, 512, scatter_kernel<1024, 16, 1, 1, false, 1, false, 512, true> },
       { 1024, 16, 1, 1024, scatter_kernel<1024, 16, 1, 1, false, 1, false, 1024, true> } },
 };
+// pcp: last radix pass at the receiver (packed input, tiles from plan_kernel, TMA output)
+static const PPCfg kPcpLast[4] = {
+    { 256, 16, 1, 256, scatter_kernel<256, 16, 1, 1, false, 4> },                      // <= 7 bits (tile 4096, as scatter_cfg2)
+    { 512, 16, 1, 256, scatter_kernel<512, 16, 1, 1, false, 2> },                      // 8 bits
+    { 512, 16, 1, 512, scatter_kernel<512, 16, 1, 1, false, 2, false, 512> },          // 9 bits
+    { 1024, 8, 1, 1024, scatter_kernel<1024, 8, 1, 1, false, 1, false, 1024> },        // 10 bits
+};
+constexpr int PCP_NS = 4;   // ring slots of the copy kernel
+static size_t pcp_copy_smem() { return (size_t)PCP_NS * PCP_PIECE * sizeof(tup_t) + (PCP_MAX_CHUNKS + 4) * sizeof(uint32_t); }
 constexpr uint32_t PP_MAX_PASS_BITS = 10;
 constexpr uint32_t PP_MAX_BITS = 2 * PP_MAX_PASS_BITS;
 
@@ -203,6 +212,19 @@ struct gj_ctx {
         cudaEvent_t ev[2][4] = {};                       // per relation: local begin, local end, push begin, push end
         cudaEvent_t jev[2] = {};                         // join begin, end
     } pp;
+    // sharded "partition, copy, partition" pipeline (gj_pcp_*), allocated on first use
+    struct PCP {
+        bool active = false;
+        uint32_t G = 0, rank = 0, g = 0, B = 0, bl = 0, b1 = 0, b2 = 0;
+        int role_of_side[2] = {0, 1};
+        uint64_t n_glob[2] = {0, 0}, n_loc[2] = {0, 0};
+        unsigned char* block = nullptr;
+        PcpTables tab[2];
+        tup_t** bases[2] = {nullptr, nullptr};
+        unsigned char* h_pin = nullptr;      // pinned: bases staging [2][256 ptrs] + status read-back [2][4]
+        cudaEvent_t ev[2][6] = {};           // per relation: part begin/end, copy begin/end, recv begin/end
+        cudaEvent_t jev[2] = {};
+    } pcp;
     unsigned char* zero_role[2] = {nullptr, nullptr};
     unsigned char* zero_common = nullptr;
     size_t zero_role_bytes = 0, zero_common_bytes = 0;
@@ -243,6 +265,8 @@ static int set_func_attrs(gj_ctx* ctx) {
     for (const PPCfg& c : kPPFirst) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (const auto& row : kPPPush)
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
+    for (const PPCfg& c : kPcpLast) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
+    CK(cudaFuncSetAttribute(pcp_copy_kernel<PCP_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem()));
     for (const auto& row : kPPPushBig)
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (int i = 0; i < kNumJoin; ++i) {
@@ -267,6 +291,10 @@ extern "C" void gj_destroy(gj_ctx* ctx) {
     cudaFree(ctx->d_dst_bases); cudaFree(ctx->flush_buf); cudaFree(ctx->tiles_block);
     cudaFree(ctx->p3.block); cudaFree(ctx->p3.zero);
     cudaFree(ctx->pp.block);
+    cudaFree(ctx->pcp.block);
+    if (ctx->pcp.h_pin) cudaFreeHost(ctx->pcp.h_pin);
+    for (auto& r : ctx->pcp.ev) for (auto& e : r) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->pcp.jev) if (e) cudaEventDestroy(e);
     if (ctx->pp.h_pin) cudaFreeHost(ctx->pp.h_pin);
     for (auto& r : ctx->pp.ev) for (auto& e : r) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->pp.jev) if (e) cudaEventDestroy(e);
@@ -476,18 +504,19 @@ static Plan choose_plan(const gj_ctx* ctx, uint64_t n_build, uint32_t forced_bit
 // enqueue helpers (no host synchronisation inside)
 // ------------------------------------------------------------------------------------------
 static int enqueue_hist(gj_ctx* ctx, cudaStream_t s, const void* in, bool packed, uint64_t n,
-                        uint32_t shift, uint32_t bits, uint32_t* ghist, int threads = 1024) {
+                        uint32_t shift, uint32_t bits, uint32_t* ghist, int threads = 1024,
+                        const uint32_t* n_dev = nullptr) {   // n_dev: the count lives on the device, n is its upper bound
     if (!n) return GJ_OK;
     const uint64_t per_cta = (uint64_t)threads * 16;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count, (n + per_cta - 1) / per_cta));
     const bool p16 = bits > 15;   // two 16-bit counters per word
     const size_t smem = p16 ? (size_t)2 << bits : (size_t)4 << bits;
     if (packed) {
-        if (p16) hist_kernel<true, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
-        else hist_kernel<true, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+        if (p16) hist_kernel<true, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, n_dev);
+        else hist_kernel<true, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, n_dev);
     } else {
-        if (p16) hist_kernel<false, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
-        else hist_kernel<false, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist);
+        if (p16) hist_kernel<false, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, n_dev);
+        else hist_kernel<false, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, n_dev);
     }
     LAUNCHED();
     return GJ_OK;
@@ -1494,6 +1523,248 @@ extern "C" int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bit
     if (!ctx || !ctx->pp.block) return fail(GJ_ERR_STATE, "gj_pp_begin first");
     if (pass1_bits) *pass1_bits = ctx->pp.b1;
     if (pass2_bits) *pass2_bits = ctx->pp.b2;
+    return GJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Sharded "partition, copy, partition" pipeline (multi-GPU; kernels.cuh section 3d).  Per relation:
+//   gj_pcp_hist : this shard's first-pass histogram on [gpu bits | top local bits] (2^b1 counters)
+//   [caller: all-gather of those histograms]
+//   gj_pcp_part : layout (pcp_layout_kernel) + first radix pass into the stage buffer (ctx->out[which])
+//   gj_pcp_copy : TMA bulk-copy kernel: every chunk to its slot in the destination's receive buffer
+//   [caller: cross-rank "all copies have landed" point]
+//   gj_pcp_recv : histogram + scan + plan + LAST radix pass over what this GPU received -> ctx->out[which]
+//   gj_pcp_join / gj_pcp_finish
+// ------------------------------------------------------------------------------------------
+static int ensure_pcp(gj_ctx* ctx) {
+    gj_ctx::PCP& q = ctx->pcp;
+    if (q.block) return GJ_OK;
+    const size_t per = (size_t)(PCP_MAX_CHUNKS + 4) * sizeof(uint32_t);
+    size_t b = 0;
+    size_t o[2][6], o_bs[2];
+    for (int r = 0; r < 2; ++r) {
+        for (int k = 0; k < 6; ++k) { o[r][k] = b; b += per; }
+        o_bs[r] = b; b += NB_MAX * sizeof(tup_t*);
+    }
+    if (cudaMalloc(&q.block, b) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "pcp metadata"); }
+    for (int r = 0; r < 2; ++r) {
+        q.tab[r].cur = reinterpret_cast<uint32_t*>(q.block + o[r][0]);
+        q.tab[r].src_start = reinterpret_cast<uint32_t*>(q.block + o[r][1]);
+        q.tab[r].dst_start = reinterpret_cast<uint32_t*>(q.block + o[r][2]);
+        q.tab[r].cnt = reinterpret_cast<uint32_t*>(q.block + o[r][3]);
+        q.tab[r].piece_prefix = reinterpret_cast<uint32_t*>(q.block + o[r][4]);
+        q.tab[r].status = reinterpret_cast<uint32_t*>(q.block + o[r][5]);
+        q.bases[r] = reinterpret_cast<tup_t**>(q.block + o_bs[r]);
+    }
+    CK(cudaHostAlloc(&q.h_pin, 2 * NB_MAX * sizeof(void*) + 64, cudaHostAllocDefault));
+    for (auto& r : q.ev) for (auto& e : r) CK(cudaEventCreate(&e));
+    for (auto& e : q.jev) CK(cudaEventCreate(&e));
+    return GJ_OK;
+}
+
+static const PPCfg& pcp_last_cfg(uint32_t bits) { return kPcpLast[bits <= 7u ? 0u : bits - 7u]; }
+
+extern "C" int gj_pcp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
+                            uint32_t local_bits, void* cuda_stream) {
+    if (!ctx) return fail(GJ_ERR_ARG, "ctx is NULL");
+    if (n_gpus < 2 || n_gpus > (uint32_t)NB_MAX || (n_gpus & (n_gpus - 1))) return fail(GJ_ERR_ARG, "n_gpus must be a power of two in [2, %d]", NB_MAX);
+    if (rank >= n_gpus) return fail(GJ_ERR_ARG, "rank %u out of range", rank);
+    uint32_t g = 0;
+    while ((1u << g) < n_gpus) ++g;
+    if (local_bits < 1 || local_bits > (uint32_t)MAX_RADIX_BITS) return fail(GJ_ERR_ARG, "local_bits must be in [1, %d]", MAX_RADIX_BITS);
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_pcp(ctx))) return rc;
+    gj_ctx::PCP& q = ctx->pcp;
+    // bl = local bits done at the source (with the GPU bits: b1 = g + bl <= 10), b2 = B - bl at the receiver
+    const uint32_t B = local_bits;
+    uint32_t bl = ctx->opt_pass1_bits ? ((uint32_t)ctx->opt_pass1_bits > g ? (uint32_t)ctx->opt_pass1_bits - g : 0u)
+                                      : (B > g ? (B - g + 1) / 2 : 0u);
+    bl = std::min(bl, std::min(PP_MAX_PASS_BITS - g, B - 1));
+    bl = std::min(bl, (uint32_t)MAX_PASS_BITS);   // the receiver plans its last pass over <= 256 first-pass partitions
+    if (B - bl > PP_MAX_PASS_BITS) bl = B - PP_MAX_PASS_BITS;
+    if (g + bl > PP_MAX_PASS_BITS || bl > (uint32_t)MAX_PASS_BITS) return fail(GJ_ERR_ARG, "%u GPU bits + %u local bits do not fit two passes of <= %u", g, B, PP_MAX_PASS_BITS);
+    q.G = n_gpus; q.rank = rank; q.g = g; q.B = B; q.bl = bl; q.b1 = g + bl; q.b2 = B - bl;
+    const bool swap = n_R_global > n_S_global;
+    q.role_of_side[0] = swap ? 1 : 0;
+    q.role_of_side[1] = swap ? 0 : 1;
+    q.n_glob[0] = n_R_global; q.n_glob[1] = n_S_global;
+    q.active = true;
+    ctx->launches = 0;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaMemsetAsync(ctx->zero_common, 0, ctx->zero_common_bytes, s));
+    CK(cudaEventRecord(ctx->stage_ev[3], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_pcp_plan(gj_ctx* ctx, uint32_t plan_bits[3]) {
+    if (!ctx || !ctx->pcp.block || !plan_bits) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
+    plan_bits[0] = ctx->pcp.g; plan_bits[1] = ctx->pcp.bl; plan_bits[2] = ctx->pcp.b2;
+    return GJ_OK;
+}
+
+extern "C" int gj_pcp_hist(gj_ctx* ctx, int which, const int32_t* d_keys, uint64_t n, uint32_t* d_coarse_hist,
+                           void* cuda_stream) {
+    if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
+    if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
+    if (!d_coarse_hist || (n && !d_keys)) return fail(GJ_ERR_ARG, "NULL argument");
+    gj_ctx::PCP& q = ctx->pcp;
+    // every chunk is staged with one spare slot (16-byte phase matching)
+    if (n + (1ull << q.b1) > (which ? ctx->maxS : ctx->maxR) + 16) return fail(GJ_ERR_ARG, "n + %u spare slots exceed the context capacity", 1u << q.b1);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    q.n_loc[which] = n;
+    CK(cudaMemsetAsync(d_coarse_hist, 0, sizeof(uint32_t) << q.b1, s));
+    CK(cudaMemsetAsync(q.tab[which].status, 0, 4 * sizeof(uint32_t), s));
+    return enqueue_hist(ctx, s, d_keys, false, n, q.B - q.bl, q.b1, d_coarse_hist);
+}
+
+extern "C" int gj_pcp_part(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays,
+                           const uint32_t* d_all_hist, uint64_t cap_tuples, void* cuda_stream) {
+    if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
+    if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
+    gj_ctx::PCP& q = ctx->pcp;
+    const uint64_t n = q.n_loc[which];
+    if (!d_all_hist || (n && (!d_keys || !d_pays))) return fail(GJ_ERR_ARG, "NULL argument");
+    if (cap_tuples > 0xFFFFFFFFull) return fail(GJ_ERR_ARG, "destination capacity exceeds 2^32 tuples");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const uint32_t perm = (q.b1 << 8) | q.g;
+    CK(cudaEventRecord(q.ev[which][0], s));
+    pcp_layout_kernel<<<1, PCP_MAX_CHUNKS, 0, s>>>(d_all_hist, q.G, q.rank, q.b1, q.bl, (uint32_t)cap_tuples, perm, q.tab[which]);
+    LAUNCHED();
+    if (n) {
+        const PPCfg& c1 = pp_first_cfg(q.b1);
+        const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
+        ScatterArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = ctx->out[which];
+        a.shift = q.B - q.bl; a.bits = q.b1; a.cursors = q.tab[which].cur; a.cursor_stride = 1;
+        a.ntiles = (uint32_t)((n + T1 - 1) / T1);
+        c1.fn<<<a.ntiles, c1.threads, pp_smem(c1), s>>>(a);
+        LAUNCHED();
+    }
+    CK(cudaEventRecord(q.ev[which][1], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* cuda_stream) {
+    if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
+    if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
+    if (!peer_bases) return fail(GJ_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    gj_ctx::PCP& q = ctx->pcp;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    void** hb = reinterpret_cast<void**>(q.h_pin) + (size_t)which * NB_MAX;
+    for (uint32_t g = 0; g < q.G; ++g) {
+        if (!peer_bases[g] || ((size_t)peer_bases[g] & 15u)) return fail(GJ_ERR_ARG, "destination buffer %u must be non-NULL and 16-byte aligned", g);
+        hb[g] = peer_bases[g];
+    }
+    CK(cudaMemcpyAsync(q.bases[which], hb, q.G * sizeof(void*), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(q.ev[which][2], s));
+    if (q.n_loc[which]) {
+        PcpCopyArgs a;
+        a.stage = ctx->out[which]; a.peer_bases = q.bases[which]; a.t = q.tab[which];
+        a.b1 = q.b1; a.bl = q.bl; a.perm = (q.b1 << 8) | q.g;
+        const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
+        uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count * 2u;
+        grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));
+        pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
+        LAUNCHED();
+    }
+    CK(cudaEventRecord(q.ev[which][3], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, uint64_t cap_tuples, void* cuda_stream) {
+    if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
+    if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
+    if (!d_own || ((size_t)d_own & 15u)) return fail(GJ_ERR_ARG, "receive buffer must be non-NULL and 16-byte aligned");
+    if (cap_tuples > (which ? ctx->maxS : ctx->maxR)) return fail(GJ_ERR_ARG, "receive capacity exceeds the context capacity");
+    CK(cudaSetDevice(ctx->device));
+    gj_ctx::PCP& q = ctx->pcp;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const int role = q.role_of_side[which];
+    const RelMeta& m = ctx->meta[role];
+    const uint32_t* n_dev = q.tab[which].status + 1;     // tuples this GPU received (pcp_layout_kernel)
+    int rc;
+    CK(cudaEventRecord(q.ev[which][4], s));
+    CK(cudaMemsetAsync(ctx->zero_role[role], 0, ctx->zero_role_bytes, s));
+    if (!q.n_glob[which]) { CK(cudaEventRecord(q.ev[which][5], s)); return GJ_OK; }
+    if ((rc = enqueue_hist(ctx, s, d_own, true, cap_tuples, 0, q.B, m.ghist, 1024, n_dev))) return rc;
+    if ((rc = enqueue_scan(ctx, s, role, 1, 1u << q.B, false))) return rc;
+    const PPCfg& c2 = pcp_last_cfg(q.b2);
+    const uint32_t T2 = (uint32_t)(c2.threads * c2.ipt);
+    {   // cursors + last-pass tile list; the receive buffer IS the first-pass output (bl bits done)
+        PlanArgs a;
+        memset(&a, 0, sizeof(a));
+        a.rel[0].off = m.off; a.rel[0].cur1 = m.cur1; a.rel[0].cur2 = m.cur2; a.rel[0].tiles = m.tiles; a.rel[0].num_tiles = m.num_tiles;
+        a.rel[1] = a.rel[0];
+        a.nrel = 1; a.with_units = 0; a.b1 = q.bl; a.b2 = q.b2; a.tile = T2; a.unit = unit_tuples(ctx);
+        a.unit_base = ctx->unit_base; a.units = ctx->units;
+        const uint32_t nb = 1u << q.B;
+        const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(128, (nb + PLAN_THREADS - 1) / PLAN_THREADS + 32));
+        plan_kernel<<<grid, PLAN_THREADS, 0, s>>>(a);
+        LAUNCHED();
+    }
+    ScatterArgs b;
+    memset(&b, 0, sizeof(b));
+    b.in_tup = (const tup_t*)d_own; b.out = ctx->out[which]; b.n = (uint32_t)cap_tuples;
+    b.shift = 0; b.bits = q.b2;
+    b.cursors = m.cur2; b.cursor_stride = 1; b.tiles = m.tiles; b.num_tiles = m.num_tiles;
+    const uint32_t grid2 = (uint32_t)(cap_tuples / T2) + (1u << q.bl) + 2;   // upper bound on tiles
+    c2.fn<<<grid2, c2.threads, pp_smem(c2), s>>>(b);
+    LAUNCHED();
+    CK(cudaEventRecord(q.ev[which][5], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_pcp_join(gj_ctx* ctx, uint64_t cap_R, uint64_t cap_S, void* cuda_stream) {
+    if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
+    CK(cudaSetDevice(ctx->device));
+    gj_ctx::PCP& q = ctx->pcp;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaStreamWaitEvent(s, ctx->stage_ev[3], 0));
+    Plan pl; pl.B = q.B; pl.b1 = q.B; pl.b2 = 0;
+    const bool r_builds = q.role_of_side[0] == 0;
+    int rc;
+    CK(cudaEventRecord(q.jev[0], s));
+    if (q.n_glob[0] && q.n_glob[1]) {
+        if ((rc = enqueue_scan(ctx, s, 0, 0, 1u << pl.B, true))) return rc;
+        if ((rc = enqueue_plan(ctx, s, 0, 0, pl, true))) return rc;
+        if ((rc = enqueue_join(ctx, s, ctx->out[r_builds ? 0 : 1], ctx->out[r_builds ? 1 : 0], pl, r_builds ? cap_R : cap_S,
+                               r_builds ? cap_S : cap_R, false, nullptr, nullptr, 0, nullptr, (int)q.g))) return rc;
+    }
+    CK(cudaEventRecord(q.jev[1], s));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    uint32_t* hs = reinterpret_cast<uint32_t*>(q.h_pin + 2 * NB_MAX * sizeof(void*));
+    for (int w = 0; w < 2; ++w) CK(cudaMemcpyAsync(hs + 4 * w, q.tab[w].status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[3], s));
+    return GJ_OK;
+}
+
+extern "C" int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
+                             uint64_t* n_local_S, float* phase_ms, uint32_t* plan_bits) {
+    if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
+    gj_ctx::PCP& q = ctx->pcp;
+    CK(cudaEventSynchronize(ctx->ev[3]));
+    q.active = false;
+    const uint32_t* hs = reinterpret_cast<const uint32_t*>(q.h_pin + 2 * NB_MAX * sizeof(void*));
+    if (n_local_R) *n_local_R = hs[1];
+    if (n_local_S) *n_local_S = hs[5];
+    if (plan_bits) { plan_bits[0] = q.g; plan_bits[1] = q.bl; plan_bits[2] = q.b2; }
+    if (hs[0] || hs[4])
+        return fail(GJ_ERR_ARG, "sharded join: a destination GPU would receive more tuples than its buffer holds "
+                                "(this GPU: %u R, %u S tuples) -- raise the receive-buffer slack", hs[1], hs[5]);
+    if (matches) *matches = ctx->h_result[0];
+    if (checksum) *checksum = ctx->h_result[1];
+    if (phase_ms) {   // [part R, copy R, recv R, part S, copy S, recv S, join]
+        for (int w = 0; w < 2; ++w) {
+            CK(cudaEventSynchronize(q.ev[w][5]));
+            for (int k = 0; k < 3; ++k) CK(cudaEventElapsedTime(&phase_ms[3 * w + k], q.ev[w][2 * k], q.ev[w][2 * k + 1]));
+        }
+        CK(cudaEventElapsedTime(&phase_ms[6], q.jev[0], q.jev[1]));
+    }
     return GJ_OK;
 }
 

@@ -71,8 +71,9 @@ __device__ __forceinline__ void hist_add(uint32_t* sh, uint32_t d, uint32_t* ghi
 template <bool PACKED, bool P16>
 __global__ void __launch_bounds__(1024, 1)
 hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bits,
-            uint32_t* __restrict__ ghist) {
+            uint32_t* __restrict__ ghist, const uint32_t* __restrict__ n_dev = nullptr) {
     extern __shared__ uint32_t sh_hist[];
+    if (n_dev) n = *n_dev;   // tuple count produced on the device (sharded pipelines: what this GPU received)
     const uint32_t nb = 1u << bits, mask = nb - 1u;
     const uint32_t nwords = P16 ? nb >> 1 : nb;
     for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) sh_hist[i] = 0;
@@ -556,6 +557,154 @@ pp_cursor_kernel(const uint32_t* __restrict__ all_hist, uint32_t n_gpus, uint32_
         if (overflow)   // nothing will arrive: give the join an empty relation
             for (uint32_t p = tid; p < np; p += PPC_THREADS) { loc_cnt[p] = 0; loc_off[p] = 0; }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3d. Sharded "partition, copy, partition" pipeline (pcp).  NVLink moves long runs far better than
+//     short ones (profiles/README.md), so here only WHOLE first-pass partitions cross it: the
+//     source scatters its shard on [gpu bits | top bL local bits] (<= 1024 chunks), a copy
+//     kernel moves every chunk into the destination's first-pass layout with TMA bulk copies
+//     (global -> shared -> peer global, no register traffic), and the receiver runs the last
+//     radix pass + join.  The coarse histograms are all-gathered BEFORE the source pass:
+//     pcp_layout_kernel derives, for chunk c = (destination d, first-pass partition j), where it
+//     lands at d -- first-pass partition j of d starts at sum_{j'<j} C[d][j'], source r writes at
+//     + sum_{s<r} H[s][c] -- and where the source stages it: every chunk gets its count + 1 slots
+//     and starts on the slot whose 16-byte phase equals its destination's, so head tuple, bulk
+//     body and tail tuple line up on both sides.
+//     status: [0] abort (a destination would overflow) [1] tuples this GPU receives [2] pieces
+// ------------------------------------------------------------------------------------------
+constexpr int PCP_MAX_CHUNKS = 1024;
+constexpr uint32_t PCP_PIECE = 2048;     // tuples per bulk copy (16 KB), even
+struct PcpTables {                       // device arrays of n1 (+1) entries
+    uint32_t* cur;                       // pass-1 cursors (consumed by the scatter)
+    uint32_t* src_start;                 // first slot of chunk c in the source's stage buffer
+    uint32_t* dst_start;                 // first slot of this source's share at the destination
+    uint32_t* cnt;                       // tuples of chunk c in this shard
+    uint32_t* piece_prefix;              // [n1 + 1], indexed by POSITION k (chunk tile_perm(k))
+    uint32_t* status;
+};
+
+__device__ __forceinline__ uint32_t pcp_pieces(uint32_t cnt, uint32_t phase) {
+    return cnt ? max(1u, (cnt - phase + PCP_PIECE - 1u) / PCP_PIECE) : 0u;
+}
+
+// one CTA of 1024 threads; thread t owns chunk t (partition order) and position t (copy order)
+__global__ void __launch_bounds__(PCP_MAX_CHUNKS)
+pcp_layout_kernel(const uint32_t* __restrict__ all_hist, uint32_t n_gpus, uint32_t rank, uint32_t b1, uint32_t bl,
+                  uint32_t cap_tuples, uint32_t perm, PcpTables t) {
+    __shared__ uint32_t s_a[PCP_MAX_CHUNKS], s_ph[PCP_MAX_CHUNKS], s_cn[PCP_MAX_CHUNKS];
+    __shared__ uint32_t s_warp[3][PCP_MAX_CHUNKS / 32];
+    const uint32_t c = threadIdx.x, lane = c & 31u, wid = c >> 5, n1 = 1u << b1;
+    uint32_t tot = 0, pre = 0, mine = 0;
+    if (c < n1)
+        for (uint32_t s = 0; s < n_gpus; ++s) {
+            const uint32_t h = all_hist[(size_t)s * n1 + c];
+            tot += h;
+            if (s < rank) pre += h;
+            if (s == rank) mine = h;
+        }
+    // two block-wide exclusive scans in chunk order: destination totals, source regions (count + 1)
+    uint32_t i0 = warp_incl_scan(tot, lane), i1 = warp_incl_scan(mine + 1u, lane);
+    if (lane == 31) { s_warp[0][wid] = i0; s_warp[1][wid] = i1; }
+    __syncthreads();
+    uint32_t w0 = 0, w1 = 0;
+    for (uint32_t w = 0; w < wid; ++w) { w0 += s_warp[0][w]; w1 += s_warp[1][w]; }
+    const uint32_t ex_tot = i0 - tot + w0, region = i1 - (mine + 1u) + w1;
+    s_a[c] = ex_tot;
+    __syncthreads();
+    const uint32_t d = c >> bl;
+    const uint32_t dbase = s_a[d << bl];                       // first chunk of this destination
+    const uint32_t dst = ex_tot - dbase + pre;
+    const uint32_t src = region + ((region ^ dst) & 1u);       // same 16-byte phase as the destination slot
+    if (c < n1) {
+        t.cur[c] = src; t.src_start[c] = src; t.dst_start[c] = dst; t.cnt[c] = mine;
+        const bool last_of_dest = ((c + 1u) & ((1u << bl) - 1u)) == 0u;
+        if (last_of_dest) {
+            const uint32_t dtot = ex_tot + tot - dbase;
+            const bool over = (unsigned long long)dtot + 16ull > (unsigned long long)cap_tuples;
+            if (over) atomicExch(&t.status[0], 1u);
+            if (d == rank) t.status[1] = over ? 0u : dtot;     // nothing will arrive: the receiver sees an empty relation
+        }
+    }
+    s_ph[c] = src & 1u; s_cn[c] = mine;
+    __syncthreads();
+    // pieces in COPY order: position k takes chunk tile_perm(k)
+    const uint32_t ck = tile_perm(c, perm);
+    const uint32_t pieces = (c < n1) ? pcp_pieces(s_cn[ck], s_ph[ck]) : 0u;
+    const uint32_t i2 = warp_incl_scan(pieces, lane);
+    if (lane == 31) s_warp[2][wid] = i2;
+    __syncthreads();
+    uint32_t w2 = 0, all = 0;
+    for (uint32_t w = 0; w < PCP_MAX_CHUNKS / 32; ++w) { const uint32_t x = s_warp[2][w]; if (w < wid) w2 += x; all += x; }
+    if (c < n1) t.piece_prefix[c] = i2 - pieces + w2;
+    if (c == 0) { t.piece_prefix[n1] = all; t.status[2] = all; }
+}
+
+struct PcpCopyArgs {
+    const tup_t* stage;                  // first-pass output of this shard
+    tup_t* const* peer_bases;            // [n_gpus] receive buffers (local or mapped over NVLink)
+    PcpTables t;
+    uint32_t b1, bl, perm;
+};
+
+// One warp per CTA, NS ring slots of PCP_PIECE tuples.  Lane 0 walks this CTA's pieces (static
+// round robin): it issues the bulk load of piece i and, LAG pieces behind, the bulk store of piece
+// i - LAG, so LAG loads are in flight per CTA and a slot is reloaded only after its previous store
+// has read it (bulk async-group accounting: one group per piece, empty groups included).
+template <int NS>
+__global__ void __launch_bounds__(32)
+pcp_copy_kernel(PcpCopyArgs a) {
+    constexpr uint32_t LAG = NS - 2;
+    static_assert(NS >= 3, "ring too small");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tup_t* ring = reinterpret_cast<tup_t*>(smem_raw);                                   // [NS][PCP_PIECE]
+    uint32_t* s_prefix = reinterpret_cast<uint32_t*>(smem_raw + (size_t)NS * PCP_PIECE * sizeof(tup_t));   // [n1 + 1]
+    __shared__ uint64_t s_full[NS];
+    __shared__ tup_t* s_dst[NS];
+    __shared__ uint32_t s_bytes[NS];
+    const uint32_t n1 = 1u << a.b1;
+    if (a.t.status[0]) return;
+    for (uint32_t i = threadIdx.x; i <= n1; i += 32) s_prefix[i] = a.t.piece_prefix[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&s_full[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const uint32_t total = s_prefix[n1];
+    uint32_t issued = 0, stored = 0;
+    for (uint32_t k = blockIdx.x; k < total || stored < issued; k += gridDim.x) {
+        if (k < total) {
+            uint32_t lo = 0, hi = n1;             // largest position whose prefix is <= k
+            while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (s_prefix[m] <= k) lo = m; else hi = m; }
+            const uint32_t c = tile_perm(lo, a.perm), slice = k - s_prefix[lo];
+            const uint32_t src0 = a.t.src_start[c], dst0 = a.t.dst_start[c], cnt = a.t.cnt[c];
+            const uint32_t phase = src0 & 1u;     // == dst0 & 1 by construction
+            const tup_t* src = a.stage + src0;
+            tup_t* dst = a.peer_bases[c >> a.bl] + dst0;
+            if (slice == 0 && phase) *dst = *src;                     // odd first slot: plain 8-byte copy
+            const uint32_t body0 = phase + slice * PCP_PIECE;         // even slot on both sides
+            uint32_t m = (cnt > body0) ? min(PCP_PIECE, cnt - body0) : 0u;
+            if (m & 1u) { dst[body0 + m - 1u] = src[body0 + m - 1u]; --m; }   // odd tail (last piece only)
+            const uint32_t slot = issued % NS;
+            // the slot's previous tenant (piece issued - NS) was stored at least NS - 1 - LAG groups ago
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NS - 1 - LAG) : "memory");
+            s_dst[slot] = dst + body0;
+            s_bytes[slot] = m * (uint32_t)sizeof(tup_t);
+            mbar_arrive_expect_tx(&s_full[slot], m * (uint32_t)sizeof(tup_t));
+            if (m) bulk_g2s(ring + (size_t)slot * PCP_PIECE, src + body0, m * (uint32_t)sizeof(tup_t), &s_full[slot]);
+            ++issued;
+        }
+        // keep at most LAG loads ahead of the stores; drain once the pieces are exhausted
+        while (stored < issued && (k >= total || issued - stored > LAG)) {
+            const uint32_t slot = stored % NS;
+            mbar_wait(&s_full[slot], (stored / NS) & 1u);
+            if (s_bytes[slot]) bulk_s2g(s_dst[slot], ring + (size_t)slot * PCP_PIECE, s_bytes[slot]);
+            bulk_commit();
+            ++stored;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------

@@ -68,6 +68,22 @@ def pp_layout(all_hist: np.ndarray, rank: int, local_bits: int):
     return cur, off[rank], Cn[rank]
 
 
+def pcp_layout(all_hist: np.ndarray, rank: int, source_local_bits: int):
+    """numpy model of pcp_layout_kernel: all_hist[s][c] = tuples of source s in chunk c = (dest <<
+    bl) | j (j = first-pass partition at the destination).  Returns (dst_start[c] of `rank`'s
+    shares, src_start[c] in `rank`'s stage buffer, tuples every destination receives)."""
+    H = np.asarray(all_hist).astype(np.int64)
+    G, n1 = H.shape
+    bl = source_local_bits
+    tot = H.sum(axis=0)
+    ex = np.concatenate(([0], np.cumsum(tot)[:-1]))
+    dbase = ex[(np.arange(n1) >> bl) << bl]
+    dst = ex - dbase + H[:rank].sum(axis=0)
+    region = np.concatenate(([0], np.cumsum(H[rank] + 1)[:-1]))
+    src = region + ((region ^ dst) & 1)
+    return dst, src, tot.reshape(-1, 1 << bl).sum(axis=1)
+
+
 @dataclass
 class ShardedResult:
     matches: int
@@ -267,6 +283,51 @@ class GpuOps:
         ph = dict(ph, shuffle_scatter_ms=ph["push_R_ms"] + ph["push_S_ms"], pass1_bits=b1, pass2_bits=b2, radix_bits=B)
         return m, c, (n_r, n_s), ph
 
+    def pcp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob):
+        """Mode "pcp": coarse histograms -> all-gather -> first radix pass at the source -> TMA bulk
+        copies of whole first-pass partitions -> last radix pass + join at the receiver.  R's copy
+        runs under S's first pass, S's copy under R's last pass."""
+        torch, eng = self.torch, self.engine
+        sR, sS = self.stream_shuffle, self.stream_local           # S on the high-priority stream
+        streams = (sR, sS)
+        eng.pcp_begin(n_glob[0], n_glob[1], G, rank, B, sR)
+        g, bl, _ = eng.pcp_plan()
+        n1 = 1 << (g + bl)                                        # chunks = first-pass partitions of all destinations
+        if getattr(self, "_pcp_key", None) != (G, n1):
+            self._pcp_hist = [torch.empty(n1, dtype=torch.int32, device=self.dev) for _ in range(2)]
+            self._pcp_all = [torch.empty(G * n1, dtype=torch.int32, device=self.dev) for _ in range(2)]
+            self._pcp_tok = [torch.zeros(1, dtype=torch.int32, device=self.dev) for _ in range(2)]
+            self._pcp_key = (G, n1)
+        cur = torch.cuda.current_stream(self.device)
+        for s in streams:
+            s.wait_stream(cur)
+        caps = (self.cap_R, self.cap_S)
+        for which, (k, p) in enumerate(rels):
+            eng.pcp_hist(which, k, self._pcp_hist[which], streams[which])
+            with torch.cuda.stream(streams[which]):
+                dist.all_gather_into_tensor(self._pcp_all[which], self._pcp_hist[which], group=group)
+        ev = {}
+        for which, (k, p) in enumerate(rels):
+            s = streams[which]
+            if which == 1:
+                s.wait_event(ev["part0"])                         # S's first pass runs under R's copy ...
+            eng.pcp_part(which, k, p, self._pcp_all[which], caps[which], s)
+            ev[f"part{which}"] = torch.cuda.Event(); ev[f"part{which}"].record(s)
+            if which == 1:
+                s.wait_event(ev["copy0"])                         # ... and one relation crosses NVLink at a time
+            eng.pcp_copy(which, peers[which], s)
+            ev[f"copy{which}"] = torch.cuda.Event(); ev[f"copy{which}"].record(s)
+            with torch.cuda.stream(s):
+                dist.all_reduce(self._pcp_tok[which], group=group)   # every rank's copies have landed
+        for which in range(2):
+            eng.pcp_recv(which, own_ptrs[which], caps[which], streams[which])
+        sS.wait_stream(sR)
+        eng.pcp_join(caps[0], caps[1], sS)
+        m, c, n_r, n_s, ph, bits = eng.pcp_finish()
+        sR.synchronize()
+        ph = dict(ph, shuffle_scatter_ms=ph["copy_R_ms"] + ph["copy_S_ms"], radix_bits=B, pass1_bits=bits[0] + bits[1], pass2_bits=bits[2])
+        return m, c, (n_r, n_s), ph
+
     def exchange_counts(self, dist, group, mine):
         """All ranks' count vectors in ONE small NCCL all-gather (doubles as a barrier)."""
         t = self.torch.tensor([int(x) for x in mine], dtype=self.torch.int64, device=self.dev)
@@ -313,14 +374,14 @@ class ShardedJoin:
         self.max_local = (max_local_R, max_local_S)
         self._peers = None
         self._own = [0, 0]
-        if mode in ("p2p", "dma", "pp"):
+        if mode in ("p2p", "dma", "pp", "pcp"):
             if ops is None:
                 self._setup_peers()
             else:                      # test stand-in: no device buffers to map
                 self._peers = [[0] * self.world, [0] * self.world]
                 self._opened = []
         elif mode != "nccl":
-            raise ValueError("mode must be 'nccl', 'p2p', 'dma' or 'pp'")
+            raise ValueError("mode must be 'auto', 'nccl', 'p2p', 'dma', 'pp' or 'pcp'")
 
     # -- CUDA IPC mapping of every rank's receive buffers (p2p mode) -------------------------
     def _setup_peers(self):
@@ -386,9 +447,9 @@ class ShardedJoin:
         shift = B
         rels = ((Rk, Rp), (Sk, Sp))
         local_n = [0, 0]
-        if self.mode == "pp":
-            m, c, local_n, tm = ops.pp_join(dist, self.group, rank, rels, G, B, self._peers, self._own,
-                                            (n_R_global, n_S_global))
+        if self.mode in ("pp", "pcp"):
+            run = ops.pp_join if self.mode == "pp" else ops.pcp_join
+            m, c, local_n, tm = run(dist, self.group, rank, rels, G, B, self._peers, self._own, (n_R_global, n_S_global))
             lap()
         elif self.mode == "nccl":
             import torch
@@ -438,13 +499,13 @@ class ShardedJoin:
                 tm = dict(tm, shuffle_scatter_ms=shuffle_ms)
         if self.mode == "nccl":
             m, c, tm = ops.local_join(local_n[0], local_n[1])
-        if self.mode != "pp":
+        if self.mode not in ("pp", "pcp"):
             lap()
         res = ops.result_tensor(m, c)
         dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
         vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
         lap()
-        if self.mode == "pp":
+        if self.mode in ("pp", "pcp"):
             d = [1e3 * (b - a) for a, b in zip(t_host, t_host[1:])]
             tm = dict(tm, host_ms={"pipeline": d[0], "reduce": d[1]})
         elif self.mode != "nccl" and len(t_host) == 5:

@@ -207,6 +207,30 @@ int gj_pp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n
                  uint64_t* n_local_S, float* phase_ms);
 int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bits);
 
+/* ---- sharded "partition, copy, partition" pipeline (multi-GPU, experimental) -------------------
+ * NVLink moves long runs far better than short ones, so here only WHOLE first-pass partitions
+ * cross it.  Per relation: gj_pcp_hist = this shard's histogram on [gpu bits | top local bits]
+ * (2^(g + bl) uint32 into d_coarse_hist); the caller all-gathers those into d_all_hist
+ * ([n_gpus][2^(g + bl)]); gj_pcp_part = layout + first radix pass into the context's stage buffer;
+ * gj_pcp_copy = a TMA bulk-copy kernel moves every chunk to its slot in the destination's receive
+ * buffer (peer_bases[g], 16-byte aligned, cap_tuples + 16 tuples); after the caller's "all copies
+ * have landed" point gj_pcp_recv runs histogram + LAST radix pass over d_own (this GPU's receive
+ * buffer); gj_pcp_join + gj_pcp_finish as for gj_pp_*.  phase_ms[7] = part R, copy R, recv R,
+ * part S, copy S, recv S, join; plan_bits[3] = gpu bits, source-side local bits, receiver-side bits.
+ * n + 2^(g + bl) must not exceed the context capacity (one spare stage slot per chunk). */
+int gj_pcp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
+                 uint32_t local_bits, void* cuda_stream);
+int gj_pcp_plan(gj_ctx* ctx, uint32_t plan_bits[3]);
+int gj_pcp_hist(gj_ctx* ctx, int which, const int32_t* d_keys, uint64_t n, uint32_t* d_coarse_hist,
+                void* cuda_stream);
+int gj_pcp_part(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays,
+                const uint32_t* d_all_hist, uint64_t cap_tuples, void* cuda_stream);
+int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* cuda_stream);
+int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, uint64_t cap_tuples, void* cuda_stream);
+int gj_pcp_join(gj_ctx* ctx, uint64_t cap_R, uint64_t cap_S, void* cuda_stream);
+int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
+                  uint64_t* n_local_S, float* phase_ms, uint32_t* plan_bits);
+
 /* CUDA IPC plumbing for the peer-store variant when every GPU is driven by its own process:
  * export a gj_malloc_device allocation as a 64-byte handle, open a peer's handle (peer access is
  * enabled lazily), close it again. */

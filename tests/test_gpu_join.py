@@ -534,6 +534,134 @@ def test_pp_destination_overflow_is_reported(gj, orc, torch_cuda):
         _pp_virtual(gj, orc, torch_cuda, G, B, k, p, k, p, slack=0.5, check_layout=False)
 
 
+# ------------------------------------------------------------------------------- sharded "partition, copy, partition"
+def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, opts=None, check_layout=True):
+    """gj_pcp_* with G virtual ranks on ONE GPU (one engine context per rank, every 'peer' buffer
+    local; the all-gather is a torch.stack)."""
+    rels = [(Rk, Rp), (Sk, Sp)]
+    n = [len(Rk), len(Sk)]
+    if splits is None:
+        splits = [np.linspace(0, n[w], G + 1).astype(np.int64) for w in range(2)]
+    shard_n = [[int(splits[w][r + 1] - splits[w][r]) for r in range(G)] for w in range(2)]
+    caps = []
+    for w in range(2):
+        d = ((rels[w][0].view(np.uint32) >> B) & (G - 1)) if n[w] else np.zeros(0, dtype=np.int64)
+        caps.append(int(max(np.bincount(d, minlength=G).max() if n[w] else 0, 1) * slack) + 64)
+    # engine capacity: the receive capacity, and the shard + one spare stage slot per chunk
+    mx = [max(caps[w], max(shard_n[w]) + 1024) for w in range(2)]
+    engs = [gj.JoinEngine(mx[0], mx[1], 0, **(opts or {})) for _ in range(G)]
+    try:
+        own = [[torch.zeros(caps[w] + 16, dtype=torch.int64, device="cuda") for _ in range(G)] for w in range(2)]
+        cols = [[dev(torch, rels[w][0][splits[w][r]:splits[w][r + 1]], rels[w][1][splits[w][r]:splits[w][r + 1]])
+                 for r in range(G)] for w in range(2)]
+        torch.cuda.synchronize()
+        for r in range(G):
+            engs[r].pcp_begin(n[0], n[1], G, r, B)
+        g, bl, b2 = engs[0].pcp_plan()
+        assert g == G.bit_length() - 1 and bl + b2 == B
+        n1 = 1 << (g + bl)
+        hist = [[torch.empty(n1, dtype=torch.int32, device="cuda") for _ in range(G)] for w in range(2)]
+        for r in range(G):
+            for w in range(2):
+                engs[r].pcp_hist(w, cols[w][r][0], hist[w][r])
+        torch.cuda.synchronize()
+        allh = [torch.stack(hist[w]).contiguous() for w in range(2)]
+        for w in range(2):
+            for r in range(G):
+                k = rels[w][0][splits[w][r]:splits[w][r + 1]].view(np.uint32)
+                assert np.array_equal(hist[w][r].cpu().numpy(), np.bincount((k >> (B - bl)) & (n1 - 1), minlength=n1))
+        for r in range(G):
+            for w in range(2):
+                engs[r].pcp_part(w, cols[w][r][0], cols[w][r][1], allh[w], caps[w])
+                engs[r].pcp_copy(w, [t.data_ptr() for t in own[w]])
+        torch.cuda.synchronize()
+        # every receive buffer is first-pass partitioned: partition j of destination d holds exactly the
+        # tuples with (key >> (B - bl)) & (2^(g+bl) - 1) == (d << bl) | j, nothing beyond the total
+        for w in range(2):
+            ah = allh[w].cpu().numpy()
+            if not n[w] or not check_layout:
+                continue
+            c_all, h_all = orc.partition_fingerprint(rels[w][0], rels[w][1], B - bl, g + bl)
+            for d in range(G):
+                _, _, tots = gj.distributed.pcp_layout(ah, d, bl)
+                tot = int(tots[d])
+                got = own[w][d].cpu().numpy()
+                assert not got[tot:].any()
+                t = got[:tot].view(np.int32).reshape(-1, 2)
+                keys = np.ascontiguousarray(t[:, 0])
+                cnt = ah.sum(axis=0)[d << bl:(d + 1) << bl]
+                pid = np.repeat(np.arange(1 << bl, dtype=np.int64) + (d << bl), cnt)
+                assert np.array_equal(((keys.view(np.uint32) >> (B - bl)) & (n1 - 1)).astype(np.int64), pid)
+                if tot:
+                    c, h = orc.partition_fingerprint(keys, np.ascontiguousarray(t[:, 1]), B - bl, g + bl)
+                    sl = slice(d << bl, (d + 1) << bl)
+                    assert np.array_equal(c[sl], c_all[sl]) and np.array_equal(h[sl], h_all[sl])
+        m = c = 0
+        got_n = [0, 0]
+        for r in range(G):
+            for w in range(2):
+                engs[r].pcp_recv(w, own[w][r].data_ptr(), caps[w])
+            engs[r].pcp_join(caps[0], caps[1])
+            mm, cc, a, b, ph, bits = engs[r].pcp_finish()
+            m += mm
+            c = (c + cc) % 2**64
+            got_n[0] += a
+            got_n[1] += b
+        assert got_n == n
+        return m, c, (g, bl, b2)
+    finally:
+        for e in engs:
+            e.close()
+
+
+@pytest.mark.parametrize("G,B,p1", [(2, 7, 0), (4, 9, 0), (8, 8, 0), (8, 13, 0), (8, 15, 0), (8, 16, 0), (2, 15, 0), (16, 14, 0),
+                                    (8, 15, 10), (8, 15, 3), (4, 12, 6), (2, 1, 0)])
+def test_pcp_virtual_shards(gj, orc, torch_cuda, G, B, p1):
+    """Source-side pass on [gpu | top local bits] (up to 1024 chunks), TMA bulk copies of whole chunks
+    (odd head / tail tuples, empty chunks, one-tuple chunks), receiver-side last pass of up to 10 bits;
+    signed keys, N:M matches, ragged shards (one empty)."""
+    rng = np.random.default_rng(11 * G + B + p1)
+    nR, nS = 900_000, 1_700_000
+    Rk = rnd(rng, nR, -(1 << 21), 1 << 21)
+    Sk = rnd(rng, nS, -(1 << 21), 1 << 21)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    splits = []
+    for n in (nR, nS):
+        cuts = np.sort(rng.integers(0, n, size=G - 1))
+        if G > 2:
+            cuts[1] = cuts[0]                   # an empty shard
+        splits.append(np.concatenate(([0], cuts, [n])).astype(np.int64))
+    m, c, bits = _pcp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, splits=splits, opts={"pass1_bits": p1} if p1 else None)
+    assert (m, c) == (want.matches, want.checksum)
+    g = G.bit_length() - 1
+    assert bits[0] == g and bits[0] + bits[1] <= 10 and bits[2] <= 10 and bits[1] <= 8
+    if p1:
+        assert bits[1] == max(min(max(p1 - g, 0), 10 - g, B - 1, 8), B - 10)
+
+
+def test_pcp_skew_tiny_and_overflow(gj, orc, torch_cuda):
+    rng = np.random.default_rng(6)
+    nR, nS, G, B = 300_000, 1_200_000, 4, 8
+    Rk = rng.permutation(nR).astype(np.int32)
+    hot = rng.integers(0, 50, size=nS // 2)
+    Sk = np.concatenate((hot, rng.integers(0, nR, size=nS - nS // 2))).astype(np.int32)
+    rng.shuffle(Sk)
+    Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    assert _pcp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, slack=1.2)[:2] == (want.matches, want.checksum)
+    # a handful of tuples: most chunks empty, some with a single tuple
+    tk = np.array([5, 5, 7, 300, -1, 1 << 20], dtype=np.int32)
+    tp = np.arange(6, dtype=np.int32) + 1
+    w2 = orc.join_check(tk, tp, tk, tp)
+    assert _pcp_virtual(gj, orc, torch_cuda, 4, 3, tk, tp, tk, tp, slack=8.0)[:2] == (w2.matches, w2.checksum)
+    e = np.zeros(0, dtype=np.int32)
+    assert _pcp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, e, e)[:2] == (0, 0)
+    k = (rng.integers(0, 1 << 8, size=200_000) | (2 << 8)).astype(np.int32)     # every key goes to GPU 2
+    with pytest.raises(gj.GJError):
+        _pcp_virtual(gj, orc, torch_cuda, G, B, k, k, k, k, slack=0.5, check_layout=False)
+
+
 # ------------------------------------------------------------------------------- device generator
 def test_device_generator_is_the_host_bijection(gj, orc, eng, torch_cuda):
     n = 1_000_003
