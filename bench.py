@@ -428,9 +428,9 @@ def multi_gpu(args):
     if kind != "unique":
         raise SystemExit("multi-GPU bench supports the unique-key workloads (B, small, cfg5)")
     if args.shuffle == "auto":
-        # short pushed runs cross NVLink slower the more destinations share a tile: measured
-        # 2 GPUs 124.8 (pp) vs 111.6 (p2p), 4 GPUs 198.0 vs 192.5, 8 GPUs 315.0 vs 352.8 G tuples/s
-        args.shuffle = "pp" if world <= 4 else "p2p"
+        # measured (profiles/README.md, G tuples/s, weak scaling): 2 GPUs pcp 128.8 / pp 124.8 / p2p 111.6;
+        # 8 GPUs pcp 406.8 / p2p 352.8 / pp 315.0.  Config 5 has only been measured with p2p and pp at 8 GPUs.
+        args.shuffle = "p2p" if (w == "cfg5" and world >= 8) else "pcp"
     strong = (w == "cfg5")
     if strong:                      # fixed total, per-GPU share shrinks with N
         nR, nS = nR // world, nS // world
@@ -565,7 +565,8 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--shuffle", default="auto", choices=["auto", "p2p", "nccl", "dma", "pp", "pcp"],
                     help="multi-GPU exchange: pp = partition locally, last radix pass pushes into the peers; p2p = peer-store "
-                         "shuffle first, local passes at the receiver; auto = pp up to 4 GPUs, p2p beyond (measured, profiles/README.md)")
+                         "shuffle first, local passes at the receiver; pcp = first radix pass at the source, whole first-pass partitions "
+                         "bulk-copied over NVLink, last pass at the receiver; auto = pcp (measured best, profiles/README.md)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: shuffle and local passes back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")

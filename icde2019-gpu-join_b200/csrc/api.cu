@@ -1667,7 +1667,7 @@ extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void
         a.stage = ctx->out[which]; a.peer_bases = q.bases[which]; a.t = q.tab[which];
         a.b1 = q.b1; a.bl = q.bl; a.perm = (q.b1 << 8) | q.g;
         const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
-        uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count * 2u;
+        uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count;   // measured (2 GPUs): 148 CTAs 3.98 ms, 296 CTAs 4.24 ms per step
         grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));
         pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
         LAUNCHED();

@@ -364,8 +364,8 @@ class ShardedJoin:
         if self.world & (self.world - 1):
             raise ValueError("world size must be a power of two (GPU id = radix bits)")
         self.gpu_bits = int(math.log2(self.world))
-        if mode == "auto":     # measured on B200 / NVLink 5 (profiles/README.md): pushed runs get shorter
-            mode = "pp" if self.world <= 4 else "p2p"   # with more destinations and cross NVLink slower
+        if mode == "auto":     # measured on B200 / NVLink 5 (profiles/README.md): only whole first-pass
+            mode = "pcp"       # partitions cross NVLink, at the bulk-copy rate (684 GB/s out per GPU at 8 GPUs)
         self.mode = mode
         self.overlap = overlap
         self.part_target = part_target
