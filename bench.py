@@ -545,6 +545,8 @@ def multi_gpu(args):
             line["shuffle"]["note"] = ("partition-then-push: every GPU partitions its own shard on [gpu|local] bits; the last radix pass "
                                        "stores its runs into the destination GPU's final partition buffer over NVLink; "
                                        "scatter_kernel_ms = cursor kernel + pushing pass of R and S")
+        if line["shuffle"].get("nvlink_out_GBs_per_gpu"):
+            line["shuffle"]["nvlink_frac_of_peer_copy_peak"] = line["shuffle"]["nvlink_out_GBs_per_gpu"] / line["shuffle"]["nvlink_peak_GBs"]
         if line["roofline"]["achieved"]:
             line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
         line["config"].update({"global_R": NR, "global_S": NS, "parallelism": f"radix-sharded over {world} GPUs, {args.shuffle} shuffle"

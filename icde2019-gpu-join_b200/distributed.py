@@ -68,6 +68,19 @@ def pp_layout(all_hist: np.ndarray, rank: int, local_bits: int):
     return cur, off[rank], Cn[rank]
 
 
+def pcp_plan_bits(n_gpus: int, local_bits: int, pass1_bits: int = 0):
+    """Mirror of the plan in gj_pcp_begin (csrc/api.cu): (gpu bits g, local bits bl of the source-side
+    pass, bits b2 of the receiver-side pass), g + bl <= 10, bl <= 8, b2 = local_bits - bl <= 10."""
+    g, B = n_gpus.bit_length() - 1, local_bits
+    bl = max(pass1_bits - g, 0) if pass1_bits else ((B - g + 1) // 2 if B > g else 0)
+    bl = min(bl, 10 - g, B - 1, 8)
+    if B - bl > 10:
+        bl = B - 10
+    if g + bl > 10 or bl > 8:
+        raise ValueError(f"{g} GPU bits + {B} local bits do not fit two passes of <= 10 bits")
+    return g, bl, B - bl
+
+
 def pcp_layout(all_hist: np.ndarray, rank: int, source_local_bits: int):
     """numpy model of pcp_layout_kernel: all_hist[s][c] = tuples of source s in chunk c = (dest <<
     bl) | j (j = first-pass partition at the destination).  Returns (dst_start[c] of `rank`'s

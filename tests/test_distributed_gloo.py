@@ -98,6 +98,53 @@ class NumpyOps:
         res = oracle.join_check(cols[0][0], cols[0][1], cols[1][0], cols[1][1], 1)
         return res.matches, res.checksum, local_n, {}
 
+    def pcp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob):
+        """Mode "pcp" without a GPU: coarse histograms with numpy, the real all-gather, the layout of
+        distributed.pcp_layout (numpy model of pcp_layout_kernel), the chunk copies emulated by an
+        all-to-all of (slot, tuple) pairs.  The receiver checks that the slots tile [0, total) exactly,
+        that its buffer is first-pass partitioned, and joins with the oracle."""
+        from oracle import oracle
+        import __graft_entry__ as ge
+        d = ge.load_package().distributed
+        torch = self.torch
+        g, bl, b2 = d.pcp_plan_bits(G, B)
+        n1 = 1 << (g + bl)
+        cols, local_n = [], []
+        for k, p in rels:
+            kk, pv = k.numpy(), p.numpy()
+            c = ((kk.view(np.uint32) >> (B - bl)) & (n1 - 1)).astype(np.int64)
+            hist = torch.from_numpy(np.bincount(c, minlength=n1).astype(np.int32))
+            allh = torch.empty(G * n1, dtype=torch.int32)
+            dist.all_gather_into_tensor(allh, hist, group=group)
+            ah = allh.numpy().reshape(G, n1)
+            dst, src, tots = d.pcp_layout(ah, rank, bl)
+            assert not ((dst ^ src) & 1).any()                      # stage slot and destination slot share the 16-byte phase
+            order = np.argsort(c, kind="stable")
+            cs = c[order]
+            start = np.concatenate(([0], np.cumsum(np.bincount(cs, minlength=n1))[:-1]))
+            slot = dst[cs] + (np.arange(cs.size) - start[cs])
+            packed = (kk[order].view(np.uint32).astype(np.uint64) | (pv[order].view(np.uint32).astype(np.uint64) << 32)).view(np.int64)
+            send = torch.from_numpy(np.ascontiguousarray(np.stack([slot, packed], axis=1)))
+            n_to = np.bincount(cs >> bl, minlength=G)
+            n_from = ah.reshape(G, G, -1)[:, rank].sum(axis=1)
+            recv = torch.empty((int(n_from.sum()), 2), dtype=torch.int64)
+            dist.all_to_all_single(recv, send, output_split_sizes=[int(x) for x in n_from],
+                                   input_split_sizes=[int(x) for x in n_to], group=group)
+            r = recv.numpy()
+            tot = int(tots[rank])
+            assert r.shape[0] == tot and np.array_equal(np.sort(r[:, 0]), np.arange(tot))
+            buf = np.empty(tot, dtype=np.int64)
+            buf[r[:, 0]] = r[:, 1]
+            u = buf.view(np.uint64)
+            keys = (u & 0xFFFFFFFF).astype(np.uint32)
+            cnt = ah.sum(axis=0)[rank << bl:(rank + 1) << bl]
+            pid = np.repeat(np.arange(1 << bl, dtype=np.int64) + (rank << bl), cnt)
+            assert np.array_equal(((keys >> (B - bl)) & (n1 - 1)).astype(np.int64), pid)
+            cols.append((keys.view(np.int32), (u >> 32).astype(np.uint32).view(np.int32)))
+            local_n.append(tot)
+        res = oracle.join_check(cols[0][0], cols[0][1], cols[1][0], cols[1][1], 1)
+        return res.matches, res.checksum, local_n, {}
+
     def result_tensor(self, m, c):
         to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v  # noqa: E731
         return self.torch.tensor([to_i64(m), to_i64(c)], dtype=self.torch.int64)
@@ -132,7 +179,8 @@ def _worker(rank, world, port, nR, nS, q, mode="nccl"):
 
 
 @pytest.mark.parametrize("world,nR,nS,mode", [(2, 20_000, 50_000, "nccl"), (4, 30_000, 30_001, "nccl"), (2, 7, 0, "nccl"),
-                                              (2, 20_000, 50_000, "pp"), (4, 30_000, 30_001, "pp"), (2, 7, 0, "pp")])
+                                              (2, 20_000, 50_000, "pp"), (4, 30_000, 30_001, "pp"), (2, 7, 0, "pp"),
+                                              (2, 20_000, 50_000, "pcp"), (4, 30_000, 30_001, "pcp"), (2, 7, 0, "pcp")])
 def test_sharded_join_host_logic_gloo(world, nR, nS, mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -180,3 +228,40 @@ def test_pp_layout_tiles_every_destination(gj):
                 assert cur[r][q] == at
                 at += H[r, q]
             assert at == off[p + 1]
+
+
+def gg_B_too_wide(G, B):
+    return (G.bit_length() - 1) + B > 20
+
+
+def test_pcp_layout_and_plan(gj):
+    """pcp: every chunk lands behind the shares of the lower ranks inside its first-pass partition at
+    the destination, stage regions do not overlap and share the destination's 16-byte phase; the
+    plan keeps g + bl <= 10, bl <= 8, b2 <= 10."""
+    d = gj.distributed
+    rng = np.random.default_rng(8)
+    G, bl = 4, 3
+    g = 2
+    H = rng.integers(0, 9, size=(G, 1 << (g + bl)))
+    H[:, 3] = 0
+    tot = H.sum(axis=0)
+    for c in range(1 << (g + bl)):
+        at = tot[(c >> bl) << bl:c].sum()
+        for r in range(G):
+            dst, src, tots = d.pcp_layout(H, r, bl)
+            assert dst[c] == at and not ((dst[c] ^ src[c]) & 1)
+            at += H[r, c]
+    for r in range(G):
+        dst, src, tots = d.pcp_layout(H, r, bl)
+        assert np.all(src[1:] >= (src + H[r])[:-1]) and src[-1] + H[r, -1] <= H[r].sum() + (1 << (g + bl))
+        assert np.array_equal(tots, tot.reshape(G, -1).sum(axis=1))
+    for G2 in (2, 4, 8, 16, 64):
+        for B in range(1, 17):
+            for p1 in (0, 3, 7, 10):
+                if gg_B_too_wide(G2, B):
+                    with pytest.raises(ValueError):
+                        d.pcp_plan_bits(G2, B, p1)
+                    continue
+                gg, b_l, b2 = d.pcp_plan_bits(G2, B, p1)
+                assert gg + b_l <= 10 and 0 <= b_l <= 8 and b_l <= B - 1 and b2 == B - b_l and 1 <= b2 <= 10, (G2, B, p1)
+    assert d.pcp_plan_bits(8, 15) == (3, 6, 9) and d.pcp_plan_bits(2, 15) == (1, 7, 8) and d.pcp_plan_bits(8, 16) == (3, 7, 9)

@@ -559,6 +559,7 @@ def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, o
             engs[r].pcp_begin(n[0], n[1], G, r, B)
         g, bl, b2 = engs[0].pcp_plan()
         assert g == G.bit_length() - 1 and bl + b2 == B
+        assert (g, bl, b2) == gj.distributed.pcp_plan_bits(G, B, (opts or {}).get("pass1_bits", 0))
         n1 = 1 << (g + bl)
         hist = [[torch.empty(n1, dtype=torch.int32, device="cuda") for _ in range(G)] for w in range(2)]
         for r in range(G):
