@@ -237,7 +237,7 @@ struct gj_ctx {
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
-            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1;
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_pcp_l2_hint = 0;
     bool attrs_set = false;
 };
 
@@ -428,7 +428,7 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
         {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
         {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
         {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
-        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k},
+        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"pcp_l2_hint", &ctx->opt_pcp_l2_hint},
     };
     for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
     return nullptr;
@@ -1666,6 +1666,7 @@ extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void
         PcpCopyArgs a;
         a.stage = ctx->out[which]; a.peer_bases = q.bases[which]; a.t = q.tab[which];
         a.b1 = q.b1; a.bl = q.bl; a.perm = (q.b1 << 8) | q.g;
+        a.l2_hint = ctx->opt_pcp_l2_hint ? 1u : 0u;
         const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
         uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count;   // measured (2 GPUs): 148 CTAs 3.98 ms, 296 CTAs 4.24 ms per step
         grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));

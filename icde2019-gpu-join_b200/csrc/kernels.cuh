@@ -183,6 +183,21 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
+// variants carrying an L2 cache policy (streaming data that must not evict the partially written
+// lines of a scatter pass running next to it)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
@@ -645,6 +660,7 @@ struct PcpCopyArgs {
     tup_t* const* peer_bases;            // [n_gpus] receive buffers (local or mapped over NVLink)
     PcpTables t;
     uint32_t b1, bl, perm;
+    uint32_t l2_hint;                    // 1: loads and stores carry an L2 evict-first policy
 };
 
 // One warp per CTA, NS ring slots of PCP_PIECE tuples.  Lane 0 walks this CTA's pieces (static
@@ -672,6 +688,7 @@ pcp_copy_kernel(PcpCopyArgs a) {
     __syncwarp();
     if (threadIdx.x != 0) return;
     const uint32_t total = s_prefix[n1];
+    const uint64_t pol = a.l2_hint ? l2_policy_evict_first() : 0ull;
     uint32_t issued = 0, stored = 0;
     for (uint32_t k = blockIdx.x; k < total || stored < issued; k += gridDim.x) {
         if (k < total) {
@@ -692,14 +709,20 @@ pcp_copy_kernel(PcpCopyArgs a) {
             s_dst[slot] = dst + body0;
             s_bytes[slot] = m * (uint32_t)sizeof(tup_t);
             mbar_arrive_expect_tx(&s_full[slot], m * (uint32_t)sizeof(tup_t));
-            if (m) bulk_g2s(ring + (size_t)slot * PCP_PIECE, src + body0, m * (uint32_t)sizeof(tup_t), &s_full[slot]);
+            if (m) {
+                if (a.l2_hint) bulk_g2s_hint(ring + (size_t)slot * PCP_PIECE, src + body0, m * (uint32_t)sizeof(tup_t), &s_full[slot], pol);
+                else bulk_g2s(ring + (size_t)slot * PCP_PIECE, src + body0, m * (uint32_t)sizeof(tup_t), &s_full[slot]);
+            }
             ++issued;
         }
         // keep at most LAG loads ahead of the stores; drain once the pieces are exhausted
         while (stored < issued && (k >= total || issued - stored > LAG)) {
             const uint32_t slot = stored % NS;
             mbar_wait(&s_full[slot], (stored / NS) & 1u);
-            if (s_bytes[slot]) bulk_s2g(s_dst[slot], ring + (size_t)slot * PCP_PIECE, s_bytes[slot]);
+            if (s_bytes[slot]) {
+                if (a.l2_hint) bulk_s2g_hint(s_dst[slot], ring + (size_t)slot * PCP_PIECE, s_bytes[slot], pol);
+                else bulk_s2g(s_dst[slot], ring + (size_t)slot * PCP_PIECE, s_bytes[slot]);
+            }
             bulk_commit();
             ++stored;
         }

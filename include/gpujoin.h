@@ -79,7 +79,8 @@ int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
  *   "join_cfg"     join kernel shape variant (0 = default)
  *   "gpu_bits"     number of key bits above the radix field consumed by the multi-GPU shuffle
  *   "shuffle_grid" persistent CTA count of the peer-store scatter (0 = one tile per CTA)
- *   "pp_out", "pp_tile16k"  sharded pipeline, see gj_pp_begin */
+ *   "pp_out", "pp_tile16k"  sharded pipeline, see gj_pp_begin
+ *   "pcp_l2_hint"  1: the pcp copy kernel's bulk loads / stores carry an L2 evict-first policy (default 0) */
 int gj_set_option(gj_ctx* ctx, const char* name, int64_t value);
 int gj_get_option(gj_ctx* ctx, const char* name, int64_t* value);
 

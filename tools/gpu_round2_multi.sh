@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round-2 queue for the multi-GPU exchange (what round 1 could not measure: GPU budget).
+# usage: gpurun --gpus N -- 'bash tools/gpu_round2_multi.sh N'     (N = 2, 4 or 8)
+#   1. parity of every exchange mode on N real GPUs
+#   2. pcp / pp / p2p on workload B (weak) and, at N = 8, config 5 (strong)
+#   3. why kernels running under the pcp copy kernel are slowed 2.6-3.8x:
+#      copy-kernel grid (shuffle_grid), L2 evict-first policy (pcp_l2_hint), source-side bits (pass1_bits)
+cd "$(dirname "$0")/.."
+N=${1:-8}
+OUT=gpurun_out; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 600 -p no:cacheprovider > $OUT/r2_pytest_multi$N.log 2>&1
+echo "exit $?" >> $OUT/r2_pytest_multi$N.log; tail -3 $OUT/r2_pytest_multi$N.log
+SPECS=("pcp:steps=5" "pcp:steps=5,pcp_l2_hint=1" "pcp:steps=5,shuffle_grid=74" "pcp:steps=5,shuffle_grid=296" "pcp:steps=5,pass1_bits=10" "pp:steps=5" "p2p:steps=5")
+if [ "$N" = "8" ]; then SPECS+=("pcp:steps=5,workload=cfg5" "pcp:steps=5,workload=cfg5,pass1_bits=9" "p2p:steps=5,workload=cfg5"); fi
+bash tools/gpu_pp3.sh $N "${SPECS[@]}"
