@@ -14,6 +14,10 @@
 //        -> decompose_chains (:843-874, probe-side splitting becomes the unit list written by
 //           plan_kernel), join_partitioned_aggregate (:885-1095) and join_partitioned_results
 //           (:1107-1416); fed by a TMA bulk-copy ring (cp.async.bulk + mbarrier).
+//   subhist_tiles_kernel, pp_cursor_kernel, scatter_kernel<..., PUSH>   (section 3c)
+//   pcp_layout_kernel, pcp_copy_kernel                                  (section 3d)
+//        -> no reference counterpart (the reference is single-GPU, hash_join_clustered_probe.cu
+//           :1001,1685 only select a device): the multi-GPU exchange, SURVEY.md section 8e.
 //
 // Data layout in HBM: inputs are columnar int32 keys / payloads (the reference's R/Pr, S/Ps);
 // between passes and into the join tuples are packed {key,payload} 8-byte pairs (tup_t) so one
