@@ -129,6 +129,13 @@ static const JoinCfg kJoin[] = {
     GJ_JC(1024, 4096, 2048, 3, 4, true),   // 6
 };
 static const int kNumJoin = (int)(sizeof(kJoin) / sizeof(kJoin[0]));
+// late-materialisation aggregate (payload = row id, side-table gathers on a match): the default shape
+static const join_fn kJoinLate = join_kernel<1024, 4096, 4096, 3, 3, false, false, true>;
+struct LateCols {   // column-major side tables: value of column z for row id i = cols[z * stride + i]
+    const int32_t* cols[2] = {nullptr, nullptr};   // [0] of the user's R, [1] of the user's S
+    uint32_t ncols[2] = {0, 0};
+    uint64_t stride[2] = {0, 0};
+};
 
 // ------------------------------------------------------------------------------------------
 // context
@@ -271,6 +278,7 @@ static int set_func_attrs(gj_ctx* ctx) {
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (int i = 0; i < kNumJoin; ++i) {
         CK(cudaFuncSetAttribute(kJoin[i].agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_agg));
+        if (i == 0) CK(cudaFuncSetAttribute(kJoinLate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[0].smem_agg));
         if (kJoin[i].smem_mat <= (size_t)227 * 1024)
             CK(cudaFuncSetAttribute(kJoin[i].mat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoin[i].smem_mat));
     }
@@ -626,9 +634,10 @@ static int fill_pass_times(gj_ctx* ctx, gj_timings* t, const Plan& pl, int nrole
 
 static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup_t* prb, const Plan& pl,
                         uint64_t n_bld, uint64_t n_prb, bool mat, int32_t* out_b, int32_t* out_p, uint64_t cap,
-                        const uint32_t* num_units = nullptr, int gpu_bits = -1) {
+                        const uint32_t* num_units = nullptr, int gpu_bits = -1, const LateCols* late = nullptr,
+                        bool bld_is_S = false) {
     (void)n_bld;
-    int cfg = (int)ctx->opt_join_cfg;
+    int cfg = late ? 0 : (int)ctx->opt_join_cfg;
     if (mat && kJoin[cfg].smem_mat > (size_t)227 * 1024) cfg = 2;   // pair staging needs 16 KB: smaller rings
     const JoinCfg& jc = kJoin[cfg];
     JoinArgs a;
@@ -637,12 +646,18 @@ static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup
     a.hash_shift = pl.B + (gpu_bits >= 0 ? (uint32_t)gpu_bits : (uint32_t)ctx->opt_gpu_bits);
     a.result = ctx->result;
     a.out_bld_pay = out_b; a.out_prb_pay = out_p; a.cap = cap;
+    a.bld_cols = a.prb_cols = nullptr; a.ncols_bld = a.ncols_prb = 0; a.stride_bld = a.stride_prb = 0;
+    if (late) {
+        const int b = bld_is_S ? 1 : 0, p = 1 - b;
+        a.bld_cols = late->cols[b]; a.ncols_bld = late->ncols[b]; a.stride_bld = late->stride[b];
+        a.prb_cols = late->cols[p]; a.ncols_prb = late->ncols[p]; a.stride_prb = late->stride[p];
+    }
     const size_t smem = mat ? jc.smem_mat : jc.smem_agg;
     uint64_t grid = (uint64_t)ctx->sm_count;   // persistent: one CTA per SM owns the whole shared memory
     if (ctx->opt_join_grid) grid = (uint64_t)ctx->opt_join_grid;
     const uint64_t max_units = n_prb / unit_tuples(ctx) + (1ull << pl.B);
     grid = std::max<uint64_t>(1, std::min(grid, max_units));
-    (mat ? jc.mat : jc.agg)<<<(uint32_t)grid, jc.threads, smem, s>>>(a);
+    (late ? kJoinLate : (mat ? jc.mat : jc.agg))<<<(uint32_t)grid, jc.threads, smem, s>>>(a);
     LAUNCHED();
     return GJ_OK;
 }
@@ -798,7 +813,8 @@ static int check_caps(gj_ctx* ctx, uint64_t nR, uint64_t nS) {
 }
 
 static int run_join(gj_ctx* ctx, Rel R, Rel S, bool mat, int32_t* out_Rp, int32_t* out_Sp, uint64_t cap,
-                    uint64_t* matches, uint64_t* checksum, uint64_t* n_pairs, gj_timings* t) {
+                    uint64_t* matches, uint64_t* checksum, uint64_t* n_pairs, gj_timings* t,
+                    const LateCols* late = nullptr) {
     const auto w0 = std::chrono::steady_clock::now();
     if (t) memset(t, 0, sizeof(*t));
     if (matches) *matches = 0;
@@ -843,7 +859,7 @@ static int run_join(gj_ctx* ctx, Rel R, Rel S, bool mat, int32_t* out_Rp, int32_
     }
     CK(cudaEventRecord(ctx->ev[2], s));
     if ((rc = enqueue_join(ctx, s, ctx->out[bld.slot], ctx->out[prb.slot], pl, bld.n, prb.n, mat,
-                           swap ? out_Sp : out_Rp, swap ? out_Rp : out_Sp, cap, num_units))) return rc;
+                           swap ? out_Sp : out_Rp, swap ? out_Rp : out_Sp, cap, num_units, -1, late, swap))) return rc;
     CK(cudaEventRecord(ctx->ev[3], s));
     CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -902,6 +918,27 @@ extern "C" int gj_join_materialize(gj_ctx* ctx, const int32_t* d_Rk, const int32
     if (rc == GJ_OK && n_pairs && *n_pairs != m)
         return fail(GJ_ERR_STATE, "internal: pairs reserved (%llu) != matches (%llu)", (unsigned long long)*n_pairs, (unsigned long long)m);
     return rc;
+}
+
+// Late materialisation (reference join_partitioned_varpayload,
+// join-primitives.cu:1420-1557, driver outOfGPU_Join_payload_var, hash_join_clustered_probe.cu:542-708)
+extern "C" int gj_join_aggregate_late(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rid, uint64_t nR,
+                                      const int32_t* d_Sk, const int32_t* d_Sid, uint64_t nS,
+                                      const int32_t* d_Dr, uint32_t cols_r, uint64_t stride_r,
+                                      const int32_t* d_Ds, uint32_t cols_s, uint64_t stride_s,
+                                      uint64_t* matches, uint64_t* sum, gj_timings* t) {
+    int rc = check_caps(ctx, nR, nS);
+    if (rc) return rc;
+    if ((nR && (!d_Rk || !d_Rid)) || (nS && (!d_Sk || !d_Sid))) return fail(GJ_ERR_ARG, "NULL input column");
+    if ((cols_r && !d_Dr) || (cols_s && !d_Ds)) return fail(GJ_ERR_ARG, "NULL side table with a non-zero column count");
+    if (cols_r > 64 || cols_s > 64) return fail(GJ_ERR_ARG, "at most 64 side-table columns per relation");
+    Rel R, S;
+    R.keys = d_Rk; R.pays = d_Rid; R.n = nR; R.slot = 0;
+    S.keys = d_Sk; S.pays = d_Sid; S.n = nS; S.slot = 1;
+    LateCols late;
+    late.cols[0] = d_Dr; late.ncols[0] = cols_r; late.stride[0] = stride_r;
+    late.cols[1] = d_Ds; late.ncols[1] = cols_s; late.stride[1] = stride_s;
+    return run_join(ctx, R, S, false, nullptr, nullptr, 0, matches, sum, nullptr, t, &late);
 }
 
 // ------------------------------------------------------------------------------------------

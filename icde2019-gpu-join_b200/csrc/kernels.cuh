@@ -995,7 +995,23 @@ struct JoinArgs {
     uint32_t hash_shift;
     unsigned long long* result;   // [0] matches [1] checksum [2] pairs reserved (materialise)
     int32_t* out_bld_pay; int32_t* out_prb_pay; unsigned long long cap;
+    // LATE (late materialisation, join_partitioned_varpayload, join-primitives.cu:1420-1557): payloads are row
+    // ids into column-major side tables; a result pair adds cols[z * stride + id] of both sides
+    const int32_t* bld_cols; const int32_t* prb_cols;
+    uint32_t ncols_bld, ncols_prb;
+    unsigned long long stride_bld, stride_prb;
 };
+
+// what one result pair contributes to the aggregate: the payload product (reference
+// join-primitives.cu:1073) or, LATE, the gathered side-table values (:1531-1536)
+template <bool LATE>
+__device__ __forceinline__ unsigned long long pair_value(const JoinArgs& a, uint32_t bld_pay, uint32_t prb_pay) {
+    if (!LATE) return (unsigned long long)((long long)(int32_t)bld_pay * (long long)(int32_t)prb_pay);
+    long long v = 0;
+    for (uint32_t z = 0; z < a.ncols_bld; ++z) v += (long long)__ldg(a.bld_cols + (size_t)z * a.stride_bld + bld_pay);
+    for (uint32_t z = 0; z < a.ncols_prb; ++z) v += (long long)__ldg(a.prb_cols + (size_t)z * a.stride_prb + prb_pay);
+    return (unsigned long long)v;
+}
 
 constexpr int JOIN_STAGE_PAIRS = 2048;   // staged result pairs per CTA (materialise)
 constexpr uint32_t STEP_DONE = 0xFFFFFFFFu;
@@ -1017,9 +1033,10 @@ struct JoinSmem {
     static constexpr size_t total = off_bar + (size_t)(NS + NR) * 16;   // full + empty barriers
 };
 
-template <int THREADS, int CAP, int U, int NR, int NS, bool MATERIALIZE, bool OPTIMISTIC>
+template <int THREADS, int CAP, int U, int NR, int NS, bool MATERIALIZE, bool OPTIMISTIC, bool LATE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 join_kernel(JoinArgs a) {
+    static_assert(!(LATE && MATERIALIZE), "late materialisation aggregates");
     using L = JoinSmem<CAP, U, NR, NS, MATERIALIZE>;
     static_assert(CAP < 0xFFFF, "16-bit entry indices");
     constexpr uint32_t NC = THREADS - 32;      // consumer threads: warps 0 .. THREADS/32-2
@@ -1225,14 +1242,14 @@ join_kernel(JoinArgs a) {
                     if ((w[q] & HEAD_VER_MASK) == ver) {
                         if (r[q].x == t[q].x) {
                             ++m32;
-                            sum += (unsigned long long)((long long)(int32_t)r[q].y * (long long)(int32_t)t[q].y);
+                            sum += pair_value<LATE>(a, r[q].y, t[q].y);
                         }
                         if (w[q] & HEAD_MULTI) {
                             for (uint32_t i = next[w[q] & 0xFFFFu]; i != 0xFFFFu; i = next[i]) {
                                 const tup_t rr = rbuf[i];
                                 if (rr.x == t[q].x) {
                                     ++m32;
-                                    sum += (unsigned long long)((long long)(int32_t)rr.y * (long long)(int32_t)t[q].y);
+                                    sum += pair_value<LATE>(a, rr.y, t[q].y);
                                 }
                             }
                         }
@@ -1252,7 +1269,7 @@ join_kernel(JoinArgs a) {
                         const tup_t r = rbuf[i];
                         if (r.x == t.x) {
                             ++matches;
-                            sum += (unsigned long long)((long long)(int32_t)r.y * (long long)(int32_t)t.y);
+                            sum += pair_value<false>(a, r.y, t.y);
                             const uint32_t pos = atomicAdd(&s_cnt, 1u);
                             if (pos < (uint32_t)JOIN_STAGE_PAIRS) {
                                 s_out_b[pos] = (int32_t)r.y;

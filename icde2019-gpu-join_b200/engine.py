@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 C_ABI_SYMBOLS = [
     "gj_create", "gj_destroy", "gj_last_error", "gj_version", "gj_set_stream", "gj_set_option",
     "gj_get_option", "gj_join_aggregate", "gj_join_aggregate_tuples", "gj_join_aggregate_host",
-    "gj_join_materialize", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
+    "gj_join_materialize", "gj_join_aggregate_late", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
     "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_stage_pass_ms", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
     "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv", "gj_pcp_join",
@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
     L.gj_join_aggregate_host.argtypes = L.gj_join_aggregate.argtypes
     L.gj_join_aggregate_tuples.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_join_materialize.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, i32p, i32p, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
+    L.gj_join_aggregate_late.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, i32p, u32, u64, i32p, u32, u64,
+                                         C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_partition.argtypes = [vp, C.c_int, i32p, i32p, u64, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u32), C.POINTER(Timings)]
     L.gj_shuffle_split.argtypes = [vp, i32p, i32p, u64, u32, u32, vp, C.POINTER(u64)]
     L.gj_shuffle_scatter_peers.argtypes = [vp, i32p, i32p, u64, u32, u32, C.POINTER(vp), C.POINTER(u64)]
@@ -271,6 +273,27 @@ class JoinEngine:
                                            _dev_ptr(out_Rp, cap, "out_Rp"), _dev_ptr(out_Sp, cap, "out_Sp"), cap,
                                            C.byref(n), C.byref(c), C.byref(t)))
         return int(n.value), JoinResult(int(n.value), int(c.value), t)
+
+    def join_aggregate_late(self, Rk, Rid, Sk, Sid, Dr, Ds) -> JoinResult:
+        """Late materialisation: Rid / Sid are row ids into the column-major side tables Dr / Ds (int32
+        CUDA tensors of shape [cols, rows], possibly with zero columns).  `checksum` of the result is the
+        sum over result pairs of all side-table values of both rows."""
+        self._sync_inputs()
+        nR, nS = Rk.numel(), Sk.numel()
+
+        def side(D, what):
+            if D is None or D.numel() == 0:
+                return C.c_void_p(0), 0, 0
+            if D.dim() != 2 or not D.is_contiguous():
+                raise TypeError(f"{what}: expected a contiguous [cols, rows] tensor")
+            return _dev_ptr(D, None, what), D.shape[0], D.shape[1]
+        pr, cr, sr = side(Dr, "Dr")
+        ps, cs, ss = side(Ds, "Ds")
+        m, c, t = C.c_uint64(), C.c_uint64(), Timings()
+        _check(self._L.gj_join_aggregate_late(self._ctx, _dev_ptr(Rk, nR, "Rk"), _dev_ptr(Rid, nR, "Rid"), nR,
+                                              _dev_ptr(Sk, nS, "Sk"), _dev_ptr(Sid, nS, "Sid"), nS,
+                                              pr, cr, sr, ps, cs, ss, C.byref(m), C.byref(c), C.byref(t)))
+        return JoinResult(int(m.value), int(c.value), t)
 
     # -- partitioner ----------------------------------------------------------------------
     def partition(self, keys, pays, radix_bits: int = 0, slot: int = 0):

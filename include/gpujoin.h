@@ -114,6 +114,20 @@ int gj_join_materialize(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, u
                         int32_t* d_out_Sp, uint64_t cap, uint64_t* n_pairs, uint64_t* checksum,
                         gj_timings* t);
 
+/* Late-materialisation join (replaces join_partitioned_varpayload,
+ * join-primitives.cu:1420-1557, and its driver outOfGPU_Join_payload_var,
+ * hash_join_clustered_probe.cu:542-708): the payload columns d_Rid / d_Sid hold ROW IDS into
+ * column-major side tables, value of column z for row id i = d_Dr[z * stride_r + i] (the reference's
+ * Dr[pval + z*rel_size], :1531-1536).  Every result pair adds the cols_r values of its R row and the
+ * cols_s values of its S row to the aggregate: *sum = that total as int64 mod 2^64, whose low 32 bits are
+ * the int32 the reference accumulates (:1460, 1552).  Row ids must lie in [0, stride); at most 64 columns
+ * per side.  Same pipeline as gj_join_aggregate; the gathers hit L2 when the side tables fit its 126 MB. */
+int gj_join_aggregate_late(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rid, uint64_t nR,
+                           const int32_t* d_Sk, const int32_t* d_Sid, uint64_t nS,
+                           const int32_t* d_Dr, uint32_t cols_r, uint64_t stride_r,
+                           const int32_t* d_Ds, uint32_t cols_s, uint64_t stride_s,
+                           uint64_t* matches, uint64_t* sum, gj_timings* t);
+
 /* ---- the partitioner on its own --------------------------------------------------------------
  * Replaces prepare_Relation_payload (join-primitives.cu:1582-1613: init_metadata_double,
  * partition_pass_one, compute_bucket_info, partition_pass_two).  Partitions one relation on its

@@ -57,6 +57,8 @@ def _load() -> C.CDLL:
     lib.orc_join_materialize.restype = C.c_uint64
     lib.orc_pairs_hash.argtypes = [_i32p, _i32p, C.c_uint64]
     lib.orc_pairs_hash.restype = C.c_uint64
+    lib.orc_late_sum.argtypes = [_i32p, _i32p, C.c_uint64, _i32p, C.c_uint32, C.c_uint64, _i32p, C.c_uint32, C.c_uint64]
+    lib.orc_late_sum.restype = C.c_uint64
     lib.orc_partition.argtypes = [_i32p, _i32p, C.c_uint64, C.c_uint32, C.c_uint32, _u64p, _i32p, _i32p]
     lib.orc_partition_fingerprint.argtypes = [_i32p, _i32p, C.c_uint64, C.c_uint32, C.c_uint32, _u64p, _u64p]
     lib.orc_max_threads.restype = C.c_int
@@ -167,6 +169,22 @@ def join_materialize(Rk, Rp, Sk, Sp, cap: int, threads: int = 0):
                                    orp, osp, cap, out)
     k = min(int(n), cap)
     return int(n), orp[:k], osp[:k], JoinResult(int(x) for x in out)
+
+
+def join_late(Rk, Rid, Sk, Sid, Dr, Ds, threads: int = 0):
+    """Late-materialisation join on the CPU (reference join_partitioned_varpayload,
+    join-primitives.cu:1420-1557): joins (key, row id) relations with the checker, then adds, for every
+    result pair, all side-table values of both rows.  Dr / Ds: int32 arrays [cols, rows] (cols may be
+    0).  Returns (matches, sum mod 2^64)."""
+    cap = max(1, int(join_check(Rk, Rid, Sk, Sid, threads).matches))
+    n, rid, sid, _ = join_materialize(Rk, Rid, Sk, Sid, cap, threads)
+    assert n <= cap
+    Dr = np.ascontiguousarray(Dr, dtype=np.int32).reshape(len(Dr), -1) if len(Dr) else np.zeros((0, 1), np.int32)
+    Ds = np.ascontiguousarray(Ds, dtype=np.int32).reshape(len(Ds), -1) if len(Ds) else np.zeros((0, 1), np.int32)
+    dr = Dr.reshape(-1) if Dr.size else np.zeros(1, np.int32)
+    ds = Ds.reshape(-1) if Ds.size else np.zeros(1, np.int32)
+    total = lib().orc_late_sum(_c(rid), _c(sid), int(n), dr, Dr.shape[0], Dr.shape[1], ds, Ds.shape[0], Ds.shape[1])
+    return int(n), int(total)
 
 
 def pairs_hash(rp, sp) -> int:

@@ -421,6 +421,22 @@ uint64_t orc_join_materialize(const int32_t *Rk, const int32_t *Rp, uint64_t nR,
 }
 
 /* Fingerprint of an explicit pair list (used on device-materialised output). */
+/* Late materialisation (reference join_partitioned_varpayload, join-primitives.cu:1420-1557): the join's
+ * payloads are row ids; for every result pair the reference adds Dr[pval + z*rel_size] for z < col_num1
+ * and Ds[bval + z*rel_size] for z < col_num2 (:1531-1536) into an int32 (:1460, 1552).  Here: the same sum
+ * over already materialised (R row id, S row id) pairs, widened to int64 mod 2^64 (its low 32 bits are the
+ * reference's value). */
+uint64_t orc_late_sum(const int32_t *rid, const int32_t *sid, uint64_t npairs, const int32_t *Dr,
+                      uint32_t cols_r, uint64_t stride_r, const int32_t *Ds, uint32_t cols_s,
+                      uint64_t stride_s) {
+    uint64_t sum = 0;
+    for (uint64_t i = 0; i < npairs; ++i) {
+        for (uint32_t z = 0; z < cols_r; ++z) sum += (uint64_t)(int64_t)Dr[(uint64_t)z * stride_r + (uint64_t)(uint32_t)rid[i]];
+        for (uint32_t z = 0; z < cols_s; ++z) sum += (uint64_t)(int64_t)Ds[(uint64_t)z * stride_s + (uint64_t)(uint32_t)sid[i]];
+    }
+    return sum;
+}
+
 uint64_t orc_pairs_hash(const int32_t *rp, const int32_t *sp, uint64_t n) {
     uint64_t h = 0;
 #pragma omp parallel for reduction(+ : h)

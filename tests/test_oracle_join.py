@@ -108,3 +108,25 @@ def test_partition_oracle(orc, shift, bits):
     cnt, hsh = orc.partition_fingerprint(k, p, shift, bits)
     cnt2, hsh2 = orc.partition_fingerprint(ko, po, shift, bits)
     assert np.array_equal(cnt, cnt2) and np.array_equal(hsh, hsh2)
+
+
+def test_late_materialisation_oracle_against_brute_force(orc):
+    """oracle.join_late (restating join_partitioned_varpayload, join-primitives.cu:1420-1557: payload = row id,
+    side-table values of both rows added per result pair) against a numpy nested loop; N:M keys,
+    negative values, zero columns on either side."""
+    rng = np.random.default_rng(12)
+    nR, nS = 2500, 4000
+    Rk = rng.integers(-300, 300, nR).astype(np.int32)
+    Sk = rng.integers(-300, 300, nS).astype(np.int32)
+    Rid, Sid = rng.permutation(nR).astype(np.int32), rng.permutation(nS).astype(np.int32)
+    Dr = rng.integers(-2**31, 2**31, (3, nR)).astype(np.int32)
+    Ds = rng.integers(-2**31, 2**31, (2, nS)).astype(np.int32)
+    ri, si = np.nonzero(Rk[:, None] == Sk[None, :])
+    for dr, ds in ((Dr, Ds), (Dr[:0], Ds), (Dr, Ds[:0]), (Dr[:1], Ds[:1])):
+        want = (int(dr[:, Rid[ri]].astype(object).sum()) + int(ds[:, Sid[si]].astype(object).sum())) % (1 << 64)
+        n, tot = orc.join_late(Rk, Rid, Sk, Sid, dr, ds)
+        assert n == len(ri) and tot == want
+    # the reference accumulates an int32 (:1460): its value is the low 32 bits of ours
+    n, tot = orc.join_late(Rk, Rid, Sk, Sid, Dr, Ds)
+    ref32 = (Dr[:, Rid[ri]].astype(np.int64).sum() + Ds[:, Sid[si]].astype(np.int64).sum()) & 0xFFFFFFFF
+    assert tot & 0xFFFFFFFF == int(ref32)
