@@ -3,8 +3,16 @@
 # usage: gpurun --gpus N -- 'bash tools/gpu_round2_multi.sh N'     (N = 2, 4 or 8)
 #   1. parity of every exchange mode on N real GPUs
 #   2. pcp / pp / p2p on workload B (weak) and, at N = 8, config 5 (strong)
-#   3. why kernels running under the pcp copy kernel are slowed 2.6-3.8x:
-#      copy-kernel grid (shuffle_grid), L2 evict-first policy (pcp_l2_hint), source-side bits (pass1_bits)
+#   3. why kernels running under the pcp copy kernel are slowed 2.6-3.8x at 8 GPUs (1.5x at 2 GPUs)
+#      (source pass of S 1.25 ms instead of 0.48; receiver pass of R 2.26 ms instead of ~0.6).  Hypotheses and
+#      the knob that tests each:
+#        H1 the copy's streaming traffic + incoming peer writes evict the scatter's partially written lines
+#           from L2 (the 8-byte-store scatter relies on L2 merging)            -> pcp_l2_hint=1
+#        H2 the copy CTAs' 68 KB of shared memory per SM lower the occupancy of the passes next to them
+#                                                                                -> shuffle_grid=74 / 296
+#        H3 page-walk contention: a 512-way scatter touches 512 x 2 MB pages (TLB reach 128 pages) while the
+#           NVLink ingress of 7 peers translates too                           -> pass1_bits=8 / 10 (256- / 1024-way)
+#      HBM bandwidth itself is not the limit: copy traffic is ~1.5 TB/s of 6.5.
 cd "$(dirname "$0")/.."
 N=${1:-8}
 OUT=gpurun_out; mkdir -p $OUT
