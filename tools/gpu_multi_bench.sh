@@ -1,5 +1,6 @@
 #!/bin/bash
-# NVLink store experiments on N GPUs: bench lines for a list of "mode:opts" specs (opts = comma separated name=value)
+# Bench lines on N GPUs for a list of "mode:opts" specs (opts = comma separated: name=value engine options,
+# no-overlap, workload=W, steps=K).  usage: gpurun --gpus N -- 'bash tools/gpu_multi_bench.sh N "pcp:" "p2p:steps=5,workload=cfg5"'
 cd "$(dirname "$0")/.."
 N=${1:-2}; shift
 OUT=gpurun_out; mkdir -p $OUT
@@ -18,7 +19,7 @@ for spec in "$@"; do
       *) args="$args --opt $kv" ;;
     esac
   done
-  f=$OUT/pp3_${N}gpu_${i}_$m.log
+  f=$OUT/mb_${N}gpu_${i}_$m.log
   echo "### $spec" > $f
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$i \
       bench.py --gpus $N --steps 6 --warmup 3 --shuffle $m $args >> $f 2>&1
