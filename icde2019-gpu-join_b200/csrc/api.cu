@@ -232,6 +232,8 @@ struct gj_ctx {
         cudaEvent_t ev[2][6] = {};           // per relation: part begin/end, copy begin/end, recv begin/end
         cudaEvent_t jev[2] = {};
     } pcp;
+    // non-partitioned baseline: chained table in global memory (allocated on first use)
+    struct NP { uint32_t* heads = nullptr; uint32_t* next = nullptr; uint64_t heads_cap = 0, next_cap = 0; } np;
     unsigned char* zero_role[2] = {nullptr, nullptr};
     unsigned char* zero_common = nullptr;
     size_t zero_role_bytes = 0, zero_common_bytes = 0;
@@ -300,6 +302,7 @@ extern "C" void gj_destroy(gj_ctx* ctx) {
     cudaFree(ctx->p3.block); cudaFree(ctx->p3.zero);
     cudaFree(ctx->pp.block);
     cudaFree(ctx->pcp.block);
+    cudaFree(ctx->np.heads); cudaFree(ctx->np.next);
     if (ctx->pcp.h_pin) cudaFreeHost(ctx->pcp.h_pin);
     for (auto& r : ctx->pcp.ev) for (auto& e : r) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->pcp.jev) if (e) cudaEventDestroy(e);
@@ -939,6 +942,64 @@ extern "C" int gj_join_aggregate_late(gj_ctx* ctx, const int32_t* d_Rk, const in
     late.cols[0] = d_Dr; late.ncols[0] = cols_r; late.stride[0] = stride_r;
     late.cols[1] = d_Ds; late.ncols[1] = cols_s; late.stride[1] = stride_s;
     return run_join(ctx, R, S, false, nullptr, nullptr, 0, matches, sum, nullptr, t, &late);
+}
+
+// Non-partitioned baseline (reference build_ht_chains / chains_probing,
+// join-primitives.cu:681-742): memset of the heads + build + probe, no radix pass.
+extern "C" int gj_join_aggregate_nopart(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
+                                        const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS,
+                                        uint64_t* matches, uint64_t* checksum, gj_timings* t) {
+    const auto w0 = std::chrono::steady_clock::now();
+    int rc = check_caps(ctx, nR, nS);
+    if (rc) return rc;
+    if ((nR && (!d_Rk || !d_Rp)) || (nS && (!d_Sk || !d_Sp))) return fail(GJ_ERR_ARG, "NULL input column");
+    if (t) memset(t, 0, sizeof(*t));
+    if (matches) *matches = 0;
+    if (checksum) *checksum = 0;
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    if (!nR || !nS) return GJ_OK;
+    const bool swap = nR > nS;     // build on the smaller relation
+    const int32_t* bk = swap ? d_Sk : d_Rk; const int32_t* bp = swap ? d_Sp : d_Rp;
+    const int32_t* pk = swap ? d_Rk : d_Sk; const int32_t* pp = swap ? d_Rp : d_Sp;
+    const uint64_t nb = swap ? nS : nR, np = swap ? nR : nS;
+    uint32_t hb = 4;
+    while (hb < 31 && (1ull << hb) < 2 * nb) ++hb;    // load factor <= 1/2
+    gj_ctx::NP& q = ctx->np;
+    if (q.heads_cap < (1ull << hb)) {
+        cudaFree(q.heads); q.heads = nullptr; q.heads_cap = 0;
+        if (cudaMalloc(&q.heads, sizeof(uint32_t) << hb) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "hash-table heads (%.1f MB)", (4ull << hb) * 1e-6); }
+        q.heads_cap = 1ull << hb;
+    }
+    if (q.next_cap < nb) {
+        cudaFree(q.next); q.next = nullptr; q.next_cap = 0;
+        if (cudaMalloc(&q.next, nb * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "hash-table links"); }
+        q.next_cap = nb;
+    }
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->zero_common, 0, ctx->zero_common_bytes, s));
+    CK(cudaEventRecord(ctx->ev[0], s));
+    CK(cudaMemsetAsync(q.heads, 0, sizeof(uint32_t) << hb, s));
+    const uint32_t gb = (uint32_t)std::min<uint64_t>((nb + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    np_build_kernel<<<gb, 256, 0, s>>>(bk, (uint32_t)nb, hb, q.heads, q.next);
+    LAUNCHED();
+    CK(cudaEventRecord(ctx->ev[2], s));
+    const uint32_t gp = (uint32_t)std::min<uint64_t>((np + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    np_probe_kernel<<<gp, 256, 0, s>>>(bk, bp, q.heads, q.next, hb, pk, pp, (uint32_t)np, ctx->result);
+    LAUNCHED();
+    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (matches) *matches = ctx->h_result[0];
+    if (checksum) *checksum = ctx->h_result[1];
+    if (t) {
+        CK(cudaEventElapsedTime(&t->hist_ms, ctx->ev[0], ctx->ev[2]));   // "hist" slot: table clear + build
+        CK(cudaEventElapsedTime(&t->join_ms, ctx->ev[2], ctx->ev[3]));   // probe
+        CK(cudaEventElapsedTime(&t->total_ms, ctx->ev[0], ctx->ev[3]));
+        t->kernel_launches = ctx->launches;
+        t->wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    }
+    return GJ_OK;
 }
 
 // ------------------------------------------------------------------------------------------

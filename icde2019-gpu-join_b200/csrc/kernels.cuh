@@ -1342,6 +1342,56 @@ join_kernel(JoinArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// 5b. Non-partitioned baseline (reference build_ht_chains / chains_probing,
+//     join-primitives.cu:681-742): one chained hash table over the whole build side in global
+//     memory -- heads[h] = index + 1 of the newest entry (0 = empty, so a memset clears it),
+//     next[i] = its predecessor -- probed straight from the probe columns.  No radix pass at
+//     all: 3 launches; on B200 a build side of a few million tuples keeps heads + columns in the
+//     126 MB L2, which is the regime where this beats partitioning (config 1).
+//     Hash = xor-fold to hb bits: the identity on dense keys below 2^hb (the reference masks).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t np_hash(uint32_t key, uint32_t hb) { return (key ^ (key >> hb)) & ((1u << hb) - 1u); }
+
+__global__ void __launch_bounds__(256)
+np_build_kernel(const int32_t* __restrict__ keys, uint32_t n, uint32_t hb, uint32_t* __restrict__ heads,
+                uint32_t* __restrict__ next) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t old = atomicExch(&heads[np_hash((uint32_t)__ldg(keys + i), hb)], i + 1u);
+        next[i] = old;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+np_probe_kernel(const int32_t* __restrict__ bk, const int32_t* __restrict__ bp, const uint32_t* __restrict__ heads,
+                const uint32_t* __restrict__ next, uint32_t hb, const int32_t* __restrict__ pk,
+                const int32_t* __restrict__ pp, uint32_t n, unsigned long long* __restrict__ result) {
+    __shared__ unsigned long long s_red[2][8];
+    unsigned long long matches = 0, sum = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int32_t key = __ldg(pk + j), pay = __ldg(pp + j);
+        for (uint32_t e = heads[np_hash((uint32_t)key, hb)]; e != 0u; e = next[e - 1u]) {
+            if (bk[e - 1u] == key) {
+                ++matches;
+                sum += (unsigned long long)((long long)bp[e - 1u] * (long long)pay);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        matches += __shfl_xor_sync(0xffffffffu, matches, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31u) == 0) { s_red[0][threadIdx.x >> 5] = matches; s_red[1][threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = 0, s = 0;
+        for (int w = 0; w < 8; ++w) { m += s_red[0][w]; s += s_red[1][w]; }
+        if (m) atomicAdd(&result[0], m);
+        if (s) atomicAdd(&result[1], s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // 6. Synthetic unique relations: key = seeded bijection of the row id.
 // ------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {

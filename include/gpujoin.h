@@ -128,6 +128,16 @@ int gj_join_aggregate_late(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Ri
                            const int32_t* d_Ds, uint32_t cols_s, uint64_t stride_s,
                            uint64_t* matches, uint64_t* sum, gj_timings* t);
 
+/* Non-partitioned baseline (replaces build_ht_chains / chains_probing,
+ * join-primitives.cu:681-742): one chained hash table over the whole build side in global memory, probed
+ * straight from the probe columns -- no radix pass, 3 launches.  Same result as gj_join_aggregate.  The
+ * comparison point for the partitioned path: on B200 a build side whose table (8 B of heads + 4 B of links
+ * + 8 B of columns per tuple) stays in the 126 MB L2 is the regime where it wins (config 1).
+ * timings: hist_ms = table clear + build, join_ms = probe. */
+int gj_join_aggregate_nopart(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
+                             const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS,
+                             uint64_t* matches, uint64_t* checksum, gj_timings* t);
+
 /* ---- the partitioner on its own --------------------------------------------------------------
  * Replaces prepare_Relation_payload (join-primitives.cu:1582-1613: init_metadata_double,
  * partition_pass_one, compute_bucket_info, partition_pass_two).  Partitions one relation on its

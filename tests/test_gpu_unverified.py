@@ -1,9 +1,12 @@
-"""Late-materialisation join through the C ABI against the oracle's
-restatement of join_partitioned_varpayload (join-primitives.cu:1420-1557).
+"""SURVEY.md section 8f rows started at the end of round 1, through the C ABI against the oracle:
+  * late-materialisation join (rank 1): gj_join_aggregate_late vs oracle.join_late, the restatement of
+    join_partitioned_varpayload (join-primitives.cu:1420-1557);
+  * non-partitioned baseline (rank 4): gj_join_aggregate_nopart (build_ht_chains / chains_probing,
+    join-primitives.cu:681-742) vs the oracle's join checker.
 
-NOT YET RUN ON A GPU: the kernel variant (join_kernel<..., LATE>), gj_join_aggregate_late and these tests
-were written after round 1's GPU budget was spent.  They are skipped unless GJ_RUN_UNVERIFIED=1 so that an
-untested path cannot turn the suite red; the first GPU run is queued in tools/gpu_round2_single.sh."""
+NOT YET RUN ON A GPU: these kernels, entry points and tests were written after round 1's GPU budget was
+spent.  They are skipped unless GJ_RUN_UNVERIFIED=1 so that an untested path cannot turn the suite red;
+the first GPU run is queued in tools/gpu_round2_single.sh."""
 import os
 
 import numpy as np
@@ -48,3 +51,23 @@ def test_late_materialisation_matches_oracle(gj, orc, torch_cuda, nR, nS, keys, 
         # with the payload product instead, the same engine still gives the plain aggregate
         plain = eng.join_aggregate(dRk, dRid, dSk, dSid)
         assert plain.matches == want_n
+
+
+@pytest.mark.parametrize("nR,nS,lo,hi", [(1 << 20, 1 << 20, 0, 1 << 20), (300_000, 700_000, -(1 << 17), 1 << 17),
+                                         (700_000, 300_000, 0, 1 << 30), (5, 1_000_000, 0, 4), (1, 1, 7, 8), (0, 10, 0, 4)])
+def test_nonpartitioned_baseline_matches_oracle(gj, orc, torch_cuda, nR, nS, lo, hi):
+    """Global chained hash table, no radix pass: same matches / checksum as the oracle (and as the
+    partitioned path); dense, sparse, signed, heavily duplicated keys; build side on R or on S."""
+    rng = np.random.default_rng(nR + 7 * nS)
+    Rk = rng.integers(lo, hi, nR).astype(np.int32)
+    Sk = rng.integers(lo, hi, nS).astype(np.int32)
+    Rp = rng.integers(-2**31, 2**31, nR).astype(np.int32)
+    Sp = rng.integers(-2**31, 2**31, nS).astype(np.int32)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    with gj.JoinEngine(max(nR, 1), max(nS, 1), 0) as eng:
+        d = dev(torch_cuda, Rk, Rp, Sk, Sp)
+        got = eng.join_aggregate_nopart(*d)
+        assert (got.matches, got.checksum) == (want.matches, want.checksum)
+        assert got.timings.kernel_launches == (2 if nR and nS else 0)
+        part = eng.join_aggregate(*d)
+        assert (part.matches, part.checksum) == (want.matches, want.checksum)
