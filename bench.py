@@ -524,7 +524,7 @@ def multi_gpu(args):
                                      "algorithmic_bytes_per_launch": 16.0 * r.local_S, "avg_launch_ms": sum(ps) / len(ps),
                                      "local_phases_ms": {"scatter_R_pass1": tm["pass_ms"][0], "scatter_R_pass2": tm["pass_ms"][1],
                                                          "scatter_S_pass1": tm["pass_ms"][2], "scatter_S_pass2": tm["pass_ms"][3]}})
-        if args.shuffle == "pcp" and tm.get("part_R_ms"):
+        if args.shuffle in ("pcp", "pcp2") and tm.get("part_R_ms"):
             line["roofline"].update({"kernel": "pcp source-side radix pass of R (layout + first pass, 16 B/tuple), rank 0",
                                      "achieved": 16.0 * nR / (tm["part_R_ms"] * 1e-3) / 1e9, "algorithmic_bytes_per_launch": 16.0 * nR,
                                      "local_phases_ms": {k: tm.get(k) for k in ("part_R_ms", "copy_R_ms", "recv_R_ms", "part_S_ms", "copy_S_ms", "recv_S_ms", "join_ms")}})
@@ -552,6 +552,7 @@ def multi_gpu(args):
         line["config"].update({"global_R": NR, "global_S": NS, "parallelism": f"radix-sharded over {world} GPUs, {args.shuffle} shuffle"
                                + (", R's push overlapped with S's local pass" if args.shuffle == "pp" else
                                   ", R's copy under S's first pass, S's copy under R's last pass" if args.shuffle == "pcp" else
+                                  ", probe side split in two halves, first half joined under the second half's copy" if args.shuffle == "pcp2" else
                                   "" if args.no_overlap or args.shuffle != "p2p" else ", S shuffle overlapped with R's local passes")})
         print(json.dumps(line))
     sj.close()
@@ -565,7 +566,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--shuffle", default="auto", choices=["auto", "p2p", "nccl", "dma", "pp", "pcp"],
+    ap.add_argument("--shuffle", default="auto", choices=["auto", "p2p", "nccl", "dma", "pp", "pcp", "pcp2"],
                     help="multi-GPU exchange: pp = partition locally, last radix pass pushes into the peers; p2p = peer-store "
                          "shuffle first, local passes at the receiver; pcp = first radix pass at the source, whole first-pass partitions "
                          "bulk-copied over NVLink, last pass at the receiver; auto = pcp (measured best, profiles/README.md)")

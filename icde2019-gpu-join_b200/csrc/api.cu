@@ -1842,6 +1842,55 @@ extern "C" int gj_pcp_join(gj_ctx* ctx, uint64_t cap_R, uint64_t cap_S, void* cu
     return GJ_OK;
 }
 
+// Join this context's BUILD partitions (relation 0 of its pcp run, already received and partitioned)
+// with a probe relation that a SECOND context on the same GPU received and partitioned (its pcp
+// relation `probe_which`).  Lets the host split the probe side in two halves that travel and are
+// partitioned independently: the join of the first half (gj_pcp_join) runs under the copy of the
+// second, this call then adds the second half's result to the same accumulators.
+extern "C" int gj_pcp_join_ext(gj_ctx* ctx, gj_ctx* probe_ctx, int probe_which, uint64_t cap_build,
+                               uint64_t cap_probe, void* cuda_stream) {
+    if (!ctx || !probe_ctx || !ctx->pcp.active || !probe_ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first (both contexts)");
+    if (probe_which != 0 && probe_which != 1) return fail(GJ_ERR_ARG, "probe_which must be 0 or 1");
+    gj_ctx::PCP& q = ctx->pcp;
+    const gj_ctx::PCP& pq = probe_ctx->pcp;
+    if (ctx->device != probe_ctx->device) return fail(GJ_ERR_ARG, "both contexts must live on the same GPU");
+    if (q.B != pq.B || q.g != pq.g || q.rank != pq.rank) return fail(GJ_ERR_ARG, "the two contexts run different plans");
+    if (q.role_of_side[0] != 0) return fail(GJ_ERR_ARG, "relation 0 of the building context must be its build side (pass the smaller relation first)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaStreamWaitEvent(s, ctx->stage_ev[3], 0));
+    const int prole = pq.role_of_side[probe_which];
+    const RelMeta& mb = ctx->meta[0];
+    const RelMeta& mp = probe_ctx->meta[prole];
+    Plan pl; pl.B = q.B; pl.b1 = q.B; pl.b2 = 0;
+    const uint32_t nb = 1u << pl.B;
+    // re-arm the unit scan (descriptors + ticket); the result accumulators behind them keep counting
+    const size_t res_off = (size_t)(reinterpret_cast<unsigned char*>(ctx->result) - ctx->zero_common);
+    CK(cudaMemsetAsync(ctx->zero_common, 0, res_off, s));
+    ScanSeq su;
+    su.in = mb.ghist; su.in2 = mp.ghist; su.out = ctx->unit_base; su.desc = ctx->unit_desc; su.ticket = ctx->unit_ticket;
+    su.mode = SCAN_UNITS; su.param = unit_tuples(ctx); su.param2 = 0;
+    int rc;
+    if ((rc = enqueue_scan_one(ctx, s, su, nb))) return rc;
+    PlanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rel[0].off = mb.off; a.rel[1].off = mp.off;
+    a.nrel = 0; a.with_units = 1; a.b1 = pl.B; a.b2 = 0; a.tile = 4096; a.unit = unit_tuples(ctx);
+    a.unit_base = ctx->unit_base; a.units = ctx->units;
+    plan_kernel<<<128, PLAN_THREADS, 0, s>>>(a);
+    LAUNCHED();
+    if ((rc = enqueue_join(ctx, s, ctx->out[0], probe_ctx->out[probe_which], pl, cap_build, cap_probe, false,
+                           nullptr, nullptr, 0, nullptr, (int)q.g))) return rc;
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[3], s));
+    // the probe context never joins: hand its status words to its own gj_pcp_finish
+    uint32_t* hs = reinterpret_cast<uint32_t*>(probe_ctx->pcp.h_pin + 2 * NB_MAX * sizeof(void*));
+    for (int i = 0; i < 4; ++i) hs[4 * (1 - probe_which) + i] = 0;
+    CK(cudaMemcpyAsync(hs + 4 * probe_which, pq.tab[probe_which].status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(probe_ctx->ev[3], s));
+    return GJ_OK;
+}
+
 extern "C" int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
                              uint64_t* n_local_S, float* phase_ms, uint32_t* plan_bits) {
     if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");

@@ -24,7 +24,7 @@ C_ABI_SYMBOLS = [
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
     "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_stage_pass_ms", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
     "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv", "gj_pcp_join",
-    "gj_pcp_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
+    "gj_pcp_join_ext", "gj_pcp_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
     "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_device_synchronize", "gj_flush_l2",
     "gj_kernel_launch_count",
@@ -119,6 +119,7 @@ def lib() -> C.CDLL:
     L.gj_pcp_copy.argtypes = [vp, C.c_int, C.POINTER(vp), vp]
     L.gj_pcp_recv.argtypes = [vp, C.c_int, vp, u64, vp]
     L.gj_pcp_join.argtypes = [vp, u64, u64, vp]
+    L.gj_pcp_join_ext.argtypes = [vp, vp, C.c_int, u64, u64, vp]
     L.gj_pcp_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(u32)]
     L.gj_generate_unique.argtypes = [vp, i32p, i32p, u64, u64, u64, u32, u32]
     L.gj_bijection.argtypes = [u64, u64, u32]
@@ -452,11 +453,14 @@ class JoinEngine:
     def pcp_join(self, cap_R: int, cap_S: int, stream=None):
         _check(self._L.gj_pcp_join(self._ctx, cap_R, cap_S, self._sptr(stream)))
 
-    def pcp_finish(self):
+    def pcp_join_ext(self, probe_engine, probe_which: int, cap_build: int, cap_probe: int, stream=None):
+        _check(self._L.gj_pcp_join_ext(self._ctx, probe_engine._ctx, probe_which, cap_build, cap_probe, self._sptr(stream)))
+
+    def pcp_finish(self, phases: bool = True):
         """Returns (matches, checksum, tuples received of R, of S, phase_ms dict, (gpu bits, source bits, receiver bits))."""
         m, c, a, b = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         ph, bits = (C.c_float * 7)(), (C.c_uint32 * 3)()
-        _check(self._L.gj_pcp_finish(self._ctx, C.byref(m), C.byref(c), C.byref(a), C.byref(b), ph, bits))
+        _check(self._L.gj_pcp_finish(self._ctx, C.byref(m), C.byref(c), C.byref(a), C.byref(b), ph if phases else None, bits))
         names = ("part_R_ms", "copy_R_ms", "recv_R_ms", "part_S_ms", "copy_S_ms", "recv_S_ms", "join_ms")
         return (int(m.value), int(c.value), int(a.value), int(b.value), dict(zip(names, (float(x) for x in ph))),
                 tuple(int(x) for x in bits))

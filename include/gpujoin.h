@@ -255,6 +255,14 @@ int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, uint64_t cap_tuples, 
 int gj_pcp_join(gj_ctx* ctx, uint64_t cap_R, uint64_t cap_S, void* cuda_stream);
 int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
                   uint64_t* n_local_S, float* phase_ms, uint32_t* plan_bits);
+/* Probe split: joins ctx's build partitions (relation 0 of its pcp run; must be its build side) with a
+ * probe relation that a SECOND context on the same GPU received and partitioned (relation probe_which of
+ * its pcp run, same n_gpus / rank / local_bits), adding to ctx's accumulators.  With the probe side cut
+ * in two halves that travel independently, gj_pcp_join of the first half runs under the copy of the
+ * second.  Afterwards gj_pcp_finish(ctx) returns the total; gj_pcp_finish(probe_ctx, ..., phase_ms = NULL)
+ * reports the probe half's received count / overflow. */
+int gj_pcp_join_ext(gj_ctx* ctx, gj_ctx* probe_ctx, int probe_which, uint64_t cap_build,
+                    uint64_t cap_probe, void* cuda_stream);
 
 /* CUDA IPC plumbing for the peer-store variant when every GPU is driven by its own process:
  * export a gj_malloc_device allocation as a 64-byte handle, open a peer's handle (peer access is

@@ -71,3 +71,80 @@ def test_nonpartitioned_baseline_matches_oracle(gj, orc, torch_cuda, nR, nS, lo,
         assert got.timings.kernel_launches == (2 if nR and nS else 0)
         part = eng.join_aggregate(*d)
         assert (part.matches, part.checksum) == (want.matches, want.checksum)
+
+
+# ------------------------------------------------------------------------------- pcp2: probe split
+def _pcp2_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, slack=1.8):
+    """The probe-split pipeline (distributed.GpuOps.pcp2_join) with G virtual ranks on one GPU: per rank
+    one engine for build + first probe half and a second engine for the second probe half; the
+    collectives are torch.stack / synchronize."""
+    assert len(Rk) <= len(Sk)
+    n = [len(Rk), len(Sk)]
+    cut = [np.linspace(0, n[w], G + 1).astype(np.int64) for w in range(2)]
+    dest_max = [int(np.bincount((k.view(np.uint32) >> B) & (G - 1), minlength=G).max()) for k in (Rk, Sk)]
+    cap_b = int(dest_max[0] * slack) + 64
+    half_cap = (int(dest_max[1] * slack / 2) + 64) & ~1
+    shard = [[int(cut[w][r + 1] - cut[w][r]) for r in range(G)] for w in range(2)]
+    e1 = [gj.JoinEngine(max(cap_b, max(shard[0]) + 1024), max(half_cap, max(shard[1]) + 1024), 0) for _ in range(G)]
+    e2 = [gj.JoinEngine(16, max(half_cap, max(shard[1]) + 1024), 0) for _ in range(G)]
+    try:
+        own_b = [torch.zeros(cap_b + 16, dtype=torch.int64, device="cuda") for _ in range(G)]
+        own_p = [torch.zeros(2 * half_cap + 16, dtype=torch.int64, device="cuda") for _ in range(G)]
+        slots = []          # per rank: [(engine, which, keys, pays, cap, dest pointers, own pointer)] x 3
+        for r in range(G):
+            bk, bp = dev(torch, Rk[cut[0][r]:cut[0][r + 1]], Rp[cut[0][r]:cut[0][r + 1]])
+            pk, pp = dev(torch, Sk[cut[1][r]:cut[1][r + 1]], Sp[cut[1][r]:cut[1][r + 1]])
+            h = (pk.numel() // 2) & ~3
+            slots.append([(e1[r], 0, bk, bp, cap_b, [t.data_ptr() for t in own_b], own_b[r].data_ptr()),
+                          (e1[r], 1, pk[:h], pp[:h], half_cap, [t.data_ptr() for t in own_p], own_p[r].data_ptr()),
+                          (e2[r], 1, pk[h:], pp[h:], half_cap, [t.data_ptr() + half_cap * 8 for t in own_p],
+                           own_p[r].data_ptr() + half_cap * 8)])
+        torch.cuda.synchronize()
+        for r in range(G):
+            e1[r].pcp_begin(n[0], n[1], G, r, B)
+            e2[r].pcp_begin(1, n[1], G, r, B)
+        g, bl, b2 = e1[0].pcp_plan()
+        n1 = 1 << (g + bl)
+        hist = [[torch.empty(n1, dtype=torch.int32, device="cuda") for _ in range(G)] for _ in range(3)]
+        for r in range(G):
+            for i, (e, w, k, p, cap, dst, own) in enumerate(slots[r]):
+                e.pcp_hist(w, k, hist[i][r])
+        torch.cuda.synchronize()
+        allh = [torch.stack(hist[i]).contiguous() for i in range(3)]
+        for r in range(G):
+            for i, (e, w, k, p, cap, dst, own) in enumerate(slots[r]):
+                e.pcp_part(w, k, p, allh[i], cap)
+                e.pcp_copy(w, dst)
+        torch.cuda.synchronize()
+        m = c = 0
+        got = [0, 0]
+        for r in range(G):
+            for i, (e, w, k, p, cap, dst, own) in enumerate(slots[r]):
+                e.pcp_recv(w, own, cap)
+            torch.cuda.synchronize()
+            e1[r].pcp_join(cap_b, half_cap)
+            torch.cuda.synchronize()
+            e1[r].pcp_join_ext(e2[r], 1, cap_b, half_cap)
+            mm, cc, nb_, np1, ph, bits = e1[r].pcp_finish()
+            _, _, _, np2, _, _ = e2[r].pcp_finish(phases=False)
+            m += mm
+            c = (c + cc) % 2**64
+            got[0] += nb_
+            got[1] += np1 + np2
+        assert got == n
+        return m, c
+    finally:
+        for e in e1 + e2:
+            e.close()
+
+
+@pytest.mark.parametrize("G,B", [(2, 7), (4, 9), (8, 13), (8, 15)])
+def test_pcp2_probe_split_virtual_shards(gj, orc, torch_cuda, G, B):
+    rng = np.random.default_rng(50 * G + B)
+    nR, nS = 700_000, 1_900_000
+    Rk = rng.integers(-(1 << 20), 1 << 20, nR).astype(np.int32)
+    Sk = rng.integers(-(1 << 20), 1 << 20, nS).astype(np.int32)
+    Rp = rng.integers(-2**31, 2**31, nR).astype(np.int32)
+    Sp = rng.integers(-2**31, 2**31, nS).astype(np.int32)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    assert _pcp2_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp) == (want.matches, want.checksum)
