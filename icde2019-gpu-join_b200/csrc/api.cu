@@ -246,7 +246,7 @@ struct gj_ctx {
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
-            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_pcp_l2_hint = 0;
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_pcp_l2_hint = 0, opt_nopart_max = 0;
     bool attrs_set = false;
 };
 
@@ -439,7 +439,7 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
         {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
         {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
         {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
-        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"pcp_l2_hint", &ctx->opt_pcp_l2_hint},
+        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"pcp_l2_hint", &ctx->opt_pcp_l2_hint}, {"nopart_max", &ctx->opt_nopart_max},
     };
     for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
     return nullptr;
@@ -881,11 +881,18 @@ static int run_join(gj_ctx* ctx, Rel R, Rel S, bool mat, int32_t* out_Rp, int32_
     return GJ_OK;
 }
 
+extern "C" int gj_join_aggregate_nopart(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
+                                        const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS,
+                                        uint64_t* matches, uint64_t* checksum, gj_timings* t);
+
 extern "C" int gj_join_aggregate(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
                                  const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS,
                                  uint64_t* matches, uint64_t* checksum, gj_timings* t) {
     int rc = check_caps(ctx, nR, nS);
     if (rc) return rc;
+    // small build sides: the L2-resident global hash table beats partitioning (option "nopart_max", 0 = never)
+    if (ctx->opt_nopart_max && std::min(nR, nS) && std::min(nR, nS) <= (uint64_t)ctx->opt_nopart_max)
+        return gj_join_aggregate_nopart(ctx, d_Rk, d_Rp, nR, d_Sk, d_Sp, nS, matches, checksum, t);
     if ((nR && (!d_Rk || !d_Rp)) || (nS && (!d_Sk || !d_Sp))) return fail(GJ_ERR_ARG, "NULL input column");
     Rel R, S;
     R.keys = d_Rk; R.pays = d_Rp; R.n = nR; R.slot = 0;

@@ -80,7 +80,10 @@ int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
  *   "gpu_bits"     number of key bits above the radix field consumed by the multi-GPU shuffle
  *   "shuffle_grid" persistent CTA count of the peer-store scatter (0 = one tile per CTA)
  *   "pp_out", "pp_tile16k"  sharded pipeline, see gj_pp_begin
- *   "pcp_l2_hint"  1: the pcp copy kernel's bulk loads / stores carry an L2 evict-first policy (default 0) */
+ *   "pcp_l2_hint"  1: the pcp copy kernel's bulk loads / stores carry an L2 evict-first policy (default 0)
+ *   "nopart_max"   gj_join_aggregate takes the non-partitioned path (gj_join_aggregate_nopart) when the
+ *                  smaller relation has at most this many tuples (default 0 = never; to be set from the
+ *                  measured crossover, tools/nopart_crossover.py) */
 int gj_set_option(gj_ctx* ctx, const char* name, int64_t value);
 int gj_get_option(gj_ctx* ctx, const char* name, int64_t* value);
 
