@@ -1101,6 +1101,101 @@ extern "C" int gj_join_aggregate_host(gj_ctx* ctx, const int32_t* h_Rk, const in
     return GJ_OK;
 }
 
+// Out-of-HBM probe side (reference outOfGPU_Join3_payload,
+// hash_join_clustered_probe.cu:1684-1984): R (the build side) is copied and partitioned once and stays
+// resident; S streams from host memory in chunks through a double buffer -- H2D of chunk i+1 on the copy
+// stream while chunk i is partitioned and joined against R's partitions -- into the same accumulators.
+extern "C" int gj_join_aggregate_stream_host(gj_ctx* ctx, const int32_t* h_Rk, const int32_t* h_Rp, uint64_t nR,
+                                             const int32_t* h_Sk, const int32_t* h_Sp, uint64_t nS,
+                                             uint64_t chunk_tuples, uint64_t* matches, uint64_t* checksum,
+                                             gj_timings* t) {
+    const auto w0 = std::chrono::steady_clock::now();
+    if (!ctx) return fail(GJ_ERR_ARG, "ctx is NULL");
+    if (nR > ctx->maxR) return fail(GJ_ERR_ARG, "the build side (%llu tuples) exceeds the context capacity (%llu)", (unsigned long long)nR, (unsigned long long)ctx->maxR);
+    if (chunk_tuples == 0 || 2 * chunk_tuples > ctx->maxS) return fail(GJ_ERR_ARG, "chunk_tuples must be in [1, max_S / 2] (double buffer)");
+    if ((nR && (!h_Rk || !h_Rp)) || (nS && (!h_Sk || !h_Sp))) return fail(GJ_ERR_ARG, "NULL input column");
+    if (t) memset(t, 0, sizeof(*t));
+    if (matches) *matches = 0;
+    if (checksum) *checksum = 0;
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    if (!nR || !nS) return GJ_OK;
+    int rc;
+    if ((rc = ensure_host_staging(ctx))) return rc;
+    cudaStream_t s = ctx->stream, c = ctx->copy_stream;
+    const Plan pl = choose_plan(ctx, nR, 0);
+    fill_plan(t, pl);
+    const uint32_t nb = 1u << pl.B;
+    int evi = 0;
+    auto next_ev = [&]() { return ctx->cev[evi++ % N_EVENTS]; };
+
+    // ---- build side: copy, histogram, offsets, radix passes; its histogram / offsets stay for every chunk
+    CK(cudaMemsetAsync(ctx->zero_block, 0, ctx->zero_bytes, s));
+    CK(cudaEventRecord(ctx->ev[0], s));
+    CK(cudaStreamWaitEvent(c, ctx->ev[0], 0));
+    CK(cudaMemcpyAsync(ctx->d_in[0], h_Rk, nR * sizeof(int32_t), cudaMemcpyHostToDevice, c));
+    cudaEvent_t e_rk = next_ev(); CK(cudaEventRecord(e_rk, c));
+    CK(cudaMemcpyAsync(ctx->d_in[1], h_Rp, nR * sizeof(int32_t), cudaMemcpyHostToDevice, c));
+    cudaEvent_t e_rp = next_ev(); CK(cudaEventRecord(e_rp, c));
+    CK(cudaStreamWaitEvent(s, e_rk, 0));
+    if ((rc = enqueue_hist(ctx, s, ctx->d_in[0], false, nR, 0, pl.B, ctx->meta[0].ghist))) return rc;
+    if ((rc = enqueue_scan(ctx, s, 0, 1, nb, false))) return rc;
+    if ((rc = enqueue_plan(ctx, s, 0, 1, pl, false))) return rc;
+    CK(cudaStreamWaitEvent(s, e_rp, 0));
+    Rel R;
+    R.keys = ctx->d_in[0]; R.pays = ctx->d_in[1]; R.n = nR; R.slot = 0;
+    if ((rc = enqueue_scatter(ctx, s, R, 0, pl, ctx->out[0]))) return rc;
+    CK(cudaEventRecord(ctx->ev[1], s));
+
+    // ---- probe side, chunk by chunk
+    const size_t res_off = (size_t)(reinterpret_cast<unsigned char*>(ctx->result) - ctx->zero_common);
+    cudaEvent_t buf_free[2] = {nullptr, nullptr};
+    uint64_t ci = 0;
+    for (uint64_t o = 0; o < nS; o += chunk_tuples, ++ci) {
+        const uint64_t m = std::min(chunk_tuples, nS - o);
+        const int b = (int)(ci & 1);
+        int32_t* dk = ctx->d_in[2] + (size_t)b * chunk_tuples;
+        int32_t* dp = ctx->d_in[3] + (size_t)b * chunk_tuples;
+        if (buf_free[b]) CK(cudaStreamWaitEvent(c, buf_free[b], 0));     // chunk ci - 2 has been scattered out of it
+        CK(cudaMemcpyAsync(dk, h_Sk + o, m * sizeof(int32_t), cudaMemcpyHostToDevice, c));
+        cudaEvent_t e_k = next_ev(); CK(cudaEventRecord(e_k, c));
+        CK(cudaMemcpyAsync(dp, h_Sp + o, m * sizeof(int32_t), cudaMemcpyHostToDevice, c));
+        cudaEvent_t e_p = next_ev(); CK(cudaEventRecord(e_p, c));
+        CK(cudaMemsetAsync(ctx->zero_role[1], 0, ctx->zero_role_bytes, s));
+        CK(cudaStreamWaitEvent(s, e_k, 0));
+        if ((rc = enqueue_hist(ctx, s, dk, false, m, 0, pl.B, ctx->meta[1].ghist))) return rc;
+        if ((rc = enqueue_scan(ctx, s, 1, 1, nb, false))) return rc;
+        if ((rc = enqueue_plan(ctx, s, 1, 1, pl, false))) return rc;
+        CK(cudaStreamWaitEvent(s, e_p, 0));
+        Rel S;
+        S.keys = dk; S.pays = dp; S.n = m; S.slot = 1;
+        if ((rc = enqueue_scatter(ctx, s, S, 1, pl, ctx->out[1]))) return rc;
+        buf_free[b] = next_ev();
+        CK(cudaEventRecord(buf_free[b], s));
+        // units of this chunk against the resident build partitions; the accumulators keep counting
+        CK(cudaMemsetAsync(ctx->zero_common, 0, res_off, s));
+        if ((rc = enqueue_scan(ctx, s, 0, 0, nb, true))) return rc;
+        if ((rc = enqueue_plan(ctx, s, 0, 0, pl, true))) return rc;
+        if ((rc = enqueue_join(ctx, s, ctx->out[0], ctx->out[1], pl, nR, m, false, nullptr, nullptr, 0))) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev[4], c));   // end of all H2D traffic
+    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(c));
+    if (matches) *matches = ctx->h_result[0];
+    if (checksum) *checksum = ctx->h_result[1];
+    if (t) {
+        CK(cudaEventElapsedTime(&t->hist_ms, ctx->ev[0], ctx->ev[1]));    // build side: copy + partition
+        CK(cudaEventElapsedTime(&t->join_ms, ctx->ev[1], ctx->ev[3]));    // all probe chunks: copy || partition || join
+        CK(cudaEventElapsedTime(&t->total_ms, ctx->ev[0], ctx->ev[3]));
+        CK(cudaEventElapsedTime(&t->h2d_ms, ctx->ev[0], ctx->ev[4]));
+        t->kernel_launches = ctx->launches;
+        t->wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    }
+    return GJ_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // the partitioner on its own
 // ------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 C_ABI_SYMBOLS = [
     "gj_create", "gj_destroy", "gj_last_error", "gj_version", "gj_set_stream", "gj_set_option",
     "gj_get_option", "gj_join_aggregate", "gj_join_aggregate_tuples", "gj_join_aggregate_host",
-    "gj_join_materialize", "gj_join_aggregate_late", "gj_join_aggregate_nopart", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
+    "gj_join_materialize", "gj_join_aggregate_late", "gj_join_aggregate_nopart", "gj_join_aggregate_stream_host", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
     "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_stage_pass_ms", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
     "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv", "gj_pcp_join",
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.gj_join_aggregate.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_join_aggregate_host.argtypes = L.gj_join_aggregate.argtypes
     L.gj_join_aggregate_nopart.argtypes = L.gj_join_aggregate.argtypes
+    L.gj_join_aggregate_stream_host.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_join_aggregate_tuples.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_join_materialize.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, i32p, i32p, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_join_aggregate_late.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, i32p, u32, u64, i32p, u32, u64,
@@ -271,6 +272,17 @@ class JoinEngine:
         _check(self._L.gj_join_aggregate_host(self._ctx, keep[0][0], keep[1][0], keep[0][1],
                                               keep[2][0], keep[3][0], keep[2][1],
                                               C.byref(m), C.byref(c), C.byref(t)))
+        return JoinResult(int(m.value), int(c.value), t)
+
+    def join_aggregate_stream_host(self, Rk, Rp, Sk, Sp, chunk_tuples: int) -> JoinResult:
+        """Out-of-HBM probe side: host columns in; R resident, S streamed in chunks of chunk_tuples."""
+        keep = [_host_ptr(x, n) for x, n in ((Rk, "Rk"), (Rp, "Rp"), (Sk, "Sk"), (Sp, "Sp"))]
+        if keep[0][1] != keep[1][1] or keep[2][1] != keep[3][1]:
+            raise ValueError("key and payload columns differ in length")
+        m, c, t = C.c_uint64(), C.c_uint64(), Timings()
+        _check(self._L.gj_join_aggregate_stream_host(self._ctx, keep[0][0], keep[1][0], keep[0][1],
+                                                     keep[2][0], keep[3][0], keep[2][1], chunk_tuples,
+                                                     C.byref(m), C.byref(c), C.byref(t)))
         return JoinResult(int(m.value), int(c.value), t)
 
     def join_materialize(self, Rk, Rp, Sk, Sp, out_Rp, out_Sp):

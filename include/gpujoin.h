@@ -107,6 +107,17 @@ int gj_join_aggregate_host(gj_ctx* ctx, const int32_t* h_Rk, const int32_t* h_Rp
                            const int32_t* h_Sk, const int32_t* h_Sp, uint64_t nS,
                            uint64_t* matches, uint64_t* checksum, gj_timings* t);
 
+/* Out-of-HBM probe side (replaces outOfGPU_Join3_payload,
+ * hash_join_clustered_probe.cu:1684-1984, the reference's PCIe-streaming mode): R (the build side,
+ * nR <= max_R) is copied and partitioned once and stays resident; S streams from HOST memory in chunks of
+ * chunk_tuples (<= max_S / 2: double buffer), the copy of chunk i+1 running under the partitioning and
+ * join of chunk i.  nS is unbounded.  timings: hist_ms = build side (copy + partition), join_ms = all
+ * probe chunks, h2d_ms = until the last byte arrived. */
+int gj_join_aggregate_stream_host(gj_ctx* ctx, const int32_t* h_Rk, const int32_t* h_Rp, uint64_t nR,
+                                  const int32_t* h_Sk, const int32_t* h_Sp, uint64_t nS,
+                                  uint64_t chunk_tuples, uint64_t* matches, uint64_t* checksum,
+                                  gj_timings* t);
+
 /* Materialising join: replaces join_partitioned_results (join-primitives.cu:1107-1416) and the
  * first run of outOfGPU_Join1_payload (hash_join_clustered_probe.cu:883-940).  Writes result
  * pairs (Pr, Ps) to the device columns d_out_Rp/d_out_Sp in unspecified order; at most `cap`

@@ -2,7 +2,10 @@
   * late-materialisation join (rank 1): gj_join_aggregate_late vs oracle.join_late, the restatement of
     join_partitioned_varpayload (join-primitives.cu:1420-1557);
   * non-partitioned baseline (rank 4): gj_join_aggregate_nopart (build_ht_chains / chains_probing,
-    join-primitives.cu:681-742) vs the oracle's join checker.
+    join-primitives.cu:681-742) vs the oracle's join checker;
+  * out-of-HBM probe side (rank 3): gj_join_aggregate_stream_host (outOfGPU_Join3_payload,
+    hash_join_clustered_probe.cu:1684-1984) vs the oracle's join checker;
+  * probe-split multi-GPU pipeline (pcp2) with virtual shards.
 
 NOT YET RUN ON A GPU: these kernels, entry points and tests were written after round 1's GPU budget was
 spent.  They are skipped unless GJ_RUN_UNVERIFIED=1 so that an untested path cannot turn the suite red;
@@ -148,3 +151,26 @@ def test_pcp2_probe_split_virtual_shards(gj, orc, torch_cuda, G, B):
     Sp = rng.integers(-2**31, 2**31, nS).astype(np.int32)
     want = orc.join_check(Rk, Rp, Sk, Sp)
     assert _pcp2_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp) == (want.matches, want.checksum)
+
+
+# ------------------------------------------------------------------------------- out-of-HBM probe side
+@pytest.mark.parametrize("nR,nS,chunk", [(200_000, 1_750_000, 500_000), (1 << 20, 1 << 20, 1 << 19), (300_000, 100_000, 250_000),
+                                         (50_000, 1_000_001, 1), (1000, 0, 100)])
+def test_streamed_probe_side_matches_oracle(gj, orc, torch_cuda, nR, nS, chunk):
+    """gj_join_aggregate_stream_host (reference outOfGPU_Join3_payload,
+    hash_join_clustered_probe.cu:1684-1984): R resident, S streamed from host memory through a double
+    buffer; ragged last chunk, a single chunk, S smaller than one chunk, empty S."""
+    if chunk == 1:
+        chunk = 333_333
+    rng = np.random.default_rng(nR + nS + chunk)
+    Rk = rng.integers(0, 1 << 19, nR).astype(np.int32)
+    Sk = rng.integers(0, 1 << 19, nS).astype(np.int32)
+    Rp = rng.integers(-2**31, 2**31, nR).astype(np.int32)
+    Sp = rng.integers(-2**31, 2**31, nS).astype(np.int32)
+    want = orc.join_check(Rk, Rp, Sk, Sp) if nS else None
+    with gj.JoinEngine(nR, 2 * chunk, 0) as eng:
+        got = eng.join_aggregate_stream_host(Rk, Rp, Sk, Sp, chunk)
+        assert (got.matches, got.checksum) == ((want.matches, want.checksum) if nS else (0, 0))
+        if nS:
+            again = eng.join_aggregate_stream_host(Rk, Rp, Sk, Sp, chunk)      # buffers and events are reused
+            assert (again.matches, again.checksum) == (want.matches, want.checksum)
