@@ -109,8 +109,10 @@ static const PPCfg kPcpLast[4] = {
     { 512, 16, 1, 512, scatter_kernel<512, 16, 1, 1, false, 2, false, 512> },          // 9 bits
     { 1024, 8, 1, 1024, scatter_kernel<1024, 8, 1, 1, false, 1, false, 1024> },        // 10 bits
 };
-constexpr int PCP_NS = 4;   // ring slots of the copy kernel
-static size_t pcp_copy_smem() { return (size_t)PCP_NS * PCP_PIECE * sizeof(tup_t) + (PCP_MAX_CHUNKS + 4) * sizeof(uint32_t); }
+constexpr int PCP_NS = 4;        // ring slots of the copy kernel (2 loads in flight per CTA)
+constexpr int PCP_NS_DEEP = 12;  // deep ring (10 loads in flight per CTA): for running the copy on a FEW SMs only, so
+                                 // that the radix passes next to it keep their full occupancy (option "pcp_ring")
+static size_t pcp_copy_smem(int ns = PCP_NS) { return (size_t)ns * PCP_PIECE * sizeof(tup_t) + (PCP_MAX_CHUNKS + 4) * sizeof(uint32_t); }
 constexpr uint32_t PP_MAX_PASS_BITS = 10;
 constexpr uint32_t PP_MAX_BITS = 2 * PP_MAX_PASS_BITS;
 
@@ -246,7 +248,7 @@ struct gj_ctx {
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
-            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_pcp_l2_hint = 0, opt_nopart_max = 0;
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_pcp_l2_hint = 0, opt_nopart_max = 0, opt_pcp_ring = 0;
     bool attrs_set = false;
 };
 
@@ -276,6 +278,7 @@ static int set_func_attrs(gj_ctx* ctx) {
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (const PPCfg& c : kPcpLast) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     CK(cudaFuncSetAttribute(pcp_copy_kernel<PCP_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem()));
+    CK(cudaFuncSetAttribute(pcp_copy_kernel<PCP_NS_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem(PCP_NS_DEEP)));
     for (const auto& row : kPPPushBig)
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (int i = 0; i < kNumJoin; ++i) {
@@ -439,7 +442,7 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
         {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
         {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
         {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
-        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"pcp_l2_hint", &ctx->opt_pcp_l2_hint}, {"nopart_max", &ctx->opt_nopart_max},
+        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"pcp_l2_hint", &ctx->opt_pcp_l2_hint}, {"nopart_max", &ctx->opt_nopart_max}, {"pcp_ring", &ctx->opt_pcp_ring},
     };
     for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
     return nullptr;
@@ -1870,7 +1873,8 @@ extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void
         const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
         uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count;   // measured (2 GPUs): 148 CTAs 3.98 ms, 296 CTAs 4.24 ms per step
         grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));
-        pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
+        if (ctx->opt_pcp_ring) pcp_copy_kernel<PCP_NS_DEEP><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
+        else pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
         LAUNCHED();
     }
     CK(cudaEventRecord(q.ev[which][3], s));

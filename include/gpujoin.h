@@ -81,6 +81,8 @@ int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
  *   "shuffle_grid" persistent CTA count of the peer-store scatter (0 = one tile per CTA)
  *   "pp_out", "pp_tile16k"  sharded pipeline, see gj_pp_begin
  *   "pcp_l2_hint"  1: the pcp copy kernel's bulk loads / stores carry an L2 evict-first policy (default 0)
+ *   "pcp_ring"     1: the pcp copy kernel uses a 12-slot ring (10 bulk loads in flight per CTA) -- for running it on
+ *                  few SMs ("shuffle_grid" = 16..32) so the passes next to it keep their occupancy (default 0)
  *   "nopart_max"   gj_join_aggregate takes the non-partitioned path (gj_join_aggregate_nopart) when the
  *                  smaller relation has at most this many tuples (default 0 = never; to be set from the
  *                  measured crossover, tools/nopart_crossover.py) */
