@@ -671,7 +671,9 @@ struct PcpCopyArgs {
 // round robin): it issues the bulk load of piece i and, LAG pieces behind, the bulk store of piece
 // i - LAG, so LAG loads are in flight per CTA and a slot is reloaded only after its previous store
 // has read it (bulk async-group accounting: one group per piece, empty groups included).
-template <int NS>
+// CONTIG: every CTA takes one contiguous range of pieces (mostly the same chunk: its table entries stay
+// in registers, no search per piece) instead of the round robin -- for running the copy on few SMs.
+template <int NS, bool CONTIG = false>
 __global__ void __launch_bounds__(32)
 pcp_copy_kernel(PcpCopyArgs a) {
     constexpr uint32_t LAG = NS - 2;
@@ -694,15 +696,27 @@ pcp_copy_kernel(PcpCopyArgs a) {
     const uint32_t total = s_prefix[n1];
     const uint64_t pol = a.l2_hint ? l2_policy_evict_first() : 0ull;
     uint32_t issued = 0, stored = 0;
-    for (uint32_t k = blockIdx.x; k < total || stored < issued; k += gridDim.x) {
-        if (k < total) {
-            uint32_t lo = 0, hi = n1;             // largest position whose prefix is <= k
-            while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (s_prefix[m] <= k) lo = m; else hi = m; }
-            const uint32_t c = tile_perm(lo, a.perm), slice = k - s_prefix[lo];
-            const uint32_t src0 = a.t.src_start[c], dst0 = a.t.dst_start[c], cnt = a.t.cnt[c];
+    uint32_t k_begin = blockIdx.x, k_end = total, k_step = gridDim.x;
+    if (CONTIG) {
+        const uint32_t per = (total + gridDim.x - 1u) / gridDim.x;
+        k_begin = min(total, blockIdx.x * per); k_end = min(total, k_begin + per); k_step = 1u;
+    }
+    uint32_t lo = 0xFFFFFFFFu, src0 = 0, dst0 = 0, cnt = 0;     // CONTIG: the current chunk's table entries
+    tup_t* dbase = nullptr;
+    for (uint32_t k = k_begin; k < k_end || stored < issued; k += k_step) {
+        if (k < k_end) {
+            if (!CONTIG || lo == 0xFFFFFFFFu || k < s_prefix[lo] || k >= s_prefix[lo + 1u]) {
+                uint32_t l = 0, hi = n1;          // largest position whose prefix is <= k
+                while (hi - l > 1) { const uint32_t m = (l + hi) >> 1; if (s_prefix[m] <= k) l = m; else hi = m; }
+                lo = l;
+                const uint32_t cc = tile_perm(lo, a.perm);
+                src0 = a.t.src_start[cc]; dst0 = a.t.dst_start[cc]; cnt = a.t.cnt[cc];
+                dbase = a.peer_bases[cc >> a.bl];
+            }
+            const uint32_t slice = k - s_prefix[lo];
             const uint32_t phase = src0 & 1u;     // == dst0 & 1 by construction
             const tup_t* src = a.stage + src0;
-            tup_t* dst = a.peer_bases[c >> a.bl] + dst0;
+            tup_t* dst = dbase + dst0;
             if (slice == 0 && phase) *dst = *src;                     // odd first slot: plain 8-byte copy
             const uint32_t body0 = phase + slice * PCP_PIECE;         // even slot on both sides
             uint32_t m = (cnt > body0) ? min(PCP_PIECE, cnt - body0) : 0u;
@@ -720,7 +734,7 @@ pcp_copy_kernel(PcpCopyArgs a) {
             ++issued;
         }
         // keep at most LAG loads ahead of the stores; drain once the pieces are exhausted
-        while (stored < issued && (k >= total || issued - stored > LAG)) {
+        while (stored < issued && (k >= k_end || issued - stored > LAG)) {
             const uint32_t slot = stored % NS;
             mbar_wait(&s_full[slot], (stored / NS) & 1u);
             if (s_bytes[slot]) {

@@ -265,3 +265,52 @@ def test_pcp_layout_and_plan(gj):
                 gg, b_l, b2 = d.pcp_plan_bits(G2, B, p1)
                 assert gg + b_l <= 10 and 0 <= b_l <= 8 and b_l <= B - 1 and b2 == B - b_l and 1 <= b2 <= 10, (G2, B, p1)
     assert d.pcp_plan_bits(8, 15) == (3, 6, 9) and d.pcp_plan_bits(2, 15) == (1, 7, 8) and d.pcp_plan_bits(8, 16) == (3, 7, 9)
+
+
+def test_pcp_copy_piece_arithmetic_model():
+    """numpy model of pcp_layout_kernel's piece prefix and pcp_copy_kernel's per-piece arithmetic
+    (csrc/kernels.cuh section 3d), both piece-to-CTA assignments: every tuple of every chunk is copied
+    exactly once, bulk bodies start on even slots on both sides and have even length, heads / tails
+    are single tuples."""
+    P = 2048
+    rng = np.random.default_rng(21)
+    for trial in range(20):
+        n1 = int(rng.choice([1, 2, 8, 64]))
+        cnt = rng.integers(0, 3 * P + 5, n1)
+        cnt[rng.integers(0, n1)] = 0
+        if n1 > 2:
+            cnt[1], cnt[2] = 1, P + 1
+        src = np.concatenate(([0], np.cumsum(cnt + 1)[:-1]))
+        dst = rng.integers(0, 50, n1) + np.concatenate(([0], np.cumsum(cnt)[:-1])) * 2
+        src = src + ((src ^ dst) & 1)                       # phase matched, as pcp_layout_kernel does
+        phase = src & 1
+        pieces = np.where(cnt > 0, np.maximum(1, (cnt - phase + P - 1) // P), 0)
+        prefix = np.concatenate(([0], np.cumsum(pieces)))
+        total = int(prefix[-1])
+        for grid, contig in ((3, False), (3, True), (7, True), (1, False)):
+            copied = [np.zeros(int(c), dtype=np.int32) for c in cnt]
+            seen = 0
+            for b in range(grid):
+                if contig:
+                    per = (total + grid - 1) // grid
+                    ks = range(min(total, b * per), min(total, b * per + per))
+                else:
+                    ks = range(b, total, grid)
+                for k in ks:
+                    seen += 1
+                    lo = max(i for i in range(n1) if prefix[i] <= k)     # the kernel's binary search: largest such position
+                    assert pieces[lo] > 0
+                    c, s = lo, k - int(prefix[lo])
+                    ph = int(phase[c])
+                    if s == 0 and ph:
+                        copied[c][0] += 1
+                    body0 = ph + s * P
+                    m = min(P, int(cnt[c]) - body0) if cnt[c] > body0 else 0
+                    if m & 1:
+                        copied[c][body0 + m - 1] += 1
+                        m -= 1
+                    assert m % 2 == 0 and (src[c] + body0) % 2 == 0 and (dst[c] + body0) % 2 == 0
+                    copied[c][body0:body0 + m] += 1
+            assert seen == total
+            for c in range(n1):
+                assert np.all(copied[c] == 1), (trial, grid, contig, c, cnt[c], phase[c])
