@@ -278,7 +278,8 @@ static int set_func_attrs(gj_ctx* ctx) {
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (const PPCfg& c : kPcpLast) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     CK(cudaFuncSetAttribute(pcp_copy_kernel<PCP_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem()));
-    CK(cudaFuncSetAttribute(pcp_copy_kernel<PCP_NS_DEEP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem(PCP_NS_DEEP)));
+    CK(cudaFuncSetAttribute(pcp_copy_kernel_x<PCP_NS_DEEP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem(PCP_NS_DEEP)));
+    CK(cudaFuncSetAttribute(pcp_copy_kernel_x<PCP_NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem()));
     for (const auto& row : kPPPushBig)
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (int i = 0; i < kNumJoin; ++i) {
@@ -1873,7 +1874,9 @@ extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void
         const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
         uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count;   // measured (2 GPUs): 148 CTAs 3.98 ms, 296 CTAs 4.24 ms per step
         grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));
-        if (ctx->opt_pcp_ring) pcp_copy_kernel<PCP_NS_DEEP, true><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
+        // default: the kernel measured in round 1; the experimental variant only on request
+        if (ctx->opt_pcp_ring) pcp_copy_kernel_x<PCP_NS_DEEP, true><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
+        else if (ctx->opt_pcp_l2_hint) pcp_copy_kernel_x<PCP_NS, false><<<grid, 32, pcp_copy_smem(), s>>>(a);
         else pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
         LAUNCHED();
     }

@@ -671,11 +671,69 @@ struct PcpCopyArgs {
 // round robin): it issues the bulk load of piece i and, LAG pieces behind, the bulk store of piece
 // i - LAG, so LAG loads are in flight per CTA and a slot is reloaded only after its previous store
 // has read it (bulk async-group accounting: one group per piece, empty groups included).
-// CONTIG: every CTA takes one contiguous range of pieces (mostly the same chunk: its table entries stay
-// in registers, no search per piece) instead of the round robin -- for running the copy on few SMs.
-template <int NS, bool CONTIG = false>
+template <int NS>
 __global__ void __launch_bounds__(32)
 pcp_copy_kernel(PcpCopyArgs a) {
+    constexpr uint32_t LAG = NS - 2;
+    static_assert(NS >= 3, "ring too small");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tup_t* ring = reinterpret_cast<tup_t*>(smem_raw);                                   // [NS][PCP_PIECE]
+    uint32_t* s_prefix = reinterpret_cast<uint32_t*>(smem_raw + (size_t)NS * PCP_PIECE * sizeof(tup_t));   // [n1 + 1]
+    __shared__ uint64_t s_full[NS];
+    __shared__ tup_t* s_dst[NS];
+    __shared__ uint32_t s_bytes[NS];
+    const uint32_t n1 = 1u << a.b1;
+    if (a.t.status[0]) return;
+    for (uint32_t i = threadIdx.x; i <= n1; i += 32) s_prefix[i] = a.t.piece_prefix[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&s_full[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const uint32_t total = s_prefix[n1];
+    uint32_t issued = 0, stored = 0;
+    for (uint32_t k = blockIdx.x; k < total || stored < issued; k += gridDim.x) {
+        if (k < total) {
+            uint32_t lo = 0, hi = n1;             // largest position whose prefix is <= k
+            while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (s_prefix[m] <= k) lo = m; else hi = m; }
+            const uint32_t c = tile_perm(lo, a.perm), slice = k - s_prefix[lo];
+            const uint32_t src0 = a.t.src_start[c], dst0 = a.t.dst_start[c], cnt = a.t.cnt[c];
+            const uint32_t phase = src0 & 1u;     // == dst0 & 1 by construction
+            const tup_t* src = a.stage + src0;
+            tup_t* dst = a.peer_bases[c >> a.bl] + dst0;
+            if (slice == 0 && phase) *dst = *src;                     // odd first slot: plain 8-byte copy
+            const uint32_t body0 = phase + slice * PCP_PIECE;         // even slot on both sides
+            uint32_t m = (cnt > body0) ? min(PCP_PIECE, cnt - body0) : 0u;
+            if (m & 1u) { dst[body0 + m - 1u] = src[body0 + m - 1u]; --m; }   // odd tail (last piece only)
+            const uint32_t slot = issued % NS;
+            // the slot's previous tenant (piece issued - NS) was stored at least NS - 1 - LAG groups ago
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NS - 1 - LAG) : "memory");
+            s_dst[slot] = dst + body0;
+            s_bytes[slot] = m * (uint32_t)sizeof(tup_t);
+            mbar_arrive_expect_tx(&s_full[slot], m * (uint32_t)sizeof(tup_t));
+            if (m) bulk_g2s(ring + (size_t)slot * PCP_PIECE, src + body0, m * (uint32_t)sizeof(tup_t), &s_full[slot]);
+            ++issued;
+        }
+        // keep at most LAG loads ahead of the stores; drain once the pieces are exhausted
+        while (stored < issued && (k >= total || issued - stored > LAG)) {
+            const uint32_t slot = stored % NS;
+            mbar_wait(&s_full[slot], (stored / NS) & 1u);
+            if (s_bytes[slot]) bulk_s2g(s_dst[slot], ring + (size_t)slot * PCP_PIECE, s_bytes[slot]);
+            bulk_commit();
+            ++stored;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// Experimental variant of pcp_copy_kernel (NOT YET RUN ON A GPU; options "pcp_ring", "pcp_l2_hint"): same
+// pipeline, plus an optional L2 evict-first policy on the bulk copies and, CONTIG, one contiguous
+// range of pieces per CTA (mostly the same chunk: its table entries stay in registers, no search per
+// piece) -- for running the copy on a few SMs only with a deep ring.
+template <int NS, bool CONTIG>
+__global__ void __launch_bounds__(32)
+pcp_copy_kernel_x(PcpCopyArgs a) {
     constexpr uint32_t LAG = NS - 2;
     static_assert(NS >= 3, "ring too small");
     extern __shared__ __align__(16) unsigned char smem_raw[];
