@@ -121,3 +121,35 @@ def test_parallel_generators_keep_the_reference_distributions(gj):
     assert abs(top[0] / n - 1 / h) < 0.01 and abs(top[1] / n - 0.5 / h) < 0.01
     flat = g.create_relation_zipf_parallel(n, 1000, 0.0, 5)
     assert np.bincount(flat)[1:].min() > 100
+
+
+def test_new_entry_points_reject_bad_calls_without_a_gpu(gj):
+    """Argument / state errors of the sharded pipelines and the section-8f entry points are reported
+    through the return code + gj_last_error() before any CUDA call is made (no exit(), no crash)."""
+    L = gj.lib()
+    null = C.c_void_p(0)
+    u64 = C.c_uint64
+    GJ_ERR_ARG, GJ_ERR_STATE = -1, -4
+    calls = [
+        (L.gj_pp_begin(null, 10, 10, 2, 0, 4, null), GJ_ERR_ARG),
+        (L.gj_pp_local(null, 0, null, null, 0, null, null), GJ_ERR_STATE),
+        (L.gj_pp_push(null, 0, null, None, 0, 0, null), GJ_ERR_STATE),
+        (L.gj_pp_join(null, null, null, 0, 0, null), GJ_ERR_STATE),
+        (L.gj_pp_finish(null, None, None, None, None, None), GJ_ERR_STATE),
+        (L.gj_pcp_begin(null, 10, 10, 2, 0, 4, null), GJ_ERR_ARG),
+        (L.gj_pcp_hist(null, 0, null, 0, null, null), GJ_ERR_STATE),
+        (L.gj_pcp_part(null, 0, null, null, null, 0, null), GJ_ERR_STATE),
+        (L.gj_pcp_copy(null, 0, None, null), GJ_ERR_STATE),
+        (L.gj_pcp_recv(null, 0, null, 0, null), GJ_ERR_STATE),
+        (L.gj_pcp_join(null, 0, 0, null), GJ_ERR_STATE),
+        (L.gj_pcp_join_ext(null, null, 0, 0, 0, null), GJ_ERR_STATE),
+        (L.gj_pcp_finish(null, None, None, None, None, None, None), GJ_ERR_STATE),
+        (L.gj_join_aggregate_late(null, null, null, 0, null, null, 0, null, 0, 0, null, 0, 0, None, None, None), GJ_ERR_ARG),
+        (L.gj_join_aggregate_nopart(null, null, null, 0, null, null, 0, None, None, None), GJ_ERR_ARG),
+        (L.gj_join_aggregate_stream_host(null, null, null, 0, null, null, 0, 1, None, None, None), GJ_ERR_ARG),
+        (L.gj_stage_pass_ms(null, None), GJ_ERR_ARG),
+    ]
+    for i, (got, want) in enumerate(calls):
+        assert got == want, (i, got, want)
+        assert L.gj_last_error()
+    assert u64  # (ctypes types referenced above)
