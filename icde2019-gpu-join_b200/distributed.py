@@ -300,9 +300,17 @@ class GpuOps:
         """Mode "pcp": coarse histograms -> all-gather -> first radix pass at the source -> TMA bulk
         copies of whole first-pass partitions -> last radix pass + join at the receiver.  R's copy
         runs under S's first pass, S's copy under R's last pass."""
+        import os
         torch, eng = self.torch, self.engine
         sR, sS = self.stream_shuffle, self.stream_local           # S on the high-priority stream
         streams = (sR, sS)
+        trace = [] if os.environ.get("GJ_TRACE") else None        # optional GPU timeline (ms since the start mark)
+
+        def mark(name, stream):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                trace.append((name, e))
         eng.pcp_begin(n_glob[0], n_glob[1], G, rank, B, sR)
         g, bl, _ = eng.pcp_plan()
         n1 = 1 << (g + bl)                                        # chunks = first-pass partitions of all destinations
@@ -315,10 +323,13 @@ class GpuOps:
         for s in streams:
             s.wait_stream(cur)
         caps = (self.cap_R, self.cap_S)
+        mark("start", sR)
+        names = ("R", "S")
         for which, (k, p) in enumerate(rels):
             eng.pcp_hist(which, k, self._pcp_hist[which], streams[which])
             with torch.cuda.stream(streams[which]):
                 dist.all_gather_into_tensor(self._pcp_all[which], self._pcp_hist[which], group=group)
+            mark(f"{names[which]} histograms gathered", streams[which])
         ev = {}
         for which, (k, p) in enumerate(rels):
             s = streams[which]
@@ -326,19 +337,27 @@ class GpuOps:
                 s.wait_event(ev["part0"])                         # S's first pass runs under R's copy ...
             eng.pcp_part(which, k, p, self._pcp_all[which], caps[which], s)
             ev[f"part{which}"] = torch.cuda.Event(); ev[f"part{which}"].record(s)
+            mark(f"{names[which]} source pass done", s)
             if which == 1:
                 s.wait_event(ev["copy0"])                         # ... and one relation crosses NVLink at a time
             eng.pcp_copy(which, peers[which], s)
             ev[f"copy{which}"] = torch.cuda.Event(); ev[f"copy{which}"].record(s)
+            mark(f"{names[which]} copy kernel done (local)", s)
             with torch.cuda.stream(s):
                 dist.all_reduce(self._pcp_tok[which], group=group)   # every rank's copies have landed
+            mark(f"{names[which]} landed everywhere", s)
         for which in range(2):
             eng.pcp_recv(which, own_ptrs[which], caps[which], streams[which])
+            mark(f"{names[which]} receiver pass done", streams[which])
         sS.wait_stream(sR)
         eng.pcp_join(caps[0], caps[1], sS)
+        mark("joined", sS)
         m, c, n_r, n_s, ph, bits = eng.pcp_finish()
         sR.synchronize()
         ph = dict(ph, shuffle_scatter_ms=ph["copy_R_ms"] + ph["copy_S_ms"], radix_bits=B, pass1_bits=bits[0] + bits[1], pass2_bits=bits[2])
+        if trace is not None:
+            torch.cuda.synchronize(self.device)
+            ph["trace_ms"] = {n: round(trace[0][1].elapsed_time(e), 3) for n, e in trace[1:]}
         return m, c, (n_r, n_s), ph
 
     def pcp2_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob):

@@ -20,6 +20,7 @@ N=${1:-8}
 OUT=gpurun_out; mkdir -p $OUT
 GJ_RUN_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 600 -p no:cacheprovider > $OUT/r2_pytest_multi$N.log 2>&1
 echo "exit $?" >> $OUT/r2_pytest_multi$N.log; tail -3 $OUT/r2_pytest_multi$N.log
+export GJ_TRACE=1   # per-stage GPU timeline of pcp in every bench line (shuffle.trace_ms_rank0)
 SPECS=("pcp:steps=5" "pcp2:steps=5" "pcp:steps=5,pcp_l2_hint=1" "pcp:steps=5,shuffle_grid=74" "pcp:steps=5,shuffle_grid=32,pcp_ring=1" "pcp:steps=5,shuffle_grid=16,pcp_ring=1" "pcp:steps=5,shuffle_grid=296" "pcp:steps=5,pass1_bits=10" "pp:steps=5" "p2p:steps=5")
 if [ "$N" = "8" ]; then SPECS+=("pcp:steps=5,workload=cfg5" "pcp2:steps=5,workload=cfg5" "pcp:steps=5,workload=cfg5,pass1_bits=9" "p2p:steps=5,workload=cfg5"); fi
 bash tools/gpu_multi_bench.sh $N "${SPECS[@]}"
