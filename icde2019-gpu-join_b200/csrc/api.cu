@@ -235,7 +235,8 @@ struct gj_ctx {
         cudaEvent_t jev[2] = {};
     } pcp;
     // non-partitioned baseline: chained table in global memory (allocated on first use)
-    struct NP { uint32_t* heads = nullptr; uint32_t* next = nullptr; uint64_t heads_cap = 0, next_cap = 0; } np;
+    struct NP { uint32_t* heads = nullptr; uint32_t* next = nullptr; uint64_t heads_cap = 0, next_cap = 0;
+                unsigned long long* slots = nullptr; uint64_t slots_cap = 0; } np;   // slots: perfect array
     unsigned char* zero_role[2] = {nullptr, nullptr};
     unsigned char* zero_common = nullptr;
     size_t zero_role_bytes = 0, zero_common_bytes = 0;
@@ -248,7 +249,7 @@ struct gj_ctx {
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
-            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_pcp_l2_hint = 0, opt_nopart_max = 0, opt_pcp_ring = 0;
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_nopart_max = 0, opt_pcp_ring = 0;
     bool attrs_set = false;
 };
 
@@ -278,8 +279,7 @@ static int set_func_attrs(gj_ctx* ctx) {
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (const PPCfg& c : kPcpLast) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     CK(cudaFuncSetAttribute(pcp_copy_kernel<PCP_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem()));
-    CK(cudaFuncSetAttribute(pcp_copy_kernel_x<PCP_NS_DEEP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem(PCP_NS_DEEP)));
-    CK(cudaFuncSetAttribute(pcp_copy_kernel_x<PCP_NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem()));
+    CK(cudaFuncSetAttribute(pcp_copy_kernel<PCP_NS_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcp_copy_smem(PCP_NS_DEEP)));
     for (const auto& row : kPPPushBig)
         for (const PPCfg& c : row) CK(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem(c)));
     for (int i = 0; i < kNumJoin; ++i) {
@@ -306,7 +306,7 @@ extern "C" void gj_destroy(gj_ctx* ctx) {
     cudaFree(ctx->p3.block); cudaFree(ctx->p3.zero);
     cudaFree(ctx->pp.block);
     cudaFree(ctx->pcp.block);
-    cudaFree(ctx->np.heads); cudaFree(ctx->np.next);
+    cudaFree(ctx->np.heads); cudaFree(ctx->np.next); cudaFree(ctx->np.slots);
     if (ctx->pcp.h_pin) cudaFreeHost(ctx->pcp.h_pin);
     for (auto& r : ctx->pcp.ev) for (auto& e : r) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->pcp.jev) if (e) cudaEventDestroy(e);
@@ -443,7 +443,7 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
         {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
         {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
         {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
-        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"pcp_l2_hint", &ctx->opt_pcp_l2_hint}, {"nopart_max", &ctx->opt_nopart_max}, {"pcp_ring", &ctx->opt_pcp_ring},
+        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"nopart_max", &ctx->opt_nopart_max}, {"pcp_ring", &ctx->opt_pcp_ring},
     };
     for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
     return nullptr;
@@ -466,7 +466,9 @@ extern "C" int gj_set_option(gj_ctx* ctx, const char* name, int64_t v) {
     if (p == &ctx->opt_pass1_bits && v > PP_MAX_PASS_BITS) return fail(GJ_ERR_ARG, "pass1_bits <= %d", (int)PP_MAX_PASS_BITS);
     if (p == &ctx->opt_pp_out && v > 1) return fail(GJ_ERR_ARG, "pp_out is 0 (8-byte stores) or 1 (TMA bulk stores)");
     if (p == &ctx->opt_pp_tile16k && v > 1) return fail(GJ_ERR_ARG, "pp_tile16k is 0 or 1");
-    if (p == &ctx->opt_unit && v && v < 1024) return fail(GJ_ERR_ARG, "unit_tuples >= 1024");
+    if (p == &ctx->opt_unit && v && (v < 1024 || v > (1 << 20))) return fail(GJ_ERR_ARG, "unit_tuples must be 0 (default) or in [1024, 2^20]");
+    if ((p == &ctx->opt_join_grid || p == &ctx->opt_shuffle_grid) && v > 65535) return fail(GJ_ERR_ARG, "%s <= 65535 CTAs", name);
+    if (p == &ctx->opt_nopart_max && v > (1ll << 31)) return fail(GJ_ERR_ARG, "nopart_max <= 2^31");
     if (p == &ctx->opt_gpu_bits && v > 8) return fail(GJ_ERR_ARG, "gpu_bits <= 8");
     if (p == &ctx->opt_part_target && v < 32) return fail(GJ_ERR_ARG, "part_target >= 32");
     if (p == &ctx->opt_h2d_chunk && v < 4096) return fail(GJ_ERR_ARG, "h2d_chunk >= 4096");
@@ -1013,15 +1015,78 @@ extern "C" int gj_join_aggregate_nopart(gj_ctx* ctx, const int32_t* d_Rk, const 
     return GJ_OK;
 }
 
+// Perfect-array variant of the non-partitioned baseline (reference build_perfect_array /
+// probe_perfect_array, join-primitives.cu:628-668): the build keys must be unique and lie in
+// [key_min, key_min + key_range); the key addresses the table.  The build side is the smaller
+// relation (R when equal).  The precondition is checked on the device: GJ_ERR_ARG if a build key is
+// out of range or occurs twice (the outputs are then not meaningful).
+extern "C" int gj_join_aggregate_perfect(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
+                                         const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS,
+                                         int32_t key_min, uint64_t key_range,
+                                         uint64_t* matches, uint64_t* checksum, gj_timings* t) {
+    const auto w0 = std::chrono::steady_clock::now();
+    int rc = check_caps(ctx, nR, nS);
+    if (rc) return rc;
+    if ((nR && (!d_Rk || !d_Rp)) || (nS && (!d_Sk || !d_Sp))) return fail(GJ_ERR_ARG, "NULL input column");
+    if (key_range == 0 || key_range > (1ull << 32)) return fail(GJ_ERR_ARG, "key_range must be in [1, 2^32]");
+    if (t) memset(t, 0, sizeof(*t));
+    if (matches) *matches = 0;
+    if (checksum) *checksum = 0;
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    if (!nR || !nS) return GJ_OK;
+    const bool swap = nR > nS;
+    const int32_t* bk = swap ? d_Sk : d_Rk; const int32_t* bp = swap ? d_Sp : d_Rp;
+    const int32_t* pk = swap ? d_Rk : d_Sk; const int32_t* pp = swap ? d_Rp : d_Sp;
+    const uint64_t nb = swap ? nS : nR, np = swap ? nR : nS;
+    gj_ctx::NP& q = ctx->np;
+    if (q.slots_cap < key_range) {
+        cudaFree(q.slots); q.slots = nullptr; q.slots_cap = 0;
+        if (cudaMalloc(&q.slots, key_range * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "perfect array (%.1f MB)", key_range * 8e-6); }
+        q.slots_cap = key_range;
+    }
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->zero_common, 0, ctx->zero_common_bytes, s));
+    uint32_t* status = reinterpret_cast<uint32_t*>(ctx->result + 2);   // result[2] is unused here: two u32 status words
+    CK(cudaEventRecord(ctx->ev[0], s));
+    CK(cudaMemsetAsync(q.slots, 0, key_range * sizeof(unsigned long long), s));
+    const uint32_t range32 = key_range >= (1ull << 32) ? 0xFFFFFFFFu : (uint32_t)key_range;   // 2^32: every key is in range
+    const uint32_t gb = (uint32_t)std::min<uint64_t>((nb + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    np_build_perfect_kernel<<<gb, 256, 0, s>>>(bk, bp, (uint32_t)nb, key_min, range32, q.slots, status);
+    LAUNCHED();
+    CK(cudaEventRecord(ctx->ev[2], s));
+    const uint32_t gp = (uint32_t)std::min<uint64_t>((np + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    np_probe_perfect_kernel<<<gp, 256, 0, s>>>(q.slots, key_min, range32, pk, pp, (uint32_t)np, ctx->result);
+    LAUNCHED();
+    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint32_t out_of_range = (uint32_t)ctx->h_result[2], dups = (uint32_t)(ctx->h_result[2] >> 32);
+    if (out_of_range || dups)
+        return fail(GJ_ERR_ARG, "perfect array: %u build keys outside [%d, %d + %llu), %u duplicate build keys", out_of_range,
+                    key_min, key_min, (unsigned long long)key_range, dups);
+    if (matches) *matches = ctx->h_result[0];
+    if (checksum) *checksum = ctx->h_result[1];
+    if (t) {
+        CK(cudaEventElapsedTime(&t->hist_ms, ctx->ev[0], ctx->ev[2]));   // "hist" slot: table clear + build
+        CK(cudaEventElapsedTime(&t->join_ms, ctx->ev[2], ctx->ev[3]));   // probe
+        CK(cudaEventElapsedTime(&t->total_ms, ctx->ev[0], ctx->ev[3]));
+        t->kernel_launches = ctx->launches;
+        t->wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    }
+    return GJ_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // end-to-end host entry: H2D copies chunked on a copy stream, histograms chase the key chunks
 // ------------------------------------------------------------------------------------------
 static int ensure_host_staging(gj_ctx* ctx) {
-    if (ctx->d_in[0]) return GJ_OK;
+    if (ctx->d_in[0] && ctx->d_in[1] && ctx->d_in[2] && ctx->d_in[3]) return GJ_OK;
     const uint64_t caps[4] = {ctx->maxR, ctx->maxR, ctx->maxS, ctx->maxS};
     for (int i = 0; i < 4; ++i)
-        if (cudaMalloc(&ctx->d_in[i], caps[i] * sizeof(int32_t)) != cudaSuccess) {
+        if (!ctx->d_in[i] && cudaMalloc(&ctx->d_in[i], caps[i] * sizeof(int32_t)) != cudaSuccess) {
             cudaGetLastError();
+            for (int k = 0; k < 4; ++k) { cudaFree(ctx->d_in[k]); ctx->d_in[k] = nullptr; }   // all or nothing
             return fail(GJ_ERR_NOMEM, "cudaMalloc of the host-entry staging columns failed");
         }
     return GJ_OK;
@@ -1870,13 +1935,10 @@ extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void
         PcpCopyArgs a;
         a.stage = ctx->out[which]; a.peer_bases = q.bases[which]; a.t = q.tab[which];
         a.b1 = q.b1; a.bl = q.bl; a.perm = (q.b1 << 8) | q.g;
-        a.l2_hint = ctx->opt_pcp_l2_hint ? 1u : 0u;
         const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
         uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count;   // measured (2 GPUs): 148 CTAs 3.98 ms, 296 CTAs 4.24 ms per step
         grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));
-        // default: the kernel measured in round 1; the experimental variant only on request
-        if (ctx->opt_pcp_ring) pcp_copy_kernel_x<PCP_NS_DEEP, true><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
-        else if (ctx->opt_pcp_l2_hint) pcp_copy_kernel_x<PCP_NS, false><<<grid, 32, pcp_copy_smem(), s>>>(a);
+        if (ctx->opt_pcp_ring) pcp_copy_kernel<PCP_NS_DEEP><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
         else pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
         LAUNCHED();
     }
@@ -1948,55 +2010,6 @@ extern "C" int gj_pcp_join(gj_ctx* ctx, uint64_t cap_R, uint64_t cap_S, void* cu
     uint32_t* hs = reinterpret_cast<uint32_t*>(q.h_pin + 2 * NB_MAX * sizeof(void*));
     for (int w = 0; w < 2; ++w) CK(cudaMemcpyAsync(hs + 4 * w, q.tab[w].status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[3], s));
-    return GJ_OK;
-}
-
-// Join this context's BUILD partitions (relation 0 of its pcp run, already received and partitioned)
-// with a probe relation that a SECOND context on the same GPU received and partitioned (its pcp
-// relation `probe_which`).  Lets the host split the probe side in two halves that travel and are
-// partitioned independently: the join of the first half (gj_pcp_join) runs under the copy of the
-// second, this call then adds the second half's result to the same accumulators.
-extern "C" int gj_pcp_join_ext(gj_ctx* ctx, gj_ctx* probe_ctx, int probe_which, uint64_t cap_build,
-                               uint64_t cap_probe, void* cuda_stream) {
-    if (!ctx || !probe_ctx || !ctx->pcp.active || !probe_ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first (both contexts)");
-    if (probe_which != 0 && probe_which != 1) return fail(GJ_ERR_ARG, "probe_which must be 0 or 1");
-    gj_ctx::PCP& q = ctx->pcp;
-    const gj_ctx::PCP& pq = probe_ctx->pcp;
-    if (ctx->device != probe_ctx->device) return fail(GJ_ERR_ARG, "both contexts must live on the same GPU");
-    if (q.B != pq.B || q.g != pq.g || q.rank != pq.rank) return fail(GJ_ERR_ARG, "the two contexts run different plans");
-    if (q.role_of_side[0] != 0) return fail(GJ_ERR_ARG, "relation 0 of the building context must be its build side (pass the smaller relation first)");
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    CK(cudaStreamWaitEvent(s, ctx->stage_ev[3], 0));
-    const int prole = pq.role_of_side[probe_which];
-    const RelMeta& mb = ctx->meta[0];
-    const RelMeta& mp = probe_ctx->meta[prole];
-    Plan pl; pl.B = q.B; pl.b1 = q.B; pl.b2 = 0;
-    const uint32_t nb = 1u << pl.B;
-    // re-arm the unit scan (descriptors + ticket); the result accumulators behind them keep counting
-    const size_t res_off = (size_t)(reinterpret_cast<unsigned char*>(ctx->result) - ctx->zero_common);
-    CK(cudaMemsetAsync(ctx->zero_common, 0, res_off, s));
-    ScanSeq su;
-    su.in = mb.ghist; su.in2 = mp.ghist; su.out = ctx->unit_base; su.desc = ctx->unit_desc; su.ticket = ctx->unit_ticket;
-    su.mode = SCAN_UNITS; su.param = unit_tuples(ctx); su.param2 = 0;
-    int rc;
-    if ((rc = enqueue_scan_one(ctx, s, su, nb))) return rc;
-    PlanArgs a;
-    memset(&a, 0, sizeof(a));
-    a.rel[0].off = mb.off; a.rel[1].off = mp.off;
-    a.nrel = 0; a.with_units = 1; a.b1 = pl.B; a.b2 = 0; a.tile = 4096; a.unit = unit_tuples(ctx);
-    a.unit_base = ctx->unit_base; a.units = ctx->units;
-    plan_kernel<<<128, PLAN_THREADS, 0, s>>>(a);
-    LAUNCHED();
-    if ((rc = enqueue_join(ctx, s, ctx->out[0], probe_ctx->out[probe_which], pl, cap_build, cap_probe, false,
-                           nullptr, nullptr, 0, nullptr, (int)q.g))) return rc;
-    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(ctx->ev[3], s));
-    // the probe context never joins: hand its status words to its own gj_pcp_finish
-    uint32_t* hs = reinterpret_cast<uint32_t*>(probe_ctx->pcp.h_pin + 2 * NB_MAX * sizeof(void*));
-    for (int i = 0; i < 4; ++i) hs[4 * (1 - probe_which) + i] = 0;
-    CK(cudaMemcpyAsync(hs + 4 * probe_which, pq.tab[probe_which].status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(probe_ctx->ev[3], s));
     return GJ_OK;
 }
 

@@ -727,85 +727,6 @@ pcp_copy_kernel(PcpCopyArgs a) {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// Experimental variant of pcp_copy_kernel (NOT YET RUN ON A GPU; options "pcp_ring", "pcp_l2_hint"): same
-// pipeline, plus an optional L2 evict-first policy on the bulk copies and, CONTIG, one contiguous
-// range of pieces per CTA (mostly the same chunk: its table entries stay in registers, no search per
-// piece) -- for running the copy on a few SMs only with a deep ring.
-template <int NS, bool CONTIG>
-__global__ void __launch_bounds__(32)
-pcp_copy_kernel_x(PcpCopyArgs a) {
-    constexpr uint32_t LAG = NS - 2;
-    static_assert(NS >= 3, "ring too small");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    tup_t* ring = reinterpret_cast<tup_t*>(smem_raw);                                   // [NS][PCP_PIECE]
-    uint32_t* s_prefix = reinterpret_cast<uint32_t*>(smem_raw + (size_t)NS * PCP_PIECE * sizeof(tup_t));   // [n1 + 1]
-    __shared__ uint64_t s_full[NS];
-    __shared__ tup_t* s_dst[NS];
-    __shared__ uint32_t s_bytes[NS];
-    const uint32_t n1 = 1u << a.b1;
-    if (a.t.status[0]) return;
-    for (uint32_t i = threadIdx.x; i <= n1; i += 32) s_prefix[i] = a.t.piece_prefix[i];
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) mbar_init(&s_full[s], 1);
-        fence_mbar_init();
-    }
-    __syncwarp();
-    if (threadIdx.x != 0) return;
-    const uint32_t total = s_prefix[n1];
-    const uint64_t pol = a.l2_hint ? l2_policy_evict_first() : 0ull;
-    uint32_t issued = 0, stored = 0;
-    uint32_t k_begin = blockIdx.x, k_end = total, k_step = gridDim.x;
-    if (CONTIG) {
-        const uint32_t per = (total + gridDim.x - 1u) / gridDim.x;
-        k_begin = min(total, blockIdx.x * per); k_end = min(total, k_begin + per); k_step = 1u;
-    }
-    uint32_t lo = 0xFFFFFFFFu, src0 = 0, dst0 = 0, cnt = 0;     // CONTIG: the current chunk's table entries
-    tup_t* dbase = nullptr;
-    for (uint32_t k = k_begin; k < k_end || stored < issued; k += k_step) {
-        if (k < k_end) {
-            if (!CONTIG || lo == 0xFFFFFFFFu || k < s_prefix[lo] || k >= s_prefix[lo + 1u]) {
-                uint32_t l = 0, hi = n1;          // largest position whose prefix is <= k
-                while (hi - l > 1) { const uint32_t m = (l + hi) >> 1; if (s_prefix[m] <= k) l = m; else hi = m; }
-                lo = l;
-                const uint32_t cc = tile_perm(lo, a.perm);
-                src0 = a.t.src_start[cc]; dst0 = a.t.dst_start[cc]; cnt = a.t.cnt[cc];
-                dbase = a.peer_bases[cc >> a.bl];
-            }
-            const uint32_t slice = k - s_prefix[lo];
-            const uint32_t phase = src0 & 1u;     // == dst0 & 1 by construction
-            const tup_t* src = a.stage + src0;
-            tup_t* dst = dbase + dst0;
-            if (slice == 0 && phase) *dst = *src;                     // odd first slot: plain 8-byte copy
-            const uint32_t body0 = phase + slice * PCP_PIECE;         // even slot on both sides
-            uint32_t m = (cnt > body0) ? min(PCP_PIECE, cnt - body0) : 0u;
-            if (m & 1u) { dst[body0 + m - 1u] = src[body0 + m - 1u]; --m; }   // odd tail (last piece only)
-            const uint32_t slot = issued % NS;
-            // the slot's previous tenant (piece issued - NS) was stored at least NS - 1 - LAG groups ago
-            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NS - 1 - LAG) : "memory");
-            s_dst[slot] = dst + body0;
-            s_bytes[slot] = m * (uint32_t)sizeof(tup_t);
-            mbar_arrive_expect_tx(&s_full[slot], m * (uint32_t)sizeof(tup_t));
-            if (m) {
-                if (a.l2_hint) bulk_g2s_hint(ring + (size_t)slot * PCP_PIECE, src + body0, m * (uint32_t)sizeof(tup_t), &s_full[slot], pol);
-                else bulk_g2s(ring + (size_t)slot * PCP_PIECE, src + body0, m * (uint32_t)sizeof(tup_t), &s_full[slot]);
-            }
-            ++issued;
-        }
-        // keep at most LAG loads ahead of the stores; drain once the pieces are exhausted
-        while (stored < issued && (k >= k_end || issued - stored > LAG)) {
-            const uint32_t slot = stored % NS;
-            mbar_wait(&s_full[slot], (stored / NS) & 1u);
-            if (s_bytes[slot]) {
-                if (a.l2_hint) bulk_s2g_hint(s_dst[slot], ring + (size_t)slot * PCP_PIECE, s_bytes[slot], pol);
-                else bulk_s2g(s_dst[slot], ring + (size_t)slot * PCP_PIECE, s_bytes[slot]);
-            }
-            bulk_commit();
-            ++stored;
-        }
-    }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
 // ------------------------------------------------------------------------------------------
 // 4. Radix scatter pass.  One tile of THREADS*IPT tuples per CTA:
 //      load (16-byte loads, registers) -> shared-memory histogram that also yields each tuple's
@@ -1085,7 +1006,7 @@ __device__ __forceinline__ unsigned long long pair_value(const JoinArgs& a, uint
     return (unsigned long long)v;
 }
 
-constexpr int JOIN_STAGE_PAIRS = 2048;   // staged result pairs per CTA (materialise)
+constexpr int JOIN_STAGE_PAIRS = 4096;   // staged result pairs per CTA (materialise): 32 KB
 constexpr uint32_t STEP_DONE = 0xFFFFFFFFu;
 // head word = MULTI(1) | version(15) | entry index(16).  A head is live only if its version equals
 // the current build chunk's, so the table is never cleared between chunks.
@@ -1123,19 +1044,20 @@ join_kernel(JoinArgs a) {
     uint64_t* s_rfull = s_sfull + NS;                                         // [NR]
     uint64_t* s_sempty = s_rfull + NR;                                        // [NS]
     uint64_t* s_rempty = s_sempty + NS;                                       // [NR]
-    __shared__ uint32_t s_cnt;
+    __shared__ uint32_t s_cnt, s_flush[2];
     __shared__ unsigned long long s_base;
     __shared__ unsigned long long s_red[2][THREADS / 32];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t nunits = *a.num_units;
     unsigned long long matches = 0, sum = 0;
+    uint32_t mat_round = 0;                    // materialise: rounds so far (uniform over the consumers)
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&s_sfull[s], 1); mbar_init(&s_sempty[s], 1); }
         for (int s = 0; s < NR; ++s) { mbar_init(&s_rfull[s], 1); mbar_init(&s_rempty[s], 1); }
         fence_mbar_init();
-        if (MATERIALIZE) s_cnt = 0;
+        if (MATERIALIZE) { s_cnt = 0; s_flush[0] = s_flush[1] = 0; }
     }
     // version 0 is never used by a chunk (versions are 1..0x7FFF), so an all-zero table is empty
     for (uint32_t i = tid; i < (uint32_t)CAP / 4; i += THREADS)
@@ -1330,23 +1252,43 @@ join_kernel(JoinArgs a) {
                 matches += m32;
             }
             const uint32_t rounds = (ns + NC - 1) / NC;
-            for (uint32_t q = 0; MATERIALIZE && q < rounds; ++q) {
+            for (uint32_t q = 0; MATERIALIZE && q < rounds; ++q, ++mat_round) {
+                // One probe tuple per thread and round.  The chain walk is warp-uniform: every iteration
+                // the warp ballots its hits and ONE lane reserves staging slots for all of them
+                // (north_star (2); the reference does the same per 16-pair warp buffer,
+                // join-primitives.cu:1212-1262).
                 const uint32_t j = q * NC + tid;
+                tup_t t = make_uint2(0u, 0u);
+                uint32_t w = 0, i = 0xFFFFu;
                 if (j < ns) {
-                    const tup_t t = sbuf[j];
+                    t = sbuf[j];
                     const uint32_t kk = t.x >> a.hash_shift;
-                    const uint32_t w = head[(kk ^ (kk >> hb)) & hmask];
-                    uint32_t i = ((w & HEAD_VER_MASK) == ver) ? (w & 0xFFFFu) : 0xFFFFu;
-                    while (i != 0xFFFFu) {
-                        const tup_t r = rbuf[i];
-                        if (r.x == t.x) {
+                    w = head[(kk ^ (kk >> hb)) & hmask];
+                    if ((w & HEAD_VER_MASK) == ver) i = w & 0xFFFFu;
+                }
+                const uint32_t lane = tid & 31u;
+                while (__any_sync(0xffffffffu, i != 0xFFFFu)) {
+                    tup_t r = make_uint2(0u, 0u);
+                    bool hit = false;
+                    if (i != 0xFFFFu) {
+                        r = rbuf[i];
+                        hit = (r.x == t.x);
+                        i = (w & HEAD_MULTI) ? (uint32_t)next[i] : 0xFFFFu;
+                    }
+                    const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+                    if (hits) {
+                        const int leader = __ffs(hits) - 1;
+                        uint32_t base = 0;
+                        if ((int)lane == leader) base = atomicAdd(&s_cnt, (uint32_t)__popc(hits));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (hit) {
                             ++matches;
                             sum += pair_value<false>(a, r.y, t.y);
-                            const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                            const uint32_t pos = base + (uint32_t)__popc(hits & ((1u << lane) - 1u));
                             if (pos < (uint32_t)JOIN_STAGE_PAIRS) {
                                 s_out_b[pos] = (int32_t)r.y;
                                 s_out_p[pos] = (int32_t)t.y;
-                            } else {   // staging full inside a round: rare direct path
+                            } else {   // staging full inside a round (N:M bursts): rare direct path
                                 const unsigned long long g = atomicAdd(&a.result[2], 1ull);
                                 if (g < a.cap) {
                                     a.out_bld_pay[g] = (int32_t)r.y;
@@ -1354,24 +1296,33 @@ join_kernel(JoinArgs a) {
                                 }
                             }
                         }
-                        i = (w & HEAD_MULTI) ? (uint32_t)next[i] : 0xFFFFu;
                     }
                 }
                 named_bar_sync(BAR_C, NC);
-                const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE_PAIRS);
-                if (c + NC > (uint32_t)JOIN_STAGE_PAIRS) {
+                // Flush decision: must be the SAME in every consumer thread (the flush below contains
+                // barriers).  s_cnt itself may already be growing again (a fast warp is in the next
+                // round), so threads do not look at it: thread 0 alone samples it and publishes the
+                // verdict one round ahead in s_flush[parity]; the barrier above orders its write before
+                // everybody's read.  With <= 1 match per probe tuple the staging area never overflows
+                // (flush once more than STAGE - 2 NC pairs may be staged); beyond that the direct path
+                // above keeps the result exact.
+                const bool do_flush = s_flush[mat_round & 1u] != 0u;
+                if (do_flush) {
+                    const uint32_t c = min(s_cnt, (uint32_t)JOIN_STAGE_PAIRS);   // stable: every consumer is between the barriers
                     if (tid == 0) s_base = atomicAdd(&a.result[2], (unsigned long long)c);
                     named_bar_sync(BAR_C, NC);
                     const unsigned long long g0 = s_base;
-                    for (uint32_t i = tid; i < c; i += NC) {
-                        if (g0 + i < a.cap) {
-                            a.out_bld_pay[g0 + i] = s_out_b[i];
-                            a.out_prb_pay[g0 + i] = s_out_p[i];
+                    for (uint32_t x = tid; x < c; x += NC) {
+                        if (g0 + x < a.cap) {
+                            a.out_bld_pay[g0 + x] = s_out_b[x];
+                            a.out_prb_pay[g0 + x] = s_out_p[x];
                         }
                     }
                     named_bar_sync(BAR_C, NC);
-                    if (tid == 0) s_cnt = 0;
+                    if (tid == 0) { s_cnt = 0; s_flush[(mat_round + 1u) & 1u] = 0u; }
                     named_bar_sync(BAR_C, NC);
+                } else if (tid == 0) {
+                    s_flush[(mat_round + 1u) & 1u] = (s_cnt + 2u * NC > (uint32_t)JOIN_STAGE_PAIRS) ? 1u : 0u;
                 }
             }
             named_bar_sync(BAR_C, NC);       // every consumer is done with this step's slots (and the table)
@@ -1445,6 +1396,54 @@ np_probe_kernel(const int32_t* __restrict__ bk, const int32_t* __restrict__ bp, 
             if (bk[e - 1u] == key) {
                 ++matches;
                 sum += (unsigned long long)((long long)bp[e - 1u] * (long long)pay);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        matches += __shfl_xor_sync(0xffffffffu, matches, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31u) == 0) { s_red[0][threadIdx.x >> 5] = matches; s_red[1][threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = 0, s = 0;
+        for (int w = 0; w < 8; ++w) { m += s_red[0][w]; s += s_red[1][w]; }
+        if (m) atomicAdd(&result[0], m);
+        if (s) atomicAdd(&result[1], s);
+    }
+}
+
+// 5c. Perfect-array variant (reference build_perfect_array / probe_perfect_array,
+//     join-primitives.cu:628-668): build keys are unique and lie in [key_min, key_min + range), so
+//     the key itself addresses a table slot -- no hash, no chain, no key compare.  A slot is the
+//     64-bit word (1 << 32) | payload, 0 = empty (the reference stores payload + 1 in an int32 and
+//     so loses the payload -1).  The build checks its own precondition: status[0] counts keys out
+//     of range, status[1] duplicates (atomicExch returned a live slot).
+__global__ void __launch_bounds__(256)
+np_build_perfect_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ pays, uint32_t n, int32_t key_min,
+                        uint32_t range, unsigned long long* __restrict__ slots, uint32_t* __restrict__ status) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)__ldg(keys + i) - (uint32_t)key_min;
+        if (k >= range) { atomicAdd(&status[0], 1u); continue; }
+        const unsigned long long old = atomicExch(&slots[k], (1ull << 32) | (uint32_t)__ldg(pays + i));
+        if (old) atomicAdd(&status[1], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+np_probe_perfect_kernel(const unsigned long long* __restrict__ slots, int32_t key_min, uint32_t range,
+                        const int32_t* __restrict__ pk, const int32_t* __restrict__ pp, uint32_t n,
+                        unsigned long long* __restrict__ result) {
+    __shared__ unsigned long long s_red[2][8];
+    unsigned long long matches = 0, sum = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)__ldg(pk + j) - (uint32_t)key_min;
+        if (k < range) {
+            const unsigned long long sl = __ldg(slots + k);
+            if (sl) {
+                ++matches;
+                sum += (unsigned long long)((long long)(int32_t)(uint32_t)sl * (long long)__ldg(pp + j));
             }
         }
     }

@@ -360,80 +360,6 @@ class GpuOps:
             ph["trace_ms"] = {n: round(trace[0][1].elapsed_time(e), 3) for n, e in trace[1:]}
         return m, c, (n_r, n_s), ph
 
-    def pcp2_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob):
-        """Mode "pcp2" = pcp with the PROBE side cut in two halves (rows) that travel and are partitioned
-        independently (the second half through a second engine context): the receiver pass + join of
-        the first half run under the copy of the second, so only half of that tail stays exposed.
-        NOT YET RUN ON A GPU (written after round 1's GPU budget was spent)."""
-        torch, e1 = self.torch, self.engine
-        caps = [self.cap_R, self.cap_S]
-        order = (1, 0) if n_glob[0] > n_glob[1] else (0, 1)          # build on the globally smaller relation
-        (bk, bp), (pk, pp) = rels[order[0]], rels[order[1]]
-        h = (pk.numel() // 2) & ~3                                    # 16-byte aligned cut
-        if not n_glob[0] or not n_glob[1] or h == 0:
-            return self.pcp_join(dist, group, rank, rels, G, B, peers, own_ptrs, n_glob)
-        cap_b, cap_p = caps[order[0]], caps[order[1]]
-        half_cap = (cap_p // 2) & ~1
-        if getattr(self, "_engine2", None) is None or self._engine2.max_S < half_cap:
-            from .engine import JoinEngine
-            self._engine2 = JoinEngine(16, half_cap, self.device)
-            self._stream3 = torch.cuda.Stream(self.device)
-        e2 = self._engine2
-        e2.set_option("pass1_bits", e1.get_option("pass1_bits"))
-        sR, sA, sB = self.stream_shuffle, self.stream_local, self._stream3
-        cur = torch.cuda.current_stream(self.device)
-        for s in (sR, sA, sB):
-            s.wait_stream(cur)
-        e1.pcp_begin(min(n_glob), max(n_glob), G, rank, B, sR)
-        e2.pcp_begin(1, max(n_glob), G, rank, B, sB)
-        g, bl, _ = e1.pcp_plan()
-        n1 = 1 << (g + bl)
-        if getattr(self, "_pcp2_key", None) != (G, n1):
-            self._pcp2_hist = [torch.empty(n1, dtype=torch.int32, device=self.dev) for _ in range(3)]
-            self._pcp2_all = [torch.empty(G * n1, dtype=torch.int32, device=self.dev) for _ in range(3)]
-            self._pcp2_tok = [torch.zeros(1, dtype=torch.int32, device=self.dev) for _ in range(3)]
-            self._pcp2_key = (G, n1)
-        # slots: 0 = build (e1 relation 0), 1 = first probe half (e1 relation 1), 2 = second half (e2 relation 1)
-        eng = (e1, e1, e2)
-        which = (0, 1, 1)
-        strm = (sR, sA, sB)
-        cols = ((bk, bp), (pk[:h], pp[:h]), (pk[h:], pp[h:]))
-        cap = (cap_b, half_cap, half_cap)
-        pb, pq_ = peers[order[0]], peers[order[1]]
-        dest = (list(pb), list(pq_), [int(x) + half_cap * 8 for x in pq_])
-        own = (own_ptrs[order[0]], own_ptrs[order[1]], own_ptrs[order[1]] + half_cap * 8)
-        for i in range(3):
-            eng[i].pcp_hist(which[i], cols[i][0], self._pcp2_hist[i], strm[i])
-            with torch.cuda.stream(strm[i]):
-                dist.all_gather_into_tensor(self._pcp2_all[i], self._pcp2_hist[i], group=group)
-        part_done = copy_done = None
-        for i in range(3):
-            s = strm[i]
-            if part_done is not None:
-                s.wait_event(part_done)                               # source passes one after the other ...
-            eng[i].pcp_part(which[i], cols[i][0], cols[i][1], self._pcp2_all[i], cap[i], s)
-            part_done = torch.cuda.Event(); part_done.record(s)
-            if copy_done is not None:
-                s.wait_event(copy_done)                               # ... and one relation on NVLink at a time
-            eng[i].pcp_copy(which[i], dest[i], s)
-            copy_done = torch.cuda.Event(); copy_done.record(s)
-            with torch.cuda.stream(s):
-                dist.all_reduce(self._pcp2_tok[i], group=group)       # every rank's copies have landed
-        for i in range(3):
-            eng[i].pcp_recv(which[i], own[i], cap[i], strm[i])
-        sA.wait_stream(sR)                                            # build side received and partitioned
-        e1.pcp_join(cap_b, half_cap, sA)                              # first half: under the second half's copy
-        sB.wait_stream(sA)
-        e1.pcp_join_ext(e2, 1, cap_b, half_cap, sB)
-        m, c, n_b, n_p1, ph, bits = e1.pcp_finish()
-        _, _, _, n_p2, _, _ = e2.pcp_finish(phases=False)
-        for s in (sR, sA):
-            s.synchronize()
-        local = [0, 0]
-        local[order[0]], local[order[1]] = n_b, n_p1 + n_p2
-        ph = dict(ph, shuffle_scatter_ms=None, radix_bits=B, pass1_bits=bits[0] + bits[1], pass2_bits=bits[2])
-        return m, c, tuple(local), ph
-
     def exchange_counts(self, dist, group, mine):
         """All ranks' count vectors in ONE small NCCL all-gather (doubles as a barrier)."""
         t = self.torch.tensor([int(x) for x in mine], dtype=self.torch.int64, device=self.dev)
@@ -480,14 +406,14 @@ class ShardedJoin:
         self.max_local = (max_local_R, max_local_S)
         self._peers = None
         self._own = [0, 0]
-        if mode in ("p2p", "dma", "pp", "pcp", "pcp2"):
+        if mode in ("p2p", "dma", "pp", "pcp"):
             if ops is None:
                 self._setup_peers()
             else:                      # test stand-in: no device buffers to map
                 self._peers = [[0] * self.world, [0] * self.world]
                 self._opened = []
         elif mode != "nccl":
-            raise ValueError("mode must be 'auto', 'nccl', 'p2p', 'dma', 'pp', 'pcp' or 'pcp2'")
+            raise ValueError("mode must be 'auto', 'nccl', 'p2p', 'dma', 'pp' or 'pcp'")
 
     # -- CUDA IPC mapping of every rank's receive buffers (p2p mode) -------------------------
     def _setup_peers(self):
@@ -553,8 +479,8 @@ class ShardedJoin:
         shift = B
         rels = ((Rk, Rp), (Sk, Sp))
         local_n = [0, 0]
-        if self.mode in ("pp", "pcp", "pcp2"):
-            run = {"pp": ops.pp_join, "pcp": ops.pcp_join, "pcp2": getattr(ops, "pcp2_join", None)}[self.mode]
+        if self.mode in ("pp", "pcp"):
+            run = {"pp": ops.pp_join, "pcp": ops.pcp_join}[self.mode]
             m, c, local_n, tm = run(dist, self.group, rank, rels, G, B, self._peers, self._own, (n_R_global, n_S_global))
             lap()
         elif self.mode == "nccl":
@@ -605,13 +531,13 @@ class ShardedJoin:
                 tm = dict(tm, shuffle_scatter_ms=shuffle_ms)
         if self.mode == "nccl":
             m, c, tm = ops.local_join(local_n[0], local_n[1])
-        if self.mode not in ("pp", "pcp", "pcp2"):
+        if self.mode not in ("pp", "pcp"):
             lap()
         res = ops.result_tensor(m, c)
         dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
         vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
         lap()
-        if self.mode in ("pp", "pcp", "pcp2"):
+        if self.mode in ("pp", "pcp"):
             d = [1e3 * (b - a) for a, b in zip(t_host, t_host[1:])]
             tm = dict(tm, host_ms={"pipeline": d[0], "reduce": d[1]})
         elif self.mode != "nccl" and len(t_host) == 5:

@@ -20,11 +20,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 C_ABI_SYMBOLS = [
     "gj_create", "gj_destroy", "gj_last_error", "gj_version", "gj_set_stream", "gj_set_option",
     "gj_get_option", "gj_join_aggregate", "gj_join_aggregate_tuples", "gj_join_aggregate_host",
-    "gj_join_materialize", "gj_join_aggregate_late", "gj_join_aggregate_nopart", "gj_join_aggregate_stream_host", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
+    "gj_join_materialize", "gj_join_aggregate_late", "gj_join_aggregate_nopart", "gj_join_aggregate_perfect", "gj_join_aggregate_stream_host", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
     "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_stage_pass_ms", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
     "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv", "gj_pcp_join",
-    "gj_pcp_join_ext", "gj_pcp_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
+    "gj_pcp_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
     "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_device_synchronize", "gj_flush_l2",
     "gj_kernel_launch_count",
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.gj_join_aggregate.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_join_aggregate_host.argtypes = L.gj_join_aggregate.argtypes
     L.gj_join_aggregate_nopart.argtypes = L.gj_join_aggregate.argtypes
+    L.gj_join_aggregate_perfect.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, C.c_int32, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_join_aggregate_stream_host.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_join_aggregate_tuples.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
     L.gj_join_materialize.argtypes = [vp, i32p, i32p, u64, i32p, i32p, u64, i32p, i32p, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(Timings)]
@@ -120,7 +121,6 @@ def lib() -> C.CDLL:
     L.gj_pcp_copy.argtypes = [vp, C.c_int, C.POINTER(vp), vp]
     L.gj_pcp_recv.argtypes = [vp, C.c_int, vp, u64, vp]
     L.gj_pcp_join.argtypes = [vp, u64, u64, vp]
-    L.gj_pcp_join_ext.argtypes = [vp, vp, C.c_int, u64, u64, vp]
     L.gj_pcp_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(u32)]
     L.gj_generate_unique.argtypes = [vp, i32p, i32p, u64, u64, u64, u32, u32]
     L.gj_bijection.argtypes = [u64, u64, u32]
@@ -244,6 +244,16 @@ class JoinEngine:
         _check(self._L.gj_join_aggregate_nopart(self._ctx, _dev_ptr(Rk, nR, "Rk"), _dev_ptr(Rp, nR, "Rp"), nR,
                                                 _dev_ptr(Sk, nS, "Sk"), _dev_ptr(Sp, nS, "Sp"), nS,
                                                 C.byref(m), C.byref(c), C.byref(t)))
+        return JoinResult(int(m.value), int(c.value), t)
+
+    def join_aggregate_perfect(self, Rk, Rp, Sk, Sp, key_min: int, key_range: int) -> JoinResult:
+        """Non-partitioned perfect-array join: unique build keys in [key_min, key_min + key_range)."""
+        self._sync_inputs()
+        nR, nS = Rk.numel(), Sk.numel()
+        m, c, t = C.c_uint64(), C.c_uint64(), Timings()
+        _check(self._L.gj_join_aggregate_perfect(self._ctx, _dev_ptr(Rk, nR, "Rk"), _dev_ptr(Rp, nR, "Rp"), nR,
+                                                 _dev_ptr(Sk, nS, "Sk"), _dev_ptr(Sp, nS, "Sp"), nS,
+                                                 int(key_min), int(key_range), C.byref(m), C.byref(c), C.byref(t)))
         return JoinResult(int(m.value), int(c.value), t)
 
     def join_aggregate_tuples(self, Rt, nR, St, nS) -> JoinResult:
@@ -464,9 +474,6 @@ class JoinEngine:
 
     def pcp_join(self, cap_R: int, cap_S: int, stream=None):
         _check(self._L.gj_pcp_join(self._ctx, cap_R, cap_S, self._sptr(stream)))
-
-    def pcp_join_ext(self, probe_engine, probe_which: int, cap_build: int, cap_probe: int, stream=None):
-        _check(self._L.gj_pcp_join_ext(self._ctx, probe_engine._ctx, probe_which, cap_build, cap_probe, self._sptr(stream)))
 
     def pcp_finish(self, phases: bool = True):
         """Returns (matches, checksum, tuples received of R, of S, phase_ms dict, (gpu bits, source bits, receiver bits))."""

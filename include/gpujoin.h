@@ -80,7 +80,6 @@ int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
  *   "gpu_bits"     number of key bits above the radix field consumed by the multi-GPU shuffle
  *   "shuffle_grid" persistent CTA count of the peer-store scatter (0 = one tile per CTA)
  *   "pp_out", "pp_tile16k"  sharded pipeline, see gj_pp_begin
- *   "pcp_l2_hint"  1: the pcp copy kernel's bulk loads / stores carry an L2 evict-first policy (default 0)
  *   "pcp_ring"     1: the pcp copy kernel uses a 12-slot ring (10 bulk loads in flight per CTA) -- for running it on
  *                  few SMs ("shuffle_grid" = 16..32) so the passes next to it keep their occupancy (default 0)
  *   "nopart_max"   gj_join_aggregate takes the non-partitioned path (gj_join_aggregate_nopart) when the
@@ -153,6 +152,17 @@ int gj_join_aggregate_late(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Ri
 int gj_join_aggregate_nopart(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
                              const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS,
                              uint64_t* matches, uint64_t* checksum, gj_timings* t);
+
+/* Perfect-array variant of the non-partitioned baseline (replaces build_perfect_array /
+ * probe_perfect_array, join-primitives.cu:628-668): the key itself addresses a table of key_range slots,
+ * slot = key - key_min; no hash, no chains, no key compare.  Precondition (checked on the device, GJ_ERR_ARG
+ * when violated): the keys of the build side (the smaller relation; R when equal) are unique and lie in
+ * [key_min, key_min + key_range).  A slot is a 64-bit word {1, payload}, so every int32 payload survives
+ * (the reference stores payload + 1 in an int32, which drops the payload -1).  timings as for _nopart. */
+int gj_join_aggregate_perfect(gj_ctx* ctx, const int32_t* d_Rk, const int32_t* d_Rp, uint64_t nR,
+                              const int32_t* d_Sk, const int32_t* d_Sp, uint64_t nS,
+                              int32_t key_min, uint64_t key_range,
+                              uint64_t* matches, uint64_t* checksum, gj_timings* t);
 
 /* ---- the partitioner on its own --------------------------------------------------------------
  * Replaces prepare_Relation_payload (join-primitives.cu:1582-1613: init_metadata_double,
@@ -271,15 +281,6 @@ int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, uint64_t cap_tuples, 
 int gj_pcp_join(gj_ctx* ctx, uint64_t cap_R, uint64_t cap_S, void* cuda_stream);
 int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
                   uint64_t* n_local_S, float* phase_ms, uint32_t* plan_bits);
-/* Probe split: joins ctx's build partitions (relation 0 of its pcp run; must be its build side) with a
- * probe relation that a SECOND context on the same GPU received and partitioned (relation probe_which of
- * its pcp run, same n_gpus / rank / local_bits), adding to ctx's accumulators.  With the probe side cut
- * in two halves that travel independently, gj_pcp_join of the first half runs under the copy of the
- * second.  Afterwards gj_pcp_finish(ctx) returns the total; gj_pcp_finish(probe_ctx, ..., phase_ms = NULL)
- * reports the probe half's received count / overflow. */
-int gj_pcp_join_ext(gj_ctx* ctx, gj_ctx* probe_ctx, int probe_which, uint64_t cap_build,
-                    uint64_t cap_probe, void* cuda_stream);
-
 /* CUDA IPC plumbing for the peer-store variant when every GPU is driven by its own process:
  * export a gj_malloc_device allocation as a 64-byte handle, open a peer's handle (peer access is
  * enabled lazily), close it again. */

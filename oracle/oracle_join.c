@@ -220,7 +220,10 @@ typedef struct { int32_t k, p; } tup;
 
 static int pick_threads(int want) {
 #ifdef _OPENMP
-    int mx = omp_get_max_threads();
+    /* want <= 0: OpenMP's default (OMP_NUM_THREADS / all cores).  An explicit count may exceed
+     * that default -- torch.distributed.run exports OMP_NUM_THREADS=1 -- up to the processors
+     * this process may run on. */
+    int mx = want > 0 ? omp_get_num_procs() : omp_get_max_threads();
     if (want <= 0 || want > mx) want = mx;
     return want < 1 ? 1 : want;
 #else
@@ -229,12 +232,17 @@ static int pick_threads(int want) {
 }
 int orc_max_threads(void) { return pick_threads(0); }
 
-/* One parallel radix pass over [0,n): per-thread histograms, prefix, scatter
- * (structure of partition-primitives.cu:60-125, minus the AVX2 write-combining). */
+/* One parallel radix pass over [0,n): per-thread histograms, prefix, scatter through
+ * software write-combining buffers -- one cache line (8 tuples) per partition and thread,
+ * written out when full (structure of partition-primitives.cu:60-125; plain 64-byte copies
+ * where the reference streams with AVX2 non-temporal stores). */
+#define SWWC_TUPLES 8
+#define SWWC_MAX_PARTS 2048
 static void pass_parallel(const int32_t *k, const int32_t *p, const tup *in, uint64_t n,
                           uint32_t shift, uint32_t bits, tup *out, uint64_t *offsets, int T) {
     uint64_t parts = 1ull << bits;
     uint64_t *hist = (uint64_t *)calloc((size_t)T * parts, sizeof(uint64_t));
+    const int swwc = parts <= SWWC_MAX_PARTS;
 #pragma omp parallel num_threads(T)
     {
 #ifdef _OPENMP
@@ -260,10 +268,32 @@ static void pass_parallel(const int32_t *k, const int32_t *p, const tup *in, uin
             }
             offsets[parts] = run;
         }
-        if (in) for (uint64_t i = lo; i < hi; ++i) out[h[digit_of(in[i].k, shift, bits)]++] = in[i];
-        else    for (uint64_t i = lo; i < hi; ++i) {
-            tup x = {k[i], p[i]};
-            out[h[digit_of(k[i], shift, bits)]++] = x;
+        if (swwc) {
+            tup *buf = (tup *)aligned_alloc(64, parts * SWWC_TUPLES * sizeof(tup));
+            uint8_t *fill = (uint8_t *)calloc(parts, 1);
+            for (uint64_t i = lo; i < hi; ++i) {
+                tup x;
+                if (in) x = in[i]; else { x.k = k[i]; x.p = p[i]; }
+                uint64_t d = digit_of(x.k, shift, bits);
+                tup *line = buf + d * SWWC_TUPLES;
+                line[fill[d]] = x;
+                if (++fill[d] == SWWC_TUPLES) {
+                    memcpy(out + h[d], line, SWWC_TUPLES * sizeof(tup));
+                    h[d] += SWWC_TUPLES;
+                    fill[d] = 0;
+                }
+            }
+            for (uint64_t d = 0; d < parts; ++d)
+                for (uint8_t j = 0; j < fill[d]; ++j) out[h[d]++] = buf[d * SWWC_TUPLES + j];
+            free(fill);
+            free(buf);
+        } else if (in) {
+            for (uint64_t i = lo; i < hi; ++i) out[h[digit_of(in[i].k, shift, bits)]++] = in[i];
+        } else {
+            for (uint64_t i = lo; i < hi; ++i) {
+                tup x = {k[i], p[i]};
+                out[h[digit_of(k[i], shift, bits)]++] = x;
+            }
         }
     }
     free(hist);

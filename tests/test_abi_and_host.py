@@ -142,10 +142,10 @@ def test_new_entry_points_reject_bad_calls_without_a_gpu(gj):
         (L.gj_pcp_copy(null, 0, None, null), GJ_ERR_STATE),
         (L.gj_pcp_recv(null, 0, null, 0, null), GJ_ERR_STATE),
         (L.gj_pcp_join(null, 0, 0, null), GJ_ERR_STATE),
-        (L.gj_pcp_join_ext(null, null, 0, 0, 0, null), GJ_ERR_STATE),
         (L.gj_pcp_finish(null, None, None, None, None, None, None), GJ_ERR_STATE),
         (L.gj_join_aggregate_late(null, null, null, 0, null, null, 0, null, 0, 0, null, 0, 0, None, None, None), GJ_ERR_ARG),
         (L.gj_join_aggregate_nopart(null, null, null, 0, null, null, 0, None, None, None), GJ_ERR_ARG),
+        (L.gj_join_aggregate_perfect(null, null, null, 0, null, null, 0, 0, 1, None, None, None), GJ_ERR_ARG),
         (L.gj_join_aggregate_stream_host(null, null, null, 0, null, null, 0, 1, None, None, None), GJ_ERR_ARG),
         (L.gj_stage_pass_ms(null, None), GJ_ERR_ARG),
     ]

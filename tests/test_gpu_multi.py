@@ -49,10 +49,7 @@ def _worker(rank, world, port, n_local, mode, overlap, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,overlap", [("nccl", False), ("p2p", False), ("p2p", True), ("dma", True), ("pp", True), ("pcp", True),
-                                          pytest.param("pcp2", True, marks=pytest.mark.skipif(
-                                              not os.environ.get("GJ_RUN_UNVERIFIED"),
-                                              reason="probe-split pipeline: written without GPU access at the end of round 1"))])
+@pytest.mark.parametrize("mode,overlap", [("nccl", False), ("p2p", False), ("p2p", True), ("dma", True), ("pp", True), ("pcp", True)])
 def test_sharded_join_on_real_gpus(mode, overlap):
     import torch
     import torch.multiprocessing as mp

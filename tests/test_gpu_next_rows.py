@@ -1,23 +1,15 @@
-"""SURVEY.md section 8f rows started at the end of round 1, through the C ABI against the oracle:
+"""SURVEY.md section 8f rows, through the C ABI against the oracle:
   * late-materialisation join (rank 1): gj_join_aggregate_late vs oracle.join_late, the restatement of
     join_partitioned_varpayload (join-primitives.cu:1420-1557);
-  * non-partitioned baseline (rank 4): gj_join_aggregate_nopart (build_ht_chains / chains_probing,
-    join-primitives.cu:681-742) vs the oracle's join checker;
+  * non-partitioned baselines (rank 4): gj_join_aggregate_nopart (build_ht_chains / chains_probing,
+    join-primitives.cu:681-742) and gj_join_aggregate_perfect (build_perfect_array / probe_perfect_array,
+    join-primitives.cu:628-668) vs the oracle's join checker;
   * out-of-HBM probe side (rank 3): gj_join_aggregate_stream_host (outOfGPU_Join3_payload,
-    hash_join_clustered_probe.cu:1684-1984) vs the oracle's join checker;
-  * probe-split multi-GPU pipeline (pcp2) with virtual shards.
-
-NOT YET RUN ON A GPU: these kernels, entry points and tests were written after round 1's GPU budget was
-spent.  They are skipped unless GJ_RUN_UNVERIFIED=1 so that an untested path cannot turn the suite red;
-the first GPU run is queued in tools/gpu_round2_single.sh."""
-import os
-
+    hash_join_clustered_probe.cu:1684-1984) vs the oracle's join checker."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("GJ_RUN_UNVERIFIED"),
-                                 reason="written without GPU access at the end of round 1; set GJ_RUN_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
@@ -76,81 +68,46 @@ def test_nonpartitioned_baseline_matches_oracle(gj, orc, torch_cuda, nR, nS, lo,
         assert (part.matches, part.checksum) == (want.matches, want.checksum)
 
 
-# ------------------------------------------------------------------------------- pcp2: probe split
-def _pcp2_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, slack=1.8):
-    """The probe-split pipeline (distributed.GpuOps.pcp2_join) with G virtual ranks on one GPU: per rank
-    one engine for build + first probe half and a second engine for the second probe half; the
-    collectives are torch.stack / synchronize."""
-    assert len(Rk) <= len(Sk)
-    n = [len(Rk), len(Sk)]
-    cut = [np.linspace(0, n[w], G + 1).astype(np.int64) for w in range(2)]
-    dest_max = [int(np.bincount((k.view(np.uint32) >> B) & (G - 1), minlength=G).max()) for k in (Rk, Sk)]
-    cap_b = int(dest_max[0] * slack) + 64
-    half_cap = (int(dest_max[1] * slack / 2) + 64) & ~1
-    shard = [[int(cut[w][r + 1] - cut[w][r]) for r in range(G)] for w in range(2)]
-    e1 = [gj.JoinEngine(max(cap_b, max(shard[0]) + 1024), max(half_cap, max(shard[1]) + 1024), 0) for _ in range(G)]
-    e2 = [gj.JoinEngine(16, max(half_cap, max(shard[1]) + 1024), 0) for _ in range(G)]
-    try:
-        own_b = [torch.zeros(cap_b + 16, dtype=torch.int64, device="cuda") for _ in range(G)]
-        own_p = [torch.zeros(2 * half_cap + 16, dtype=torch.int64, device="cuda") for _ in range(G)]
-        slots = []          # per rank: [(engine, which, keys, pays, cap, dest pointers, own pointer)] x 3
-        for r in range(G):
-            bk, bp = dev(torch, Rk[cut[0][r]:cut[0][r + 1]], Rp[cut[0][r]:cut[0][r + 1]])
-            pk, pp = dev(torch, Sk[cut[1][r]:cut[1][r + 1]], Sp[cut[1][r]:cut[1][r + 1]])
-            h = (pk.numel() // 2) & ~3
-            slots.append([(e1[r], 0, bk, bp, cap_b, [t.data_ptr() for t in own_b], own_b[r].data_ptr()),
-                          (e1[r], 1, pk[:h], pp[:h], half_cap, [t.data_ptr() for t in own_p], own_p[r].data_ptr()),
-                          (e2[r], 1, pk[h:], pp[h:], half_cap, [t.data_ptr() + half_cap * 8 for t in own_p],
-                           own_p[r].data_ptr() + half_cap * 8)])
-        torch.cuda.synchronize()
-        for r in range(G):
-            e1[r].pcp_begin(n[0], n[1], G, r, B)
-            e2[r].pcp_begin(1, n[1], G, r, B)
-        g, bl, b2 = e1[0].pcp_plan()
-        n1 = 1 << (g + bl)
-        hist = [[torch.empty(n1, dtype=torch.int32, device="cuda") for _ in range(G)] for _ in range(3)]
-        for r in range(G):
-            for i, (e, w, k, p, cap, dst, own) in enumerate(slots[r]):
-                e.pcp_hist(w, k, hist[i][r])
-        torch.cuda.synchronize()
-        allh = [torch.stack(hist[i]).contiguous() for i in range(3)]
-        for r in range(G):
-            for i, (e, w, k, p, cap, dst, own) in enumerate(slots[r]):
-                e.pcp_part(w, k, p, allh[i], cap)
-                e.pcp_copy(w, dst)
-        torch.cuda.synchronize()
-        m = c = 0
-        got = [0, 0]
-        for r in range(G):
-            for i, (e, w, k, p, cap, dst, own) in enumerate(slots[r]):
-                e.pcp_recv(w, own, cap)
-            torch.cuda.synchronize()
-            e1[r].pcp_join(cap_b, half_cap)
-            torch.cuda.synchronize()
-            e1[r].pcp_join_ext(e2[r], 1, cap_b, half_cap)
-            mm, cc, nb_, np1, ph, bits = e1[r].pcp_finish()
-            _, _, _, np2, _, _ = e2[r].pcp_finish(phases=False)
-            m += mm
-            c = (c + cc) % 2**64
-            got[0] += nb_
-            got[1] += np1 + np2
-        assert got == n
-        return m, c
-    finally:
-        for e in e1 + e2:
-            e.close()
-
-
-@pytest.mark.parametrize("G,B", [(2, 7), (4, 9), (8, 13), (8, 15)])
-def test_pcp2_probe_split_virtual_shards(gj, orc, torch_cuda, G, B):
-    rng = np.random.default_rng(50 * G + B)
-    nR, nS = 700_000, 1_900_000
-    Rk = rng.integers(-(1 << 20), 1 << 20, nR).astype(np.int32)
-    Sk = rng.integers(-(1 << 20), 1 << 20, nS).astype(np.int32)
-    Rp = rng.integers(-2**31, 2**31, nR).astype(np.int32)
-    Sp = rng.integers(-2**31, 2**31, nS).astype(np.int32)
+@pytest.mark.parametrize("nR,nS,key_min,spread", [(1 << 20, 1 << 20, 0, 1), (300_000, 2_000_000, -150_000, 1),
+                                                   (2_000_000, 300_000, 1 << 30, 3), (1, 1000, -5, 1), (0, 10, 0, 1)])
+def test_perfect_array_matches_oracle(gj, orc, torch_cuda, nR, nS, key_min, spread):
+    """Perfect array: unique build keys in [key_min, key_min + range) (dense or every `spread`-th value),
+    probe keys partly outside the range, every int32 payload incl. -1 (which the reference's payload+1
+    sentinel loses, join-primitives.cu:640); the build side is the smaller relation."""
+    rng = np.random.default_rng(nR + 11 * nS)
+    nb, npr = min(nR, nS), max(nR, nS)
+    rangev = max(nb * spread, 1)
+    bk = (key_min + spread * rng.permutation(nb).astype(np.int64)).astype(np.int32)
+    pk = rng.integers(key_min - rangev // 8, key_min + rangev + rangev // 8 + 1, npr).astype(np.int64)
+    pk = np.clip(pk, -2**31, 2**31 - 1).astype(np.int32)
+    bp = rng.integers(-2**31, 2**31, nb).astype(np.int32)
+    if nb:
+        bp[:: max(1, nb // 7)] = -1
+    pp = rng.integers(-2**31, 2**31, npr).astype(np.int32)
+    Rk, Rp, Sk, Sp = (bk, bp, pk, pp) if nR <= nS else (pk, pp, bk, bp)
     want = orc.join_check(Rk, Rp, Sk, Sp)
-    assert _pcp2_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp) == (want.matches, want.checksum)
+    with gj.JoinEngine(max(nR, 1), max(nS, 1), 0) as eng:
+        d = dev(torch_cuda, Rk, Rp, Sk, Sp)
+        got = eng.join_aggregate_perfect(*d, key_min, rangev)
+        assert (got.matches, got.checksum) == (want.matches, want.checksum)
+        assert got.timings.kernel_launches == (2 if nR and nS else 0)
+
+
+def test_perfect_array_rejects_violated_precondition(gj, torch_cuda):
+    """Duplicate or out-of-range build keys are detected on the device and reported, never silently joined."""
+    Rk = np.array([0, 1, 2, 2, 4], dtype=np.int32)          # duplicate key 2
+    Sk = np.arange(10, dtype=np.int32)
+    ones = lambda n: np.ones(n, dtype=np.int32)  # noqa: E731
+    with gj.JoinEngine(16, 16, 0) as eng:
+        d = dev(torch_cuda, Rk, ones(5), Sk, ones(10))
+        with pytest.raises(gj.GJError, match="duplicate"):
+            eng.join_aggregate_perfect(*d, 0, 8)
+        d = dev(torch_cuda, np.array([0, 1, 9], dtype=np.int32), ones(3), Sk, ones(10))
+        with pytest.raises(gj.GJError, match="outside"):
+            eng.join_aggregate_perfect(*d, 0, 8)             # key 9 outside [0, 8)
+        d = dev(torch_cuda, np.array([3, 1, 7], dtype=np.int32), ones(3), Sk, ones(10))
+        r = eng.join_aggregate_perfect(*d, 0, 8)              # the context stays usable
+        assert (r.matches, r.checksum) == (3, 3)
 
 
 # ------------------------------------------------------------------------------- out-of-HBM probe side
