@@ -10,13 +10,19 @@ reduction) over one synthetic workload.  Metric (BASELINE.json): join throughput
 4B-key/4B-payload tuples (the configuration north_star's single-GPU target is quoted on); N>1 =
 the same per-GPU shard sizes (weak scaling), radix-sharded with an all-to-all shuffle.
 
-  value         device-resident: inputs already in HBM when the timed region starts
+  value         device-resident: inputs already in HBM when the timed region starts; every step is
+                checked: match count and 64-bit payload checksum against the closed form of the
+                generated key sets (payload = mix(key), computed here with torch, independent of
+                the engine and of the oracle)
   e2e           through the public host entry (gj_join_aggregate_host): pinned HOST columns in,
                 H2D copies + result read-back inside the timed region
   roofline      the dominant kernel (radix scatter pass): algorithmic 16 B/tuple per launch over
                 its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  the oracle's multithreaded host radix join (a port: the reference has no CPU
                 join) on a bounded sample of the same workload
+  materialize   the materialising join (exact-size pair output) on the same inputs
+  config5       BASELINE config 5 (2e9 x 2e9 tuples in total, strong scaling): the per-GPU share
+                2e9/N, device-generated, 3 timed steps, with the speed-up over the 1-GPU run
   reference_cuda  the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref/bench_ref),
                 same inputs via .bin files, run on the same GPU in the same run
 
@@ -141,6 +147,46 @@ def make_host_keys(gj, w, out_R=None, out_S=None):
     return R, S, expect
 
 
+PAY_SEED_R, PAY_SEED_S = 40, 50      # payload = mix32(key ^ f(seed)), bit for bit gj_payload_of_key (csrc/kernels.cuh)
+_M32 = 0xFFFFFFFF
+
+
+def _mix32_t(x):
+    """mix32 of csrc/kernels.cuh on an int64 torch tensor holding uint32 values."""
+    x = x ^ (x >> 16)
+    x = (x * 0x7feb352d) & _M32
+    x = x ^ (x >> 15)
+    x = (x * 0x846ca68b) & _M32
+    return x ^ (x >> 16)
+
+
+def payload_i64(torch, keys, seed, lo=0, hi=None):
+    """payload_of_key(key, seed) of keys[lo:hi] as SIGNED values in an int64 tensor."""
+    k = keys[lo:hi].to(torch.int64) & _M32
+    c = (seed * 0xC2B2AE35 + 0x27D4EB2F) & _M32
+    v = _mix32_t(k ^ c)
+    return torch.where(v >= (1 << 31), v - (1 << 32), v)
+
+
+def fill_payloads(torch, keys, pays, seed, chunk=1 << 26):
+    for lo in range(0, keys.numel(), chunk):
+        pays[lo:lo + chunk] = payload_i64(torch, keys, seed, lo, lo + chunk).to(torch.int32)
+
+
+def closed_form(torch, probe_keys, n_build_keys, chunk=1 << 26):
+    """Expected (matches, checksum) when the build side holds every key of [0, n_build_keys) exactly
+    once, from the PROBE key column alone: a probe tuple matches iff 0 <= key < n_build_keys and then
+    contributes payload(key, 40) * payload(key, 50) (int64 arithmetic wraps = mod 2^64)."""
+    m, c = 0, 0
+    for lo in range(0, probe_keys.numel(), chunk):
+        k = probe_keys[lo:lo + chunk]
+        hit = (k >= 0) & (k.to(torch.int64) < n_build_keys)
+        prod = payload_i64(torch, k, PAY_SEED_R) * payload_i64(torch, k, PAY_SEED_S)
+        m += int(hit.sum().item())
+        c = (c + int(torch.where(hit, prod, torch.zeros_like(prod)).sum().item())) & 0xFFFFFFFFFFFFFFFF
+    return m, c
+
+
 def pinned_i32(torch, n):
     t = torch.empty(n, dtype=torch.int32).pin_memory()
     return t, t.numpy()
@@ -149,36 +195,6 @@ def pinned_i32(torch, n):
 # --------------------------------------------------------------------------------------------
 # arms
 # --------------------------------------------------------------------------------------------
-def cpu_port_throughput(w, budget_tuples=64_000_000, reps=2):
-    """The oracle's multithreaded host radix join on a bounded sample of workload `w`."""
-    from oracle import oracle
-    nR, nS, kind, z = WORKLOADS[w]
-    scale = min(1.0, budget_tuples / (nR + nS))
-    mR, mS = max(1024, int(nR * scale)), max(1024, int(nS * scale))
-    Rk = oracle.random_unique_gen(mR, mR, 4) if mR <= (1 << 22) else None
-    if Rk is None:   # large samples: any permutation will do for a timing sample
-        rng = np.random.default_rng(4)
-        Rk = rng.permutation(mR).astype(np.int32)
-    rng = np.random.default_rng(5)
-    if kind == "unique":
-        Sk = rng.permutation(mS).astype(np.int32) if mS == mR else rng.integers(0, mR, mS).astype(np.int32)
-    elif kind == "fk":
-        Sk = rng.integers(0, mR, mS).astype(np.int32)
-    else:
-        ranks = np.arange(1, mR + 1, dtype=np.float64) ** (-z)
-        cdf = np.cumsum(ranks / ranks.sum())
-        Sk = np.searchsorted(cdf, rng.random(mS)).clip(0, mR - 1).astype(np.int32)
-    ones_r, ones_s = np.ones(mR, np.int32), np.ones(mS, np.int32)
-    best = None
-    for _ in range(reps):
-        res, secs = oracle.join_check(Rk, ones_r, Sk, ones_s, 0, with_time=True)
-        best = secs if best is None else min(best, secs)
-    return {"value": (mR + mS) / best, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
-            "sample": f"|R|={mR}, |S|={mS} sample of the same key distribution, best of {reps}, "
-                      f"{best * 1e3:.1f} ms (oracle/oracle_join.c orc_join_check, OpenMP)",
-            "seconds": best}
-
-
 def run_reference_cuda(gj, w, steps, timeout_s=420):
     """The reference's CUDA kernels rebuilt for sm_100a, run on identical inputs via .bin files."""
     exe = os.path.join(ROOT, "oracle", "_ref", "bench_ref")
@@ -215,42 +231,196 @@ def run_reference_cuda(gj, w, steps, timeout_s=420):
                     "'Without materialization' block, data resident, wall-clock around cudaDeviceSynchronize"}
 
 
+def config_of(w, n_gpus):
+    """The `config` object of a line: a function of (workload, N) only, so that the GPU arm and the
+    reference arm of one driver run print the same one."""
+    nR, nS, kind, z = WORKLOADS[w]
+    strong = (w == "cfg5")
+    per_R, per_S = (nR // n_gpus, nS // n_gpus) if strong else (nR, nS)
+    return {"workload": workload_name(w), "per_gpu_R": per_R, "per_gpu_S": per_S,
+            "global_R": per_R * n_gpus, "global_S": per_S * n_gpus,
+            "parallelism": "1 GPU" if n_gpus == 1 else f"radix-sharded over {n_gpus} GPUs (top radix bits = GPU id), "
+                           + ("strong scaling" if strong else "weak scaling: the same shard sizes on every GPU"),
+            "l2": ("inputs (>= 2 GB per step) far exceed the 126 MB L2; no flush needed" if 8 * (per_R + per_S) > (1 << 29) else
+                   "inputs fit the 126 MB L2 (a latency-bound case by design, not the headline); no flush")}
+
+
 def base_line(args, w, n_gpus):
     return {"metric": METRIC, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic (seeded ETHZ-style generator)",
-            "config": {"workload": workload_name(w), "per_gpu_R": WORKLOADS[w][0], "per_gpu_S": WORKLOADS[w][1],
-                       "l2": "inputs (>= 2 GB per step) far exceed the 126 MB L2; no flush needed"}}
+            "higher_is_better": True, "scaling": "strong" if w == "cfg5" else "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic (seeded ETHZ-style generator; payload = mix32(key))",
+            "config": config_of(w, n_gpus)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+CPU_SAMPLE_MAX = 128_000_000     # tuples per side the CPU arm joins per step (workload B in full)
+
+
+def cpu_join_sample(w, n_gpus=1):
+    """Inputs of the CPU arm: the stated workload in full where one side has at most 128 M tuples
+    (workload B: all of it), else a sample with the same |R|:|S| ratio and key distribution."""
+    cfg = config_of(w, n_gpus)
+    nR, nS = cfg["global_R"], cfg["global_S"]
+    kind, z = WORKLOADS[w][2], WORKLOADS[w][3]
+    scale = min(1.0, CPU_SAMPLE_MAX / max(nR, nS))
+    mR, mS = max(1024, int(nR * scale)), max(1024, int(nS * scale))
+    rng = np.random.default_rng(4)
+    Rk = rng.permutation(mR).astype(np.int32)
+    rng = np.random.default_rng(5)
+    if kind == "unique":
+        Sk = rng.permutation(mS).astype(np.int32) if mS == mR else rng.integers(0, mR, mS).astype(np.int32)
+    elif kind == "fk":
+        Sk = rng.integers(0, mR, mS).astype(np.int32)
+    else:
+        ranks = np.arange(1, mR + 1, dtype=np.float64) ** (-z)
+        cdf = np.cumsum(ranks / ranks.sum())
+        Sk = np.searchsorted(cdf, rng.random(mS)).clip(0, mR - 1).astype(np.int32)
+    what = ("the whole workload" if scale == 1.0 else f"a {scale:.4f} sample (same |R|:|S| and key distribution)")
+    return Rk, Sk, f"|R|={mR}, |S|={mS}: {what}"
+
+
+def cpu_port_throughput(w, n_gpus=1, reps=2, inputs=None):
+    """The oracle's multithreaded host radix join (oracle/oracle_join.c orc_join_check: two radix passes
+    through software write-combining buffers + per-partition chained hash join) on ALL host threads --
+    the count is passed explicitly, torch.distributed.run exports OMP_NUM_THREADS=1."""
+    from oracle import oracle
+    Rk, Sk, what = inputs if inputs is not None else cpu_join_sample(w, n_gpus)
+    threads = host_threads()
+    Rp, Sp = oracle.payload_of_keys(Rk, PAY_SEED_R), oracle.payload_of_keys(Sk, PAY_SEED_S)
+    times = []
+    for _ in range(reps):
+        res, secs = oracle.join_check(Rk, Rp, Sk, Sp, threads, with_time=True)
+        times.append(secs)
+    best = min(times)
+    return {"value": (Rk.size + Sk.size) / best, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{what}; best of {reps}: {best * 1e3:.1f} ms (oracle/oracle_join.c orc_join_check, OpenMP, "
+                      f"{threads} threads, SWWC radix passes)",
+            "matches": int(res.matches), "checksum": int(res.checksum), "seconds": times}
 
 
 def reference_arm(args):
-    """--impl reference: the CPU port on all host threads (rank 0 only under torchrun)."""
+    """--impl reference: the CPU port on all host threads (rank 0 only under torchrun).  One step = one
+    whole join of cpu_join_sample() -- for workload B the full 128 M x 128 M."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     w = args.workload
-    # each step: one bounded sample join
+    n_gpus = max(args.gpus, int(os.environ.get("WORLD_SIZE", "1")))
     from oracle import oracle
     oracle.lib()
-    vals = []
-    cb = None
+    inputs = cpu_join_sample(w, n_gpus)
+    Rk, Sk, what = inputs
+    threads = host_threads()
+    Rp, Sp = oracle.payload_of_keys(Rk, PAY_SEED_R), oracle.payload_of_keys(Sk, PAY_SEED_S)
+    secs, t_begin = [], time.perf_counter()
     for i in range(args.warmup + args.steps):
-        cb = cpu_port_throughput(w, budget_tuples=32_000_000, reps=1)
+        res, s_ = oracle.join_check(Rk, Rp, Sk, Sp, threads, with_time=True)
         if i >= args.warmup:
-            vals.append(cb["value"])
-        if i >= 2 and cb["seconds"] * (args.warmup + args.steps) > 240:   # keep the run within minutes
+            secs.append(s_)
+        if len(secs) >= 3 and time.perf_counter() - t_begin > 200:      # keep the run within minutes
             break
-    v = statistics.median(vals) if vals else cb["value"]
-    line = base_line(args, w, args.gpus)
-    cb = dict(cb, value=v)
-    cb.pop("seconds", None)
-    sample_tuples = sum(int(x) for x in re.findall(r"\|[RS]\|=(\d+)", cb["sample"]))
-    line.update({"impl": "reference", "value": v, "ms_per_step": sample_tuples / v * 1e3, "cpu_baseline": cb,
+    per_step = statistics.median(secs)
+    v = (Rk.size + Sk.size) / per_step
+    line = base_line(args, w, n_gpus)
+    cb = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+          "sample": f"{what}; median of {len(secs)} timed joins: {per_step * 1e3:.1f} ms "
+                    f"(oracle/oracle_join.c orc_join_check, OpenMP, {threads} threads, SWWC radix passes)"}
+    line.update({"impl": "reference", "value": v, "steps": len(secs), "ms_per_step": per_step * 1e3, "cpu_baseline": cb,
                  "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                 "gpu_launches": 0,
+                 "gpu_launches": 0, "checked": f"matches={int(res.matches)} checksum={int(res.checksum)}",
                  "note": "the reference has no CPU join (its joinCpu is dead code, hash_join_clustered_probe.cu:2013-2059); "
                          "this arm is the oracle's host radix join (structure of partition-primitives.cu:40-125). "
                          "The reference's CUDA kernels are timed by --impl reference-cuda / key reference_cuda."})
     print(json.dumps(line))
+
+
+CFG5_CACHE = os.path.join(tempfile.gettempdir(), "gj_cfg5_1gpu.json")
+CFG5_1GPU_MEASURED = {"value": 75.8e9, "ms_per_step": 52.8,
+                      "source": "profiles/r1_final/bench_1gpu_cfg5.log (round 1, same kernels)"}
+
+
+def run_cfg5_share(torch, gj, n_gpus, rank, dev_index, sharded=None, steps=3, warm=1, opts=()):
+    """BASELINE config 5: |R|=|S|=2e9 in total, this GPU generates and joins rows [rank, rank+1) * 2e9/N.
+    Returns (ms per step on this rank, matches, checksum of the last step, expected matches, expected checksum)."""
+    n_tot = WORKLOADS["cfg5"][0]
+    n = n_tot // n_gpus
+    dev = torch.device("cuda", dev_index)
+    if sharded is None:
+        eng = gj.JoinEngine(n, n, dev_index)
+    else:
+        eng = sharded.ops.engine
+    for kv in opts:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
+    cols = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(4)]
+    eng.generate_unique(cols[0], cols[1], rank * n, n_tot, 4, PAY_SEED_R)
+    eng.generate_unique(cols[2], cols[3], rank * n, n_tot, 5, PAY_SEED_S)
+    torch.cuda.synchronize()
+    # expected: every key of [0, n_tot) once on each side -> this rank's PROBE shard contributes its own keys
+    want = closed_form(torch, cols[2], n_tot)
+
+    def step():
+        if sharded is None:
+            r = eng.join_aggregate(*cols)
+            return r.matches, r.checksum, r.timings.as_dict()
+        r = sharded.join_aggregate(*cols, n * n_gpus, n * n_gpus)
+        return r.matches, r.checksum, r.phases_ms
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if sharded is not None:
+        import torch.distributed as dist
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        m, c, tm = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if sharded is None:
+        eng.close()
+    del cols
+    torch.cuda.empty_cache()
+    return ms, m, c, want, tm
+
+
+def cfg5_record(ms_step, n_gpus, shuffle=None, tm=None):
+    n_tot = WORKLOADS["cfg5"][0]
+    rec = {"workload": workload_name("cfg5"), "scaling": "strong", "n_gpus": n_gpus, "per_gpu_R": n_tot // n_gpus,
+           "per_gpu_S": n_tot // n_gpus, "steps": 3, "warmup": 1, "ms_per_step": ms_step,
+           "value": 2 * n_tot / (ms_step * 1e-3), "unit": UNIT}
+    if shuffle:
+        rec["shuffle"] = shuffle
+    if n_gpus == 1:
+        try:
+            with open(CFG5_CACHE, "w") as f:
+                json.dump({"value": rec["value"], "ms_per_step": ms_step, "when": time.time()}, f)
+        except OSError:
+            pass
+        rec["speedup_vs_1gpu"] = 1.0
+    else:
+        base, src = None, None
+        try:
+            with open(CFG5_CACHE) as f:
+                d = json.load(f)
+            if time.time() - d["when"] < 6 * 3600:
+                base, src = d["value"], f"1-GPU run of this bench on this box ({CFG5_CACHE})"
+        except Exception:
+            pass
+        if base is None:
+            base, src = CFG5_1GPU_MEASURED["value"], CFG5_1GPU_MEASURED["source"]
+        rec["speedup_vs_1gpu"] = rec["value"] / base
+        rec["one_gpu_value"] = base
+        rec["one_gpu_source"] = src
+    if tm:
+        rec["phases_ms_rank0"] = {k: v for k, v in tm.items() if isinstance(v, (int, float))}
+    return rec
 
 
 def single_gpu(args):
@@ -263,9 +433,7 @@ def single_gpu(args):
     nR, nS, kind, z = WORKLOADS[w]
     torch.cuda.set_device(0)
     pins = [pinned_i32(torch, n) for n in (nR, nR, nS, nS)]
-    R, S, expect = make_host_keys(gj, w, pins[0][1], pins[2][1])
-    pins[1][1][:] = 1
-    pins[3][1][:] = 1          # payload columns of ones, as the reference (hash_join_clustered_probe.cu:1994-1999)
+    R, S, expect_m = make_host_keys(gj, w, pins[0][1], pins[2][1])
     hRk, hRp, hSk, hSp = (p[0] for p in pins)
 
     eng = gj.JoinEngine(nR, nS, 0)
@@ -274,12 +442,21 @@ def single_gpu(args):
         eng.set_option(k, int(v))
     stream = torch.cuda.Stream()
     eng.use_torch_stream(stream)
-    dRk, dRp, dSk, dSp = (t.cuda() for t in (hRk, hRp, hSk, hSp))
+    dRk, dSk = hRk.cuda(), hSk.cuda()
+    dRp, dSp = torch.empty_like(dRk), torch.empty_like(dSk)
+    # real payloads (a function of the key), so that the checksum checks the key/payload pairing of
+    # every tuple through both radix passes and the join
+    fill_payloads(torch, dRk, dRp, PAY_SEED_R)
+    fill_payloads(torch, dSk, dSp, PAY_SEED_S)
+    hRp.copy_(dRp); hSp.copy_(dSp)
+    want_m, want_c = closed_form(torch, dSk, nR)
+    if want_m != expect_m:
+        raise SystemExit(f"closed form disagrees with the generator's definition: {want_m} != {expect_m}")
     torch.cuda.synchronize()
 
     def check(res):
-        if res.matches != expect or res.checksum != expect:
-            raise SystemExit(f"WRONG RESULT: matches={res.matches} checksum={res.checksum}, expected {expect}")
+        if res.matches != want_m or res.checksum != want_c:
+            raise SystemExit(f"WRONG RESULT: matches={res.matches} checksum={res.checksum}, expected {want_m} / {want_c}")
 
     # ---- device-resident throughput ----
     for _ in range(args.warmup):
@@ -293,11 +470,11 @@ def single_gpu(args):
     e0.record(stream)
     for _ in range(args.steps):
         res = eng.join_aggregate(dRk, dRp, dSk, dSp)
+        check(res)
         tms.append(res.timings.as_dict())
     e1.record(stream)
     torch.cuda.synchronize()
     launches = gj.kernel_launch_count() - launches0
-    check(res)
     ms_step = e0.elapsed_time(e1) / args.steps
     value = (nR + nS) / (ms_step * 1e-3)
 
@@ -309,23 +486,30 @@ def single_gpu(args):
         for i, ms in enumerate(t["pass_ms"]):
             if ms > 0:
                 per_launch.append((16.0 * n_of[i], ms))
-    alg_bytes = statistics.mean(b for b, _ in per_launch)
-    avg_ms = statistics.mean(ms for _, ms in per_launch)
-    achieved = sum(b for b, _ in per_launch) / sum(ms for _, ms in per_launch) / 1e6   # GB/s
     med = lambda k: statistics.median(t[k] for t in tms)  # noqa: E731
-    traffic = None
-    tf = os.path.join(ROOT, "profiles", "scatter_dram_bytes.json")
-    if os.path.exists(tf):
-        try:
-            traffic = json.load(open(tf)).get("bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "scatter_kernel (radix scatter pass; %d launches per step)" % sum(1 for x in tms[0]["pass_ms"] if x > 0),
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
+    roofline = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
                 "per_phase_ms": {"hist_scan_plan": med("hist_ms"), "scatter_passes": med("part_ms"), "join": med("join_ms"),
-                                 "total": med("total_ms")},
-                "pipeline_frac": (44.0 if tms[0]["pass2_bits"] else 28.0) * (nR + nS) / (med("total_ms") * 1e-3) / 1e9 / peak}
+                                 "total": med("total_ms")}}
+    if per_launch:
+        achieved = sum(b for b, _ in per_launch) / sum(ms for _, ms in per_launch) / 1e6   # GB/s
+        traffic, traffic_src = None, None
+        tf = os.path.join(ROOT, "profiles", "scatter_dram_bytes.json")
+        if os.path.exists(tf) and w == "B":
+            try:
+                td = json.load(open(tf))
+                traffic, traffic_src = td.get("bytes_per_launch"), f"profiles/scatter_dram_bytes.json ({td.get('source', 'ncu --set full')})"
+            except Exception:
+                pass
+        roofline.update({"kernel": "scatter_kernel (radix scatter pass; %d launches per step)" % sum(1 for x in tms[0]["pass_ms"] if x > 0),
+                         "achieved": achieved, "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": statistics.mean(b for b, _ in per_launch),
+                         "avg_launch_ms": statistics.mean(ms for _, ms in per_launch),
+                         "pipeline_frac": (44.0 if tms[0]["pass2_bits"] else 28.0) * (nR + nS) / (med("total_ms") * 1e-3) / 1e9 / peak})
+    else:   # non-partitioned path (small inputs): build + probe kernels, random access into an L2-resident table
+        roofline.update({"kernel": "np_build_kernel + np_probe_kernel (non-partitioned path, L2-resident table)",
+                         "achieved": 8.0 * (nR + nS) / (med("total_ms") * 1e-3) / 1e9, "traffic": None,
+                         "algorithmic_bytes_per_launch": 8.0 * (nR + nS)})
+        roofline["frac"] = roofline["achieved"] / peak
 
     # ---- end to end: pinned host columns in, result out ----
     for _ in range(max(1, min(args.warmup, 2))):
@@ -335,15 +519,44 @@ def single_gpu(args):
     e2e_t = []
     for _ in range(args.steps):
         r2 = eng.join_aggregate_host(hRk, hRp, hSk, hSp)
+        check(r2)
         e2e_t.append(r2.timings.as_dict())
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop()      # sampled across both timed regions (device-resident and end-to-end)
-    check(r2)
     e2e = {"value": (nR + nS) / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": 8 * (nR + nS), "d2h_bytes_per_step": 32,
            "h2d_ms": statistics.median(t["h2d_ms"] for t in e2e_t),
            "api": "gj_join_aggregate_host (JoinEngine.join_aggregate_host), pinned host columns"}
+
+    # ---- the materialising join on the same inputs: exact-size pair output ----
+    mat = None
+    if not args.no_materialize:
+        out_r = torch.empty(want_m, dtype=torch.int32, device="cuda")
+        out_s = torch.empty(want_m, dtype=torch.int32, device="cuda")
+        msteps = max(3, min(args.steps, 5))
+        mts = []
+        for i in range(1 + msteps):
+            npairs, mr = eng.join_materialize(dRk, dRp, dSk, dSp, out_r, out_s)
+            if npairs != want_m or mr.checksum != want_c:
+                raise SystemExit(f"WRONG RESULT (materialize): pairs={npairs} checksum={mr.checksum}, expected {want_m} / {want_c}")
+            if i:
+                mts.append(mr.timings.as_dict())
+        # the written pairs reproduce the checksum: sum over output rows of Pr * Ps
+        got_c = 0
+        for lo in range(0, want_m, 1 << 26):
+            got_c = (got_c + int((out_r[lo:lo + (1 << 26)].to(torch.int64) * out_s[lo:lo + (1 << 26)].to(torch.int64)).sum().item())) & 0xFFFFFFFFFFFFFFFF
+        if got_c != want_c:
+            raise SystemExit(f"WRONG RESULT (materialize): checksum of the written pairs {got_c} != {want_c}")
+        tot = statistics.median(t["total_ms"] for t in mts)
+        jm = statistics.median(t["join_ms"] for t in mts)
+        mat = {"value": (nR + nS) / (tot * 1e-3), "unit": UNIT, "ms_per_step": tot, "pairs": want_m, "join_ms": jm,
+               "join_kernel": {"algorithmic_bytes": 8.0 * (nR + nS) + 8.0 * want_m, "achieved_GBs": (8.0 * (nR + nS) + 8.0 * want_m) / (jm * 1e-3) / 1e9,
+                               "frac": (8.0 * (nR + nS) + 8.0 * want_m) / (jm * 1e-3) / 1e9 / peak},
+               "api": "gj_join_materialize, device-resident, CUDA events inside the call; pairs staged per CTA (warp-aggregated "
+                      "reservation), one global reservation per flush; checked: exact pair count, checksum, and the checksum "
+                      "recomputed from the written (Pr, Ps) columns"}
+        del out_r, out_s
     eng.close()
     del dRk, dRp, dSk, dSp
     torch.cuda.empty_cache()
@@ -352,66 +565,54 @@ def single_gpu(args):
     line.update({"value": value, "ms_per_step": ms_step, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                  "roofline": roofline,
                  "plan": {"radix_bits": tms[0]["radix_bits"], "pass1_bits": tms[0]["pass1_bits"], "pass2_bits": tms[0]["pass2_bits"]},
-                 "checked": f"matches == checksum == {expect} every step"})
-    line["config"]["parallelism"] = "1 GPU"
+                 "checked": f"every step: matches == {want_m} and checksum == {want_c} (closed form over the generated keys, payload = mix32(key))"})
+    if mat:
+        line["materialize"] = mat
     if not args.no_cpu_baseline:
         cb = cpu_port_throughput(w)
         cb.pop("seconds", None)
+        if cb["sample"].find("the whole workload") >= 0 and kind == "unique":
+            # the CPU port joined the same key sets (any permutation of [0, n)): its aggregate must equal ours
+            cb["agrees_with_gpu"] = (cb["matches"], cb["checksum"]) == (want_m, want_c)
         line["cpu_baseline"] = cb
     if not args.no_ref_cuda:
         line["reference_cuda"] = run_reference_cuda(gj, w, 1)
+    if w == "B" and not args.no_cfg5:
+        ms5, m5, c5, want5, tm5 = run_cfg5_share(torch, gj, 1, 0, 0, opts=args.opt)
+        if (m5, c5) != want5:
+            raise SystemExit(f"WRONG RESULT (config 5): {m5} {c5}, expected {want5}")
+        line["config5"] = cfg5_record(ms5, 1, tm=tm5)
+        line["config5"]["checked"] = f"matches == {want5[0]} and checksum == {want5[1]}"
     print(json.dumps(line))
 
 
 def cfg5_single(args):
-    """BASELINE config 5 on ONE GPU (the strong-scaling denominator): 2e9 x 2e9 device-generated
-    tuples.  Build partitions are 30.5 K tuples at the 16-bit radix cap, so the join runs its
-    multi-chunk steps (8 build chunks x 8 probe chunks per partition) -- reported as measured."""
+    """--workload cfg5 on ONE GPU: the strong-scaling denominator as a line of its own."""
     import torch
     import __graft_entry__ as ge
     gj = ge.load_package()
-    w = args.workload
-    n = WORKLOADS[w][0]
     torch.cuda.set_device(0)
-    eng = gj.JoinEngine(n, n, 0)
-    for kv in args.opt:
-        k, v = kv.split("=")
-        eng.set_option(k, int(v))
-    stream = torch.cuda.Stream()
-    eng.use_torch_stream(stream)
-    cols = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(4)]
-    eng.generate_unique(cols[0], cols[1], 0, n, 4, 40)
-    eng.generate_unique(cols[2], cols[3], 0, n, 5, 50)
-    cols[1].fill_(1); cols[3].fill_(1)
-    torch.cuda.synchronize()
-    steps, warm = min(args.steps, 3), 1
-    for _ in range(warm):
-        res = eng.join_aggregate(*cols)
     launches0 = gj.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    tms = []
-    for _ in range(steps):
-        res = eng.join_aggregate(*cols)
-        tms.append(res.timings.as_dict())
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if res.matches != n or res.checksum != n:
-        raise SystemExit(f"WRONG RESULT: {res.matches} {res.checksum}, expected {n}")
-    ms_step = e0.elapsed_time(e1) / steps
+    ms5, m5, c5, want5, t = run_cfg5_share(torch, gj, 1, 0, 0, steps=min(args.steps, 3), opts=args.opt)
+    if (m5, c5) != want5:
+        raise SystemExit(f"WRONG RESULT: {m5} {c5}, expected {want5}")
+    n = WORKLOADS["cfg5"][0]
     peak, peak_src = measured_peak()
-    t = tms[-1]
-    line = base_line(args, w, 1)
-    line.update({"scaling": "strong", "steps": steps, "warmup": warm, "value": 2 * n / (ms_step * 1e-3), "ms_per_step": ms_step,
+    passes = 3 if t.get("pass3_bits") else (2 if t.get("pass2_bits") else 1)
+    # three-pass plan: every pass 16 B/tuple + the third level's sub-histogram (8 B/tuple)
+    alg = (16.0 * passes + (8.0 if passes == 3 else 0.0)) * 2 * n
+    line = base_line(args, "cfg5", 1)
+    line.update({"steps": min(args.steps, 3), "warmup": 1, "value": 2 * n / (ms5 * 1e-3), "ms_per_step": ms5,
                  "e2e": None, "gpu_launches": int(gj.kernel_launch_count() - launches0),
-                 "roofline": {"bound": "hbm", "kernel": "scatter_kernel", "achieved": 16.0 * 2 * n * 2 / (t["part_ms"] * 1e-3) / 1e9,
-                              "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                 "roofline": {"bound": "hbm", "kernel": f"scatter passes ({passes} per relation" + (" + sub-histogram of the third level)" if passes == 3 else ")"),
+                              "achieved": alg / (t["part_ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                              "traffic": None, "algorithmic_bytes_per_step": alg,
                               "per_phase_ms": {k: t[k] for k in ("hist_ms", "part_ms", "join_ms", "total_ms")}},
-                 "plan": {"radix_bits": t["radix_bits"], "pass1_bits": t["pass1_bits"], "pass2_bits": t["pass2_bits"]},
-                 "checked": f"matches == checksum == {n}"})
+                 "plan": {"radix_bits": t["radix_bits"], "pass1_bits": t["pass1_bits"], "pass2_bits": t["pass2_bits"], "pass3_bits": t.get("pass3_bits")},
+                 "checked": f"matches == {want5[0]} and checksum == {want5[1]}"})
     line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
+    line["config5"] = cfg5_record(ms5, 1)
     print(json.dumps(line))
-    eng.close()
 
 
 def multi_gpu(args):
@@ -428,34 +629,43 @@ def multi_gpu(args):
     if kind != "unique":
         raise SystemExit("multi-GPU bench supports the unique-key workloads (B, small, cfg5)")
     if args.shuffle == "auto":
-        # measured (profiles/README.md, G tuples/s, weak scaling): 2 GPUs pcp 128.8 / pp 124.8 / p2p 111.6;
-        # 8 GPUs pcp 406.8 / p2p 352.8 / pp 315.0.  Config 5 has only been measured with p2p and pp at 8 GPUs.
-        args.shuffle = "p2p" if (w == "cfg5" and world >= 8) else "pcp"
+        args.shuffle = "pcp"        # measured best at 2, 4 and 8 GPUs (profiles/README.md)
     strong = (w == "cfg5")
     if strong:                      # fixed total, per-GPU share shrinks with N
         nR, nS = nR // world, nS // world
     NR, NS = nR * world, nS * world
-    sj = gj.distributed.ShardedJoin(nR, nS, device=local, mode=args.shuffle, overlap=not args.no_overlap)
+    if NR != NS:
+        raise SystemExit("unique workloads need |R| == |S|")
+    stages = tuple(int(x) for x in args.pcp_stages.split(","))
+    # engine capacity: the larger of this workload's and config 5's shard (one context serves both)
+    n5 = WORKLOADS["cfg5"][0] // world
+    with_cfg5 = (w == "B" and not args.no_cfg5)
+    capn = max(nR, n5) if with_cfg5 else nR
+    sj = gj.distributed.ShardedJoin(capn, capn, device=local, mode=args.shuffle, overlap=not args.no_overlap, pcp_stages=stages)
     for kv in args.opt:
         k, v = kv.split("=")
         sj.ops.engine.set_option(k, int(v))
     eng = sj.ops.engine
     dev = torch.device("cuda", local)
     cols = [torch.empty(n, dtype=torch.int32, device=dev) for n in (nR, nR, nS, nS)]
-    eng.generate_unique(cols[0], cols[1], rank * nR, NR, 4, 40)
-    eng.generate_unique(cols[2], cols[3], rank * nS, NS, 5, 50)
-    if NR != NS:
-        raise SystemExit("unique workloads need |R| == |S|")
-    cols[1].fill_(1); cols[3].fill_(1)
-    expect = NS
+    eng.generate_unique(cols[0], cols[1], rank * nR, NR, 4, PAY_SEED_R)      # payload = mix32(key): the checksum
+    eng.generate_unique(cols[2], cols[3], rank * nS, NS, 5, PAY_SEED_S)      # checks the pairing of every tuple
+    # closed form from the keys THIS rank generated: every key of [0, NR) exists once in R, so each of
+    # this rank's probe keys matches and contributes payload(key, 40) * payload(key, 50)
+    mine = closed_form(torch, cols[2], NR)
+    tot = torch.tensor([mine[0], mine[1] - (1 << 64) if mine[1] >= (1 << 63) else mine[1]], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    want_m, want_c = int(tot[0].item()), int(tot[1].item()) & 0xFFFFFFFFFFFFFFFF
+    if want_m != NS:
+        raise SystemExit(f"generator: {want_m} matching probe keys, expected {NS}")
     do_e2e = nR + nS <= 600_000_000
     host = [c.cpu().pin_memory() for c in cols] if do_e2e else None
     torch.cuda.synchronize()
 
     def step():
         r = sj.join_aggregate(*cols, NR, NS)
-        if r.matches != expect or r.checksum != expect:
-            raise SystemExit(f"rank {rank}: WRONG RESULT {r.matches} {r.checksum}, expected {expect}")
+        if r.matches != want_m or r.checksum != want_c:
+            raise SystemExit(f"rank {rank}: WRONG RESULT {r.matches} {r.checksum}, expected {want_m} {want_c}")
         return r
 
     for _ in range(args.warmup):
@@ -467,8 +677,10 @@ def multi_gpu(args):
     launches0 = gj.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    phases = []
     for _ in range(args.steps):
         r = step()
+        phases.append(r.phases_ms)
     e1.record()
     torch.cuda.synchronize(); dist.barrier()
     launches = gj.kernel_launch_count() - launches0
@@ -493,67 +705,70 @@ def multi_gpu(args):
         torch.cuda.synchronize(); dist.barrier()
         e2 = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device=dev)
         dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+    local_rs = (r.local_R, r.local_S)
+    del cols, host
+    torch.cuda.empty_cache()
+
+    cfg5 = None
+    if with_cfg5:
+        ms5, m5, c5, want5, tm5 = run_cfg5_share(torch, gj, world, rank, local, sharded=sj)
+        t5 = torch.tensor([ms5], device=dev)
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        w5 = torch.tensor([want5[0], want5[1] - (1 << 64) if want5[1] >= (1 << 63) else want5[1]], dtype=torch.int64, device=dev)
+        dist.all_reduce(w5)
+        exp5 = (int(w5[0].item()), int(w5[1].item()) & 0xFFFFFFFFFFFFFFFF)
+        if (m5, c5) != exp5:
+            raise SystemExit(f"rank {rank}: WRONG RESULT (config 5) {m5} {c5}, expected {exp5}")
+        cfg5 = cfg5_record(float(t5.item()), world, shuffle=args.shuffle, tm=tm5)
+        cfg5["checked"] = f"matches == {exp5[0]} and checksum == {exp5[1]} (closed form, all-reduced)"
+
     if rank == 0:
         peak, peak_src = measured_peak()
         line = base_line(args, w, world)
-        if strong:
-            line["scaling"] = "strong"
-            line["config"].update({"per_gpu_R": nR, "per_gpu_S": nS})
+        med = lambda k: statistics.median(p[k] for p in phases if isinstance(p.get(k), (int, float)))  # noqa: E731
         tm = r.phases_ms
+        sent = int((nR + nS) * (world - 1) / world)
         line.update({"value": (NR + NS) / (ms_step * 1e-3), "ms_per_step": ms_step,
                      "e2e": None if not do_e2e else {"value": (NR + NS) / (float(e2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(e2.item()),
                              "h2d_bytes_per_step": 8 * (NR + NS), "d2h_bytes_per_step": 32 * world,
                              "api": "ShardedJoin.join_aggregate after per-rank H2D of pinned host shards"},
                      "gpu_launches": int(launches) * world, "clocks": clocks,
-                     "roofline": {"bound": "hbm", "kernel": "scatter_kernel (local radix passes, rank 0)",
-                                  "achieved": 16.0 * (r.local_R + r.local_S) * (2 if tm.get("pass2_bits") else 1) / (tm["part_ms"] * 1e-3) / 1e9 if tm.get("part_ms") else None,
-                                  "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
-                                  "local_phases_ms": {k: tm.get(k) for k in ("hist_ms", "part_ms", "join_ms", "total_ms")}},
-                     "shuffle": {"mode": args.shuffle, "tuples_per_gpu_out": int((nR + nS) * (world - 1) / world),
-                                 "scatter_kernel_ms": tm.get("shuffle_scatter_ms"),
-                                 "nvlink_out_GBs_per_gpu": (8.0 * (nR + nS) * (world - 1) / world / (tm["shuffle_scatter_ms"] * 1e-3) / 1e9)
-                                 if tm.get("shuffle_scatter_ms") else None,
-                                 "nvlink_peak_GBs": 770.0, "host_ms_rank0": tm.get("host_ms"), "trace_ms_rank0": tm.get("trace_ms"),
-                                 "note": "peer-store scatter: one kernel reads the local shard (8 B/tuple HBM) and stores each run into the destination GPU's HBM over NVLink"},
-                     "checked": f"matches == checksum == {expect} every step"})
-        if tm.get("pass_ms") and any(tm["pass_ms"][2:]):
-            # the receiver's radix passes over S run alone (R's overlap S's shuffle): 16 B/tuple per launch
+                     "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None},
+                     "shuffle": {"mode": args.shuffle, "tuples_per_gpu_out": sent, "nvlink_peak_GBs": 770.0,
+                                 "host_ms_rank0": tm.get("host_ms"), "trace_ms_rank0": tm.get("trace_ms")},
+                     "checked": f"every step: matches == {want_m} and checksum == {want_c} (closed form over the generated keys, payload = mix32(key), all-reduced)"})
+        if args.shuffle == "pcp" and tm.get("part_R_ms"):
+            ph = {k: med(k) for k in ("part_R_ms", "copy_R_ms", "recv_R_ms", "part_S_ms", "copy_S_ms", "recv_S_ms", "tail_ms")}
+            copy_ms = ph["copy_R_ms"] + ph["copy_S_ms"]
+            # dominant HBM kernel that runs ALONE: the source pass of the first relation (layout + first pass, 16 B/tuple)
+            line["roofline"].update({"kernel": "pcp source-side radix pass of R (layout + first pass, 16 B/tuple), rank 0",
+                                     "achieved": 16.0 * nR / (ph["part_R_ms"] * 1e-3) / 1e9, "algorithmic_bytes_per_launch": 16.0 * nR,
+                                     "local_phases_ms": ph})
+            line["plan"] = {"gpu_bits": world.bit_length() - 1, "local_bits": tm.get("radix_bits"), "source_pass_bits": tm.get("pass1_bits"),
+                            "receiver_pass_bits": tm.get("pass2_bits"), "stages_build_probe": list(stages)}
+            line["shuffle"].update({"copy_kernels_ms": copy_ms, "nvlink_out_GBs_per_gpu": 8.0 * sent / (copy_ms * 1e-3) / 1e9,
+                                    "nvlink_busy_frac_of_step": copy_ms / ms_step,
+                                    "hbm_bytes_per_tuple": 4 + 16 + 16.0 * (world - 1) / world + 8 + 16 + 8,
+                                    "note": "partition-copy-partition, streamed: first radix pass at the source on [gpu | top local bits] (own chunks "
+                                            "straight into the receive buffer), whole first-pass partitions bulk-copied in stages (TMA, global->shared->"
+                                            "peer global) with a flag store into every peer after each stage; the receiver partitions and joins a stage "
+                                            "while later ones are in flight; tail_ms = last probe byte landed -> last join done"})
+            line["shuffle"]["nvlink_frac_of_peer_copy_peak"] = line["shuffle"]["nvlink_out_GBs_per_gpu"] / 770.0
+        elif args.shuffle == "pp" and tm.get("local_R_ms"):
+            line["roofline"].update({"kernel": "pp local phase of R (hist + first radix pass + fine counts), rank 0",
+                                     "achieved": 28.0 * nR / (tm["local_R_ms"] * 1e-3) / 1e9, "algorithmic_bytes_per_launch": 28.0 * nR,
+                                     "local_phases_ms": {k: tm.get(k) for k in ("local_R_ms", "push_R_ms", "local_S_ms", "push_S_ms", "join_ms")}})
+            line["shuffle"]["scatter_kernel_ms"] = tm.get("shuffle_scatter_ms")
+        elif tm.get("pass_ms") and any(tm["pass_ms"][2:]):
             ps = [x for x in tm["pass_ms"][2:] if x > 0]
             line["roofline"].update({"kernel": "scatter_kernel (receiver's radix passes over S, rank 0)",
-                                     "achieved": 16.0 * r.local_S / (sum(ps) / len(ps) * 1e-3) / 1e9,
-                                     "algorithmic_bytes_per_launch": 16.0 * r.local_S, "avg_launch_ms": sum(ps) / len(ps),
-                                     "local_phases_ms": {"scatter_R_pass1": tm["pass_ms"][0], "scatter_R_pass2": tm["pass_ms"][1],
-                                                         "scatter_S_pass1": tm["pass_ms"][2], "scatter_S_pass2": tm["pass_ms"][3]}})
-        if args.shuffle in ("pcp", "pcp2") and tm.get("part_R_ms"):
-            line["roofline"].update({"kernel": "pcp source-side radix pass of R (layout + first pass, 16 B/tuple), rank 0",
-                                     "achieved": 16.0 * nR / (tm["part_R_ms"] * 1e-3) / 1e9, "algorithmic_bytes_per_launch": 16.0 * nR,
-                                     "local_phases_ms": {k: tm.get(k) for k in ("part_R_ms", "copy_R_ms", "recv_R_ms", "part_S_ms", "copy_S_ms", "recv_S_ms", "join_ms")}})
-            line["plan"] = {"gpu_bits": world.bit_length() - 1, "local_bits": tm.get("radix_bits"),
-                            "source_pass_bits": tm.get("pass1_bits"), "receiver_pass_bits": tm.get("pass2_bits")}
-            line["shuffle"]["note"] = ("partition-copy-partition: first radix pass at the source on [gpu | top local bits], whole first-pass "
-                                       "partitions bulk-copied (TMA, global->shared->peer global) into the receiver's layout, last pass + join "
-                                       "at the receiver; scatter_kernel_ms = the copy kernels of R and S")
-        if args.shuffle == "pp" and tm.get("local_R_ms"):
-            # dominant HBM-bound kernels of the sharded pipeline: the local phase of one relation =
-            # coarse histogram (4 B) + first pass (16 B) + fine counts (8 B) per tuple
-            line["roofline"].update({"kernel": "pp local phase of R (hist + first radix pass + fine counts), rank 0",
-                                     "achieved": 28.0 * nR / (tm["local_R_ms"] * 1e-3) / 1e9,
-                                     "algorithmic_bytes_per_launch": 28.0 * nR,
-                                     "local_phases_ms": {k: tm.get(k) for k in ("local_R_ms", "push_R_ms", "local_S_ms", "push_S_ms", "join_ms")}})
-            line["plan"] = {"gpu_bits": world.bit_length() - 1, "local_bits": tm.get("radix_bits"),
-                            "pass1_bits": tm.get("pass1_bits"), "pass2_bits": tm.get("pass2_bits")}
-            line["shuffle"]["note"] = ("partition-then-push: every GPU partitions its own shard on [gpu|local] bits; the last radix pass "
-                                       "stores its runs into the destination GPU's final partition buffer over NVLink; "
-                                       "scatter_kernel_ms = cursor kernel + pushing pass of R and S")
-        if line["shuffle"].get("nvlink_out_GBs_per_gpu"):
-            line["shuffle"]["nvlink_frac_of_peer_copy_peak"] = line["shuffle"]["nvlink_out_GBs_per_gpu"] / line["shuffle"]["nvlink_peak_GBs"]
-        if line["roofline"]["achieved"]:
+                                     "achieved": 16.0 * local_rs[1] / (sum(ps) / len(ps) * 1e-3) / 1e9,
+                                     "algorithmic_bytes_per_launch": 16.0 * local_rs[1], "avg_launch_ms": sum(ps) / len(ps)})
+            line["shuffle"]["scatter_kernel_ms"] = tm.get("shuffle_scatter_ms")
+        if line["roofline"].get("achieved"):
             line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
-        line["config"].update({"global_R": NR, "global_S": NS, "parallelism": f"radix-sharded over {world} GPUs, {args.shuffle} shuffle"
-                               + (", R's push overlapped with S's local pass" if args.shuffle == "pp" else
-                                  ", R's copy under S's first pass, S's copy under R's last pass" if args.shuffle == "pcp" else
-                                  ", probe side split in two halves, first half joined under the second half's copy" if args.shuffle == "pcp2" else
-                                  "" if args.no_overlap or args.shuffle != "p2p" else ", S shuffle overlapped with R's local passes")})
+        if cfg5:
+            line["config5"] = cfg5
         print(json.dumps(line))
     sj.close()
     dist.destroy_process_group()
@@ -566,7 +781,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--shuffle", default="auto", choices=["auto", "p2p", "nccl", "dma", "pp", "pcp", "pcp2"],
+    ap.add_argument("--pcp-stages", default="2,4", help="pcp: copy/receive stages of the building and of the probing relation")
+    ap.add_argument("--shuffle", default="auto", choices=["auto", "p2p", "nccl", "dma", "pp", "pcp"],
                     help="multi-GPU exchange: pp = partition locally, last radix pass pushes into the peers; p2p = peer-store "
                          "shuffle first, local passes at the receiver; pcp = first radix pass at the source, whole first-pass partitions "
                          "bulk-copied over NVLink, last pass at the receiver; auto = pcp (measured best, profiles/README.md)")
@@ -574,6 +790,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: shuffle and local passes back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-materialize", action="store_true", help="skip the materialising-join sub-record")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the config-5 (2e9 x 2e9, strong scaling) sub-record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

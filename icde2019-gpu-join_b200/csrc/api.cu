@@ -230,7 +230,12 @@ struct gj_ctx {
         unsigned char* block = nullptr;
         PcpTables tab[2];
         tup_t** bases[2] = {nullptr, nullptr};
-        unsigned char* h_pin = nullptr;      // pinned: bases staging [2][256 ptrs] + status read-back [2][4]
+        uint32_t** flag_ptrs[2] = {nullptr, nullptr};   // device: every GPU's flag buffer (local or mapped)
+        int first = 0;                       // the relation that builds (travels first)
+        uint32_t epoch = 0;                  // join number: the value the stage flags take
+        uint32_t stages[2] = {0, 0};
+        bool parted[2] = {false, false}, recv_done[2] = {false, false};
+        unsigned char* h_pin = nullptr;      // pinned: bases + flag pointers staging [2][2][256 ptrs] + status read-back [2][4]
         cudaEvent_t ev[2][6] = {};           // per relation: part begin/end, copy begin/end, recv begin/end
         cudaEvent_t jev[2] = {};
     } pcp;
@@ -249,7 +254,7 @@ struct gj_ctx {
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
-            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_nopart_max = 0, opt_pcp_ring = 0;
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_nopart_max = 0, opt_pcp_ring = 0, opt_pcp_timeout_ms = 5000;
     bool attrs_set = false;
 };
 
@@ -443,7 +448,7 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
         {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
         {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
         {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
-        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"nopart_max", &ctx->opt_nopart_max}, {"pcp_ring", &ctx->opt_pcp_ring},
+        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"nopart_max", &ctx->opt_nopart_max}, {"pcp_ring", &ctx->opt_pcp_ring}, {"pcp_timeout_ms", &ctx->opt_pcp_timeout_ms},
     };
     for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
     return nullptr;
@@ -522,18 +527,20 @@ static Plan choose_plan(const gj_ctx* ctx, uint64_t n_build, uint32_t forced_bit
 // ------------------------------------------------------------------------------------------
 static int enqueue_hist(gj_ctx* ctx, cudaStream_t s, const void* in, bool packed, uint64_t n,
                         uint32_t shift, uint32_t bits, uint32_t* ghist, int threads = 1024,
-                        const uint32_t* n_dev = nullptr) {   // n_dev: the count lives on the device, n is its upper bound
+                        const uint32_t* lo_dev = nullptr, const uint32_t* hi_dev = nullptr,   // the slot range lives on the device, n is its upper bound
+                        int max_ctas = 0) {
     if (!n) return GJ_OK;
     const uint64_t per_cta = (uint64_t)threads * 16;
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count, (n + per_cta - 1) / per_cta));
+    const uint64_t sms = max_ctas > 0 ? (uint64_t)max_ctas : (uint64_t)ctx->sm_count;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(sms, (n + per_cta - 1) / per_cta));
     const bool p16 = bits > 15;   // two 16-bit counters per word
     const size_t smem = p16 ? (size_t)2 << bits : (size_t)4 << bits;
     if (packed) {
-        if (p16) hist_kernel<true, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, n_dev);
-        else hist_kernel<true, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, n_dev);
+        if (p16) hist_kernel<true, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, lo_dev, hi_dev);
+        else hist_kernel<true, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, lo_dev, hi_dev);
     } else {
-        if (p16) hist_kernel<false, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, n_dev);
-        else hist_kernel<false, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, n_dev);
+        if (p16) hist_kernel<false, true><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, lo_dev, hi_dev);
+        else hist_kernel<false, false><<<grid, threads, smem, s>>>(in, (uint32_t)n, shift, bits, ghist, lo_dev, hi_dev);
     }
     LAUNCHED();
     return GJ_OK;
@@ -583,6 +590,7 @@ static int enqueue_plan(gj_ctx* ctx, cudaStream_t s, int first, uint32_t nrel, c
         a.rel[r].off = m.off; a.rel[r].cur1 = m.cur1; a.rel[r].cur2 = m.cur2; a.rel[r].tiles = m.tiles; a.rel[r].num_tiles = m.num_tiles;
     }
     a.nrel = nrel; a.with_units = with_units ? 1u : 0u; a.b1 = pl.b1; a.b2 = pl.b2;
+    a.j_lo = a.j_hi = 0;
     if (nrel == 0) for (uint32_t r = 0; r < 2; ++r) a.rel[r].off = ctx->meta[r].off;   // units only
     const ScatterCfg& c2 = scatter_cfg2(ctx, pl.b2);
     a.tile = (uint32_t)(c2.threads * c2.ipt);
@@ -1796,24 +1804,33 @@ extern "C" int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bit
 }
 
 // ------------------------------------------------------------------------------------------
-// Sharded "partition, copy, partition" pipeline (multi-GPU; kernels.cuh section 3d).  Per relation:
+// Sharded "partition, copy, partition" pipeline (multi-GPU; kernels.cuh section 3d).  The relation
+// that builds (the globally smaller one) goes first.  Per relation:
 //   gj_pcp_hist : this shard's first-pass histogram on [gpu bits | top local bits] (2^b1 counters)
 //   [caller: all-gather of those histograms]
-//   gj_pcp_part : layout (pcp_layout_kernel) + first radix pass into the stage buffer (ctx->out[which])
-//   gj_pcp_copy : TMA bulk-copy kernel: every chunk to its slot in the destination's receive buffer
-//   [caller: cross-rank "all copies have landed" point]
-//   gj_pcp_recv : histogram + scan + plan + LAST radix pass over what this GPU received -> ctx->out[which]
-//   gj_pcp_join / gj_pcp_finish
+//   gj_pcp_part : layout (pcp_layout_kernel) + first radix pass: remote chunks into the stage buffer,
+//                 this GPU's own chunks straight into its receive buffer
+//   gj_pcp_copy : n_stages x (TMA bulk-copy kernel over a group of first-pass partitions, then a flag
+//                 store into every peer): every remote chunk to its slot in the destination's buffer
+//   gj_pcp_recv : per stage: wait for every source's flag, histogram + scan + plan + LAST radix pass
+//                 over the first-pass partitions of the stage; for the probing relation also unit
+//                 planning + join of those partitions -- while later stages still cross NVLink
+//   gj_pcp_finish
+// Buffers: the first relation stages in ctx->scratch and ends in ctx->out[first]; the second stages
+// in ctx->out[second] and ends in ctx->scratch (free again once the first relation's copy is done,
+// which every rank's flags for the second relation imply).
 // ------------------------------------------------------------------------------------------
 static int ensure_pcp(gj_ctx* ctx) {
     gj_ctx::PCP& q = ctx->pcp;
     if (q.block) return GJ_OK;
     const size_t per = (size_t)(PCP_MAX_CHUNKS + 4) * sizeof(uint32_t);
     size_t b = 0;
-    size_t o[2][6], o_bs[2];
+    size_t o[2][7], o_db[2], o_bs[2], o_fl[2];
     for (int r = 0; r < 2; ++r) {
-        for (int k = 0; k < 6; ++k) { o[r][k] = b; b += per; }
+        for (int k = 0; k < 7; ++k) { o[r][k] = b; b += per; }
+        o_db[r] = b; b += PCP_MAX_CHUNKS * sizeof(tup_t*);
         o_bs[r] = b; b += NB_MAX * sizeof(tup_t*);
+        o_fl[r] = b; b += NB_MAX * sizeof(uint32_t*);
     }
     if (cudaMalloc(&q.block, b) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "pcp metadata"); }
     for (int r = 0; r < 2; ++r) {
@@ -1823,15 +1840,33 @@ static int ensure_pcp(gj_ctx* ctx) {
         q.tab[r].cnt = reinterpret_cast<uint32_t*>(q.block + o[r][3]);
         q.tab[r].piece_prefix = reinterpret_cast<uint32_t*>(q.block + o[r][4]);
         q.tab[r].status = reinterpret_cast<uint32_t*>(q.block + o[r][5]);
+        q.tab[r].recv_off = reinterpret_cast<uint32_t*>(q.block + o[r][6]);
+        q.tab[r].dig_base = reinterpret_cast<tup_t**>(q.block + o_db[r]);
         q.bases[r] = reinterpret_cast<tup_t**>(q.block + o_bs[r]);
+        q.flag_ptrs[r] = reinterpret_cast<uint32_t**>(q.block + o_fl[r]);
     }
-    CK(cudaHostAlloc(&q.h_pin, 2 * NB_MAX * sizeof(void*) + 64, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&q.h_pin, 4 * NB_MAX * sizeof(void*) + 64, cudaHostAllocDefault));
     for (auto& r : q.ev) for (auto& e : r) CK(cudaEventCreate(&e));
     for (auto& e : q.jev) CK(cudaEventCreate(&e));
     return GJ_OK;
 }
 
 static const PPCfg& pcp_last_cfg(uint32_t bits) { return kPcpLast[bits <= 7u ? 0u : bits - 7u]; }
+static int pcp_last_ctas_per_sm(uint32_t bits) { return bits <= 7u ? 4 : (bits <= 9u ? 2 : 1); }
+// SMs left to the kernels that run next to the copy kernel: with "shuffle_grid" = k <= half the SMs and
+// the deep ring, k SMs are filled by copy CTAs (196 KB of shared memory each) and host nothing else
+static int pcp_free_sms(const gj_ctx* ctx) {
+    const int64_t k = ctx->opt_shuffle_grid;
+    return (ctx->opt_pcp_ring && k > 0 && k <= ctx->sm_count / 2) ? ctx->sm_count - (int)k : ctx->sm_count;
+}
+static tup_t* pcp_stage_buf(gj_ctx* ctx, int which) { return which == ctx->pcp.first ? ctx->scratch : ctx->out[which]; }
+static tup_t* pcp_final_buf(gj_ctx* ctx, int which) { return which == ctx->pcp.first ? ctx->out[which] : ctx->scratch; }
+static uint64_t pcp_stage_cap(const gj_ctx* ctx, int which) {
+    return which == ctx->pcp.first ? std::max(ctx->maxR, ctx->maxS) : (which ? ctx->maxS : ctx->maxR);
+}
+static uint64_t pcp_final_cap(const gj_ctx* ctx, int which) {
+    return which == ctx->pcp.first ? (which ? ctx->maxS : ctx->maxR) : std::max(ctx->maxR, ctx->maxS);
+}
 
 extern "C" int gj_pcp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
                             uint32_t local_bits, void* cuda_stream) {
@@ -1857,8 +1892,12 @@ extern "C" int gj_pcp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_globa
     const bool swap = n_R_global > n_S_global;
     q.role_of_side[0] = swap ? 1 : 0;
     q.role_of_side[1] = swap ? 0 : 1;
+    q.first = swap ? 1 : 0;
     q.n_glob[0] = n_R_global; q.n_glob[1] = n_S_global;
+    q.recv_done[0] = q.recv_done[1] = false;
+    q.parted[0] = q.parted[1] = false;
     q.active = true;
+    ++q.epoch;
     ctx->launches = 0;
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     CK(cudaMemsetAsync(ctx->zero_common, 0, ctx->zero_common_bytes, s));
@@ -1878,8 +1917,8 @@ extern "C" int gj_pcp_hist(gj_ctx* ctx, int which, const int32_t* d_keys, uint64
     if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
     if (!d_coarse_hist || (n && !d_keys)) return fail(GJ_ERR_ARG, "NULL argument");
     gj_ctx::PCP& q = ctx->pcp;
-    // every chunk is staged with one spare slot (16-byte phase matching)
-    if (n + (1ull << q.b1) > (which ? ctx->maxS : ctx->maxR) + 16) return fail(GJ_ERR_ARG, "n + %u spare slots exceed the context capacity", 1u << q.b1);
+    // every staged chunk has one spare slot (16-byte phase matching)
+    if (n + (1ull << q.b1) > pcp_stage_cap(ctx, which) + 16) return fail(GJ_ERR_ARG, "n + %u spare slots exceed the context capacity", 1u << q.b1);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     q.n_loc[which] = n;
@@ -1889,127 +1928,191 @@ extern "C" int gj_pcp_hist(gj_ctx* ctx, int which, const int32_t* d_keys, uint64
 }
 
 extern "C" int gj_pcp_part(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays,
-                           const uint32_t* d_all_hist, uint64_t cap_tuples, void* cuda_stream) {
+                           const uint32_t* d_all_hist, void* d_own, uint64_t cap_tuples, void* cuda_stream) {
     if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
     if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
     gj_ctx::PCP& q = ctx->pcp;
     const uint64_t n = q.n_loc[which];
     if (!d_all_hist || (n && (!d_keys || !d_pays))) return fail(GJ_ERR_ARG, "NULL argument");
+    if (!d_own || ((size_t)d_own & 15u)) return fail(GJ_ERR_ARG, "receive buffer must be non-NULL and 16-byte aligned");
     if (cap_tuples > 0xFFFFFFFFull) return fail(GJ_ERR_ARG, "destination capacity exceeds 2^32 tuples");
+    if (which != q.first && !q.parted[q.first]) return fail(GJ_ERR_STATE, "partition the building (smaller) relation first");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     const uint32_t perm = (q.b1 << 8) | q.g;
     CK(cudaEventRecord(q.ev[which][0], s));
-    pcp_layout_kernel<<<1, PCP_MAX_CHUNKS, 0, s>>>(d_all_hist, q.G, q.rank, q.b1, q.bl, (uint32_t)cap_tuples, perm, q.tab[which]);
+    pcp_layout_kernel<<<1, PCP_MAX_CHUNKS, 0, s>>>(d_all_hist, q.G, q.rank, q.b1, q.bl, (uint32_t)cap_tuples, perm,
+                                                  pcp_stage_buf(ctx, which), (tup_t*)d_own, q.tab[which]);
     LAUNCHED();
     if (n) {
         const PPCfg& c1 = pp_first_cfg(q.b1);
         const uint32_t T1 = (uint32_t)(c1.threads * c1.ipt);
         ScatterArgs a;
         memset(&a, 0, sizeof(a));
-        a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = ctx->out[which];
+        a.in_keys = d_keys; a.in_pays = d_pays; a.n = (uint32_t)n; a.out = nullptr;
+        a.dst_bases = q.tab[which].dig_base;        // per chunk: the stage buffer, or this GPU's receive buffer
+        a.abort_flag = q.tab[which].status;         // a destination would overflow: nothing is written
         a.shift = q.B - q.bl; a.bits = q.b1; a.cursors = q.tab[which].cur; a.cursor_stride = 1;
         a.ntiles = (uint32_t)((n + T1 - 1) / T1);
         c1.fn<<<a.ntiles, c1.threads, pp_smem(c1), s>>>(a);
         LAUNCHED();
     }
     CK(cudaEventRecord(q.ev[which][1], s));
+    q.parted[which] = true;
     return GJ_OK;
 }
 
-extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* cuda_stream) {
+extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* const* peer_flags, uint32_t n_stages,
+                           void* cuda_stream) {
     if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
     if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
-    if (!peer_bases) return fail(GJ_ERR_ARG, "NULL argument");
-    CK(cudaSetDevice(ctx->device));
+    if (!peer_bases || !peer_flags) return fail(GJ_ERR_ARG, "NULL argument");
+    if (n_stages < 1 || n_stages > (uint32_t)PCP_MAX_STAGES) return fail(GJ_ERR_ARG, "n_stages must be in [1, %d]", PCP_MAX_STAGES);
     gj_ctx::PCP& q = ctx->pcp;
+    if (!q.parted[which]) return fail(GJ_ERR_STATE, "gj_pcp_part first");
+    CK(cudaSetDevice(ctx->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    void** hb = reinterpret_cast<void**>(q.h_pin) + (size_t)which * NB_MAX;
+    void** hb = reinterpret_cast<void**>(q.h_pin) + (size_t)which * 2 * NB_MAX;
     for (uint32_t g = 0; g < q.G; ++g) {
         if (!peer_bases[g] || ((size_t)peer_bases[g] & 15u)) return fail(GJ_ERR_ARG, "destination buffer %u must be non-NULL and 16-byte aligned", g);
+        if (!peer_flags[g]) return fail(GJ_ERR_ARG, "flag buffer %u is NULL", g);
         hb[g] = peer_bases[g];
+        hb[NB_MAX + g] = peer_flags[g];
     }
     CK(cudaMemcpyAsync(q.bases[which], hb, q.G * sizeof(void*), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(q.flag_ptrs[which], hb + NB_MAX, q.G * sizeof(void*), cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(q.ev[which][2], s));
-    if (q.n_loc[which]) {
-        PcpCopyArgs a;
-        a.stage = ctx->out[which]; a.peer_bases = q.bases[which]; a.t = q.tab[which];
-        a.b1 = q.b1; a.bl = q.bl; a.perm = (q.b1 << 8) | q.g;
-        const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
-        uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count;   // measured (2 GPUs): 148 CTAs 3.98 ms, 296 CTAs 4.24 ms per step
-        grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));
-        if (ctx->opt_pcp_ring) pcp_copy_kernel<PCP_NS_DEEP><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
-        else pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
+    const uint32_t nj = 1u << q.bl, K = std::min(n_stages, nj);
+    q.stages[which] = K;
+    PcpCopyArgs a;
+    a.stage = pcp_stage_buf(ctx, which); a.peer_bases = q.bases[which]; a.t = q.tab[which];
+    a.b1 = q.b1; a.bl = q.bl; a.perm = (q.b1 << 8) | q.g;
+    const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
+    uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count;
+    grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));
+    for (uint32_t k = 0; k < K; ++k) {
+        // copy positions are (first-pass partition j, destination d) with d fastest: stage k = partitions [j_lo, j_hi)
+        a.pos_lo = (uint32_t)(((uint64_t)k * nj / K) << q.g);
+        a.pos_hi = (uint32_t)(((uint64_t)(k + 1) * nj / K) << q.g);
+        if (q.n_loc[which]) {
+            if (ctx->opt_pcp_ring) pcp_copy_kernel<PCP_NS_DEEP><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
+            else pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
+            LAUNCHED();
+        }
+        pcp_signal_kernel<<<1, std::max(32u, q.G), 0, s>>>(q.flag_ptrs[which], q.G, q.rank, (uint32_t)which * PCP_MAX_STAGES + k, q.epoch);
         LAUNCHED();
     }
     CK(cudaEventRecord(q.ev[which][3], s));
     return GJ_OK;
 }
 
-extern "C" int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, uint64_t cap_tuples, void* cuda_stream) {
+extern "C" int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, const void* d_flags, uint64_t cap_tuples,
+                           void* cuda_stream) {
     if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
     if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
     if (!d_own || ((size_t)d_own & 15u)) return fail(GJ_ERR_ARG, "receive buffer must be non-NULL and 16-byte aligned");
-    if (cap_tuples > (which ? ctx->maxS : ctx->maxR)) return fail(GJ_ERR_ARG, "receive capacity exceeds the context capacity");
-    CK(cudaSetDevice(ctx->device));
+    if (!d_flags) return fail(GJ_ERR_ARG, "flag buffer is NULL");
     gj_ctx::PCP& q = ctx->pcp;
+    if (cap_tuples > pcp_final_cap(ctx, which)) return fail(GJ_ERR_ARG, "receive capacity exceeds the context capacity");
+    if (!q.stages[which] || !q.parted[which]) return fail(GJ_ERR_STATE, "gj_pcp_part and gj_pcp_copy first");
+    const bool joins = (which != q.first);          // the probing relation: join every stage as it lands
+    if (joins && !q.recv_done[q.first]) return fail(GJ_ERR_STATE, "receive the building (smaller) relation first");
+    CK(cudaSetDevice(ctx->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     const int role = q.role_of_side[which];
     const RelMeta& m = ctx->meta[role];
-    const uint32_t* n_dev = q.tab[which].status + 1;     // tuples this GPU received (pcp_layout_kernel)
+    const PcpTables& tb = q.tab[which];
+    const uint32_t nb = 1u << q.B, nj = 1u << q.bl, K = q.stages[which];
+    const int free_sms = pcp_free_sms(ctx);
     int rc;
+    CK(cudaStreamWaitEvent(s, q.ev[which][1], 0));   // this GPU's own chunks are in place (source pass done)
     CK(cudaEventRecord(q.ev[which][4], s));
     CK(cudaMemsetAsync(ctx->zero_role[role], 0, ctx->zero_role_bytes, s));
-    if (!q.n_glob[which]) { CK(cudaEventRecord(q.ev[which][5], s)); return GJ_OK; }
-    if ((rc = enqueue_hist(ctx, s, d_own, true, cap_tuples, 0, q.B, m.ghist, 1024, n_dev))) return rc;
-    if ((rc = enqueue_scan(ctx, s, role, 1, 1u << q.B, false))) return rc;
+    const bool empty = !q.n_glob[which];
     const PPCfg& c2 = pcp_last_cfg(q.b2);
     const uint32_t T2 = (uint32_t)(c2.threads * c2.ipt);
-    {   // cursors + last-pass tile list; the receive buffer IS the first-pass output (bl bits done)
-        PlanArgs a;
-        memset(&a, 0, sizeof(a));
-        a.rel[0].off = m.off; a.rel[0].cur1 = m.cur1; a.rel[0].cur2 = m.cur2; a.rel[0].tiles = m.tiles; a.rel[0].num_tiles = m.num_tiles;
-        a.rel[1] = a.rel[0];
-        a.nrel = 1; a.with_units = 0; a.b1 = q.bl; a.b2 = q.b2; a.tile = T2; a.unit = unit_tuples(ctx);
-        a.unit_base = ctx->unit_base; a.units = ctx->units;
-        const uint32_t nb = 1u << q.B;
-        const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(128, (nb + PLAN_THREADS - 1) / PLAN_THREADS + 32));
-        plan_kernel<<<grid, PLAN_THREADS, 0, s>>>(a);
-        LAUNCHED();
-    }
-    ScatterArgs b;
-    memset(&b, 0, sizeof(b));
-    b.in_tup = (const tup_t*)d_own; b.out = ctx->out[which]; b.n = (uint32_t)cap_tuples;
-    b.shift = 0; b.bits = q.b2;
-    b.cursors = m.cur2; b.cursor_stride = 1; b.tiles = m.tiles; b.num_tiles = m.num_tiles;
-    const uint32_t grid2 = (uint32_t)(cap_tuples / T2) + (1u << q.bl) + 2;   // upper bound on tiles
-    c2.fn<<<grid2, c2.threads, pp_smem(c2), s>>>(b);
-    LAUNCHED();
-    CK(cudaEventRecord(q.ev[which][5], s));
-    return GJ_OK;
-}
-
-extern "C" int gj_pcp_join(gj_ctx* ctx, uint64_t cap_R, uint64_t cap_S, void* cuda_stream) {
-    if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
-    CK(cudaSetDevice(ctx->device));
-    gj_ctx::PCP& q = ctx->pcp;
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    CK(cudaStreamWaitEvent(s, ctx->stage_ev[3], 0));
-    Plan pl; pl.B = q.B; pl.b1 = q.B; pl.b2 = 0;
+    const size_t res_off = (size_t)(reinterpret_cast<unsigned char*>(ctx->result) - ctx->zero_common);
+    const size_t desc_off = (size_t)(reinterpret_cast<unsigned char*>(m.desc) - ctx->zero_role[role]);
     const bool r_builds = q.role_of_side[0] == 0;
-    int rc;
-    CK(cudaEventRecord(q.jev[0], s));
-    if (q.n_glob[0] && q.n_glob[1]) {
-        if ((rc = enqueue_scan(ctx, s, 0, 0, 1u << pl.B, true))) return rc;
-        if ((rc = enqueue_plan(ctx, s, 0, 0, pl, true))) return rc;
-        if ((rc = enqueue_join(ctx, s, ctx->out[r_builds ? 0 : 1], ctx->out[r_builds ? 1 : 0], pl, r_builds ? cap_R : cap_S,
-                               r_builds ? cap_S : cap_R, false, nullptr, nullptr, 0, nullptr, (int)q.g))) return rc;
+    bool waited_build = false;
+    for (uint32_t k = 0; k < K && !empty; ++k) {
+        const uint32_t j_lo = (uint32_t)((uint64_t)k * nj / K), j_hi = (uint32_t)((uint64_t)(k + 1) * nj / K);
+        pcp_wait_kernel<<<1, std::max(32u, q.G), 0, s>>>((const uint32_t*)d_flags, q.G, q.rank, (uint32_t)which * PCP_MAX_STAGES + k,
+                                                         q.epoch, (unsigned long long)ctx->opt_pcp_timeout_ms * 1000000ull, tb.status);
+        LAUNCHED();
+        if (k + 1 == K) CK(cudaEventRecord(q.jev[0], s));      // the last byte of this relation has landed
+        // fine histogram of what arrived for [j_lo, j_hi); the counters of earlier stages stay, so the
+        // full-range scan below yields the same offsets for them again and the new ones behind them
+        if (k) CK(cudaMemsetAsync(ctx->zero_role[role] + desc_off, 0, ctx->zero_role_bytes - desc_off, s));
+        if ((rc = enqueue_hist(ctx, s, d_own, true, cap_tuples, 0, q.B, m.ghist, 1024, tb.recv_off + j_lo, tb.recv_off + j_hi, free_sms))) return rc;
+        {
+            ScanSeq so;
+            so.in = m.ghist; so.in2 = nullptr; so.out = m.off; so.desc = m.desc; so.ticket = m.ticket;
+            so.mode = SCAN_PLAIN; so.param = 0; so.param2 = 0;
+            if ((rc = enqueue_scan_one(ctx, s, so, nb))) return rc;
+        }
+        {   // cursors + last-pass tile list of the stage; the receive buffer IS the first-pass output (bl bits done)
+            PlanArgs a;
+            memset(&a, 0, sizeof(a));
+            a.rel[0].off = m.off; a.rel[0].cur1 = m.cur1; a.rel[0].cur2 = m.cur2; a.rel[0].tiles = m.tiles; a.rel[0].num_tiles = m.num_tiles;
+            a.rel[1] = a.rel[0];
+            a.nrel = 1; a.with_units = 0; a.b1 = q.bl; a.b2 = q.b2; a.tile = T2; a.unit = unit_tuples(ctx);
+            a.unit_base = ctx->unit_base; a.units = ctx->units;
+            a.j_lo = j_lo; a.j_hi = j_hi;
+            const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(128, (nb / K + PLAN_THREADS - 1) / PLAN_THREADS + 32));
+            plan_kernel<<<grid, PLAN_THREADS, 0, s>>>(a);
+            LAUNCHED();
+        }
+        {
+            ScatterArgs b;
+            memset(&b, 0, sizeof(b));
+            b.in_tup = (const tup_t*)d_own; b.out = pcp_final_buf(ctx, which); b.n = (uint32_t)cap_tuples;
+            b.shift = 0; b.bits = q.b2;
+            b.cursors = m.cur2; b.cursor_stride = 1; b.tiles = m.tiles; b.num_tiles = m.num_tiles;
+            const uint64_t bound = cap_tuples / T2 + (j_hi - j_lo) + 2;   // upper bound on the stage's tiles (skew: all of them)
+            const uint32_t grid2 = (uint32_t)std::min<uint64_t>(bound, (uint64_t)free_sms * pcp_last_ctas_per_sm(q.b2) * 2);
+            c2.fn<<<grid2, c2.threads, pp_smem(c2), s>>>(b);
+            LAUNCHED();
+        }
+        if (joins && q.n_glob[0] && q.n_glob[1]) {
+            if (!waited_build) {
+                CK(cudaStreamWaitEvent(s, q.ev[q.first][5], 0));    // the build side is received and partitioned
+                CK(cudaStreamWaitEvent(s, ctx->stage_ev[3], 0));    // the accumulators are zeroed
+                waited_build = true;
+            }
+            CK(cudaMemsetAsync(ctx->zero_common, 0, res_off, s));   // re-arm the unit scan; the accumulators keep counting
+            ScanSeq su;
+            su.in = ctx->meta[0].ghist; su.in2 = ctx->meta[1].ghist; su.out = ctx->unit_base; su.desc = ctx->unit_desc; su.ticket = ctx->unit_ticket;
+            su.mode = SCAN_UNITS; su.param = unit_tuples(ctx); su.param2 = 0;
+            su.lo = j_lo << q.b2; su.hi = j_hi << q.b2;
+            if ((rc = enqueue_scan_one(ctx, s, su, nb))) return rc;
+            PlanArgs a;
+            memset(&a, 0, sizeof(a));
+            a.rel[0].off = ctx->meta[0].off; a.rel[1].off = ctx->meta[1].off;
+            a.nrel = 0; a.with_units = 1; a.b1 = q.bl; a.b2 = q.b2; a.tile = T2; a.unit = unit_tuples(ctx);
+            a.unit_base = ctx->unit_base; a.units = ctx->units;
+            a.j_lo = j_lo; a.j_hi = j_hi;
+            plan_kernel<<<std::max(1u, std::min(128u, (nb / K + PLAN_THREADS - 1) / PLAN_THREADS)), PLAN_THREADS, 0, s>>>(a);
+            LAUNCHED();
+            Plan pl; pl.B = q.B; pl.b1 = q.B; pl.b2 = 0;
+            const int bw = r_builds ? 0 : 1;
+            const int64_t keep_grid = ctx->opt_join_grid;
+            if (!keep_grid && free_sms < ctx->sm_count) ctx->opt_join_grid = free_sms;
+            rc = enqueue_join(ctx, s, pcp_final_buf(ctx, bw), pcp_final_buf(ctx, 1 - bw), pl, 0, cap_tuples / K + 1, false,
+                              nullptr, nullptr, 0, nullptr, (int)q.g);
+            ctx->opt_join_grid = keep_grid;
+            if (rc) return rc;
+        }
     }
-    CK(cudaEventRecord(q.jev[1], s));
-    CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    uint32_t* hs = reinterpret_cast<uint32_t*>(q.h_pin + 2 * NB_MAX * sizeof(void*));
-    for (int w = 0; w < 2; ++w) CK(cudaMemcpyAsync(hs + 4 * w, q.tab[w].status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaEventRecord(q.ev[which][5], s));
+    q.recv_done[which] = true;
+    if (joins) {
+        CK(cudaEventRecord(q.jev[1], s));
+        CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        uint32_t* hs = reinterpret_cast<uint32_t*>(q.h_pin + 4 * NB_MAX * sizeof(void*));
+        for (int w = 0; w < 2; ++w) CK(cudaMemcpyAsync(hs + 4 * w, q.tab[w].status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(ctx->ev[3], s));
+    }
     return GJ_OK;
 }
 
@@ -2017,23 +2120,29 @@ extern "C" int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum,
                              uint64_t* n_local_S, float* phase_ms, uint32_t* plan_bits) {
     if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
     gj_ctx::PCP& q = ctx->pcp;
+    if (!q.recv_done[0] || !q.recv_done[1]) return fail(GJ_ERR_STATE, "gj_pcp_recv of both relations first");
     CK(cudaEventSynchronize(ctx->ev[3]));
     q.active = false;
-    const uint32_t* hs = reinterpret_cast<const uint32_t*>(q.h_pin + 2 * NB_MAX * sizeof(void*));
+    q.stages[0] = q.stages[1] = 0;
+    const uint32_t* hs = reinterpret_cast<const uint32_t*>(q.h_pin + 4 * NB_MAX * sizeof(void*));
     if (n_local_R) *n_local_R = hs[1];
     if (n_local_S) *n_local_S = hs[5];
     if (plan_bits) { plan_bits[0] = q.g; plan_bits[1] = q.bl; plan_bits[2] = q.b2; }
+    if (hs[3] || hs[7])
+        return fail(GJ_ERR_STATE, "sharded join: timed out waiting for a peer's data (option \"pcp_timeout_ms\" = %lld)", (long long)ctx->opt_pcp_timeout_ms);
     if (hs[0] || hs[4])
         return fail(GJ_ERR_ARG, "sharded join: a destination GPU would receive more tuples than its buffer holds "
                                 "(this GPU: %u R, %u S tuples) -- raise the receive-buffer slack", hs[1], hs[5]);
     if (matches) *matches = ctx->h_result[0];
     if (checksum) *checksum = ctx->h_result[1];
-    if (phase_ms) {   // [part R, copy R, recv R, part S, copy S, recv S, join]
+    if (phase_ms) {   // [part R, copy R, recv R, part S, copy S, recv S, tail = last byte of the probe side landed -> last join done]
         for (int w = 0; w < 2; ++w) {
             CK(cudaEventSynchronize(q.ev[w][5]));
+            CK(cudaEventSynchronize(q.ev[w][3]));
             for (int k = 0; k < 3; ++k) CK(cudaEventElapsedTime(&phase_ms[3 * w + k], q.ev[w][2 * k], q.ev[w][2 * k + 1]));
         }
-        CK(cudaEventElapsedTime(&phase_ms[6], q.jev[0], q.jev[1]));
+        phase_ms[6] = 0.f;
+        if (q.n_glob[1 - q.first]) CK(cudaEventElapsedTime(&phase_ms[6], q.jev[0], q.jev[1]));
     }
     return GJ_OK;
 }
@@ -2094,6 +2203,7 @@ extern "C" int gj_malloc_pinned(void** p, uint64_t bytes) {
 extern "C" int gj_free_pinned(void* p) { CK(cudaFreeHost(p)); return GJ_OK; }
 extern "C" int gj_memcpy_h2d(void* d, const void* h, uint64_t bytes) { CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); return GJ_OK; }
 extern "C" int gj_memcpy_d2h(void* h, const void* d, uint64_t bytes) { CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); return GJ_OK; }
+extern "C" int gj_memset_device(void* d, int value, uint64_t bytes) { CK(cudaMemset(d, value, bytes)); return GJ_OK; }
 extern "C" int gj_device_synchronize(void) { CK(cudaDeviceSynchronize()); return GJ_OK; }
 
 extern "C" int gj_flush_l2(gj_ctx* ctx) {

@@ -75,9 +75,13 @@ __device__ __forceinline__ void hist_add(uint32_t* sh, uint32_t d, uint32_t* ghi
 template <bool PACKED, bool P16>
 __global__ void __launch_bounds__(1024, 1)
 hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bits,
-            uint32_t* __restrict__ ghist, const uint32_t* __restrict__ n_dev = nullptr) {
+            uint32_t* __restrict__ ghist, const uint32_t* __restrict__ lo_dev = nullptr,
+            const uint32_t* __restrict__ hi_dev = nullptr) {
     extern __shared__ uint32_t sh_hist[];
-    if (n_dev) n = *n_dev;   // tuple count produced on the device (sharded pipelines: what this GPU received)
+    // sharded pipelines: the slots [*lo_dev, *hi_dev) of `in` (what this GPU received for a group of
+    // first-pass partitions) -- known on the device only
+    uint32_t first = 0;
+    if (lo_dev) { first = *lo_dev; n = *hi_dev - first; }
     const uint32_t nb = 1u << bits, mask = nb - 1u;
     const uint32_t nwords = P16 ? nb >> 1 : nb;
     for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) sh_hist[i] = 0;
@@ -87,7 +91,7 @@ hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bi
     const uint32_t gsz = gridDim.x * blockDim.x;
 #define GJ_HADD(key) hist_add<P16>(sh_hist, ((uint32_t)(key) >> shift) & mask, ghist)
     if (!PACKED) {
-        const int32_t* keys = (const int32_t*)in;
+        const int32_t* keys = (const int32_t*)in + first;
         uint32_t head = (uint32_t)(((16u - (uint32_t)((size_t)keys & 15u)) & 15u) >> 2);
         if (head > n) head = n;
         const uint32_t nvec = (n - head) >> 2;
@@ -110,7 +114,7 @@ hist_kernel(const void* __restrict__ in, uint32_t n, uint32_t shift, uint32_t bi
         if (gtid < head) GJ_HADD(keys[gtid]);
         if (tail0 + gtid < n) GJ_HADD(keys[tail0 + gtid]);
     } else {
-        const tup_t* tp = (const tup_t*)in;
+        const tup_t* tp = (const tup_t*)in + first;
         uint32_t head = (uint32_t)(((size_t)tp & 15u) ? 1u : 0u);
         if (head > n) head = n;
         const uint32_t nvec = (n - head) >> 1;
@@ -187,21 +191,6 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
-// variants carrying an L2 cache policy (streaming data that must not evict the partially written
-// lines of a scatter pass running next to it)
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol) : "memory");
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
@@ -226,6 +215,7 @@ struct ScanSeq {
     uint32_t mode;                // SCAN_*
     uint32_t param;               // UNITS: probe tuples per unit; TILES: tuples per scatter tile
     uint32_t param2;              // TILES: parent order (tile_perm), 0 = identity
+    uint32_t lo = 0, hi = 0;      // UNITS: only partitions in [lo, hi) produce units (hi == 0: all)
 };
 struct ScanArgs {
     ScanSeq seq[3];
@@ -268,7 +258,7 @@ scan_lookback_kernel(ScanArgs a) {
         v[j] = 0;
         if (base + j < a.nb) {
             if (r.mode == SCAN_PLAIN) v[j] = r.in[base + j];
-            else if (r.mode == SCAN_UNITS) v[j] = units_of(r.in[base + j], r.in2[base + j], r.param);
+            else if (r.mode == SCAN_UNITS) v[j] = (r.hi == 0u || (base + j >= r.lo && base + j < r.hi)) ? units_of(r.in[base + j], r.in2[base + j], r.param) : 0u;
             else { const uint32_t c = tile_perm(base + j, r.param2); v[j] = tiles_of(r.in[c], r.in[c + 1], r.param); }
         }
         tsum += v[j];
@@ -352,6 +342,9 @@ struct PlanArgs {
     uint32_t unit;         // probe tuples per join unit
     const uint32_t* unit_base;   // nb + 1 (exclusive scan of units per partition)
     uint4* units;
+    // staged receiver of the sharded pipeline: only first-pass partitions [j_lo, j_hi) get cursors,
+    // tiles and units (j_hi == 0: everything)
+    uint32_t j_lo, j_hi;
 };
 
 __global__ void __launch_bounds__(PLAN_THREADS)
@@ -360,16 +353,18 @@ plan_kernel(PlanArgs a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t gtid = blockIdx.x * PLAN_THREADS + tid, gsz = gridDim.x * PLAN_THREADS;
     const uint32_t B = a.b1 + a.b2, nb = 1u << B, n1 = 1u << a.b1;
+    const uint32_t j_lo = a.j_hi ? a.j_lo : 0u, j_hi = a.j_hi ? a.j_hi : n1;
+    const uint32_t p_lo = a.j_hi ? (j_lo << a.b2) : 0u, p_hi = a.j_hi ? (j_hi << a.b2) : nb;
     for (uint32_t r = 0; r < a.nrel; ++r) {
         const PlanRel R = a.rel[r];
-        for (uint32_t p = gtid; p < nb; p += gsz) R.cur2[p] = R.off[p];
+        for (uint32_t p = p_lo + gtid; p < p_hi; p += gsz) R.cur2[p] = R.off[p];
         if (a.b2) {
             // every CTA recomputes the (<= 256 entry) tile prefix in shared memory
             uint32_t lo = 0, hi = 0, a0 = 0, tiles = 0;
             if (tid < n1) {
                 lo = R.off[tid << a.b2]; hi = R.off[(tid + 1) << a.b2];
                 a0 = lo & ~1u;
-                tiles = hi > lo ? (hi - a0 + a.tile - 1) / a.tile : 0u;
+                tiles = (hi > lo && tid >= j_lo && tid < j_hi) ? (hi - a0 + a.tile - 1) / a.tile : 0u;
                 if (blockIdx.x == 0) R.cur1[tid * CUR1_STRIDE] = lo;
             }
             __syncthreads();   // previous relation's readers of s_tp are done
@@ -403,7 +398,7 @@ plan_kernel(PlanArgs a) {
     if (!a.with_units) return;
     const uint32_t* offB = a.rel[0].off;
     const uint32_t* offP = a.rel[1].off;
-    for (uint32_t p = gtid; p < nb; p += gsz) {
+    for (uint32_t p = p_lo + gtid; p < p_hi; p += gsz) {
         const uint32_t bb = offB[p], be = offB[p + 1], lo = offP[p], hi = offP[p + 1];
         if (be > bb && hi > lo) {
             uint32_t at = a.unit_base[p];
@@ -587,19 +582,29 @@ pp_cursor_kernel(const uint32_t* __restrict__ all_hist, uint32_t n_gpus, uint32_
 //     radix pass + join.  The coarse histograms are all-gathered BEFORE the source pass:
 //     pcp_layout_kernel derives, for chunk c = (destination d, first-pass partition j), where it
 //     lands at d -- first-pass partition j of d starts at sum_{j'<j} C[d][j'], source r writes at
-//     + sum_{s<r} H[s][c] -- and where the source stages it: every chunk gets its count + 1 slots
-//     and starts on the slot whose 16-byte phase equals its destination's, so head tuple, bulk
-//     body and tail tuple line up on both sides.
+//     + sum_{s<r} H[s][c] -- and where the source stages it: every REMOTE chunk gets its count + 1
+//     stage slots and starts on the slot whose 16-byte phase equals its destination's, so head
+//     tuple, bulk body and tail tuple line up on both sides.  The chunks a GPU keeps (d == rank) are
+//     never staged or copied: the source pass stores them straight into this GPU's receive buffer.
+//     The exchange is a STREAM: chunks travel in ascending first-pass partition j on every GPU
+//     (tile_perm), the copy is issued in stages (groups of j), each followed by a flag store into
+//     every peer (pcp_signal_kernel); the receiver waits per stage (pcp_wait_kernel) and runs
+//     histogram + last radix pass + join over the partitions of that stage while the later
+//     stages are still crossing NVLink.
 //     status: [0] abort (a destination would overflow) [1] tuples this GPU receives [2] pieces
+//             [3] a wait timed out
 // ------------------------------------------------------------------------------------------
 constexpr int PCP_MAX_CHUNKS = 1024;
+constexpr int PCP_MAX_STAGES = 64;
 constexpr uint32_t PCP_PIECE = 2048;     // tuples per bulk copy (16 KB), even
 struct PcpTables {                       // device arrays of n1 (+1) entries
-    uint32_t* cur;                       // pass-1 cursors (consumed by the scatter)
-    uint32_t* src_start;                 // first slot of chunk c in the source's stage buffer
+    uint32_t* cur;                       // pass-1 cursors (consumed by the scatter), relative to dig_base[c]
+    tup_t** dig_base;                    // pass-1 output base of chunk c: the stage buffer, or this GPU's receive buffer
+    uint32_t* src_start;                 // remote chunks: first slot of chunk c in the source's stage buffer
     uint32_t* dst_start;                 // first slot of this source's share at the destination
     uint32_t* cnt;                       // tuples of chunk c in this shard
-    uint32_t* piece_prefix;              // [n1 + 1], indexed by POSITION k (chunk tile_perm(k))
+    uint32_t* piece_prefix;              // [n1 + 1], indexed by POSITION k (chunk tile_perm(k)); own chunks: no pieces
+    uint32_t* recv_off;                  // [2^bl + 1] this GPU's receive layout: first-pass partition j starts at recv_off[j]
     uint32_t* status;
 };
 
@@ -610,10 +615,14 @@ __device__ __forceinline__ uint32_t pcp_pieces(uint32_t cnt, uint32_t phase) {
 // one CTA of 1024 threads; thread t owns chunk t (partition order) and position t (copy order)
 __global__ void __launch_bounds__(PCP_MAX_CHUNKS)
 pcp_layout_kernel(const uint32_t* __restrict__ all_hist, uint32_t n_gpus, uint32_t rank, uint32_t b1, uint32_t bl,
-                  uint32_t cap_tuples, uint32_t perm, PcpTables t) {
+                  uint32_t cap_tuples, uint32_t perm, tup_t* stage, tup_t* own, PcpTables t) {
     __shared__ uint32_t s_a[PCP_MAX_CHUNKS], s_ph[PCP_MAX_CHUNKS], s_cn[PCP_MAX_CHUNKS];
     __shared__ uint32_t s_warp[3][PCP_MAX_CHUNKS / 32];
+    __shared__ uint32_t s_over;
     const uint32_t c = threadIdx.x, lane = c & 31u, wid = c >> 5, n1 = 1u << b1;
+    const uint32_t d = c >> bl;
+    const bool mine_stays = (d == rank);
+    if (c == 0) s_over = 0;
     uint32_t tot = 0, pre = 0, mine = 0;
     if (c < n1)
         for (uint32_t s = 0; s < n_gpus; ++s) {
@@ -622,30 +631,38 @@ pcp_layout_kernel(const uint32_t* __restrict__ all_hist, uint32_t n_gpus, uint32
             if (s < rank) pre += h;
             if (s == rank) mine = h;
         }
-    // two block-wide exclusive scans in chunk order: destination totals, source regions (count + 1)
-    uint32_t i0 = warp_incl_scan(tot, lane), i1 = warp_incl_scan(mine + 1u, lane);
+    // two block-wide exclusive scans in chunk order: destination totals, stage regions (count + 1, remote chunks only)
+    const uint32_t region_sz = (c < n1 && !mine_stays) ? mine + 1u : 0u;
+    uint32_t i0 = warp_incl_scan(tot, lane), i1 = warp_incl_scan(region_sz, lane);
     if (lane == 31) { s_warp[0][wid] = i0; s_warp[1][wid] = i1; }
     __syncthreads();
     uint32_t w0 = 0, w1 = 0;
     for (uint32_t w = 0; w < wid; ++w) { w0 += s_warp[0][w]; w1 += s_warp[1][w]; }
-    const uint32_t ex_tot = i0 - tot + w0, region = i1 - (mine + 1u) + w1;
+    const uint32_t ex_tot = i0 - tot + w0, region = i1 - region_sz + w1;
     s_a[c] = ex_tot;
     __syncthreads();
-    const uint32_t d = c >> bl;
-    const uint32_t dbase = s_a[d << bl];                       // first chunk of this destination
+    const uint32_t dbase = s_a[min(d << bl, (uint32_t)PCP_MAX_CHUNKS - 1u)];   // first chunk of this destination
     const uint32_t dst = ex_tot - dbase + pre;
     const uint32_t src = region + ((region ^ dst) & 1u);       // same 16-byte phase as the destination slot
+    const bool last_of_dest = (c < n1) && (((c + 1u) & ((1u << bl) - 1u)) == 0u);
+    uint32_t dtot = 0;
+    if (last_of_dest) {
+        dtot = ex_tot + tot - dbase;
+        // +16: bulk copies and 16-byte loads of the join round partition ends out to tuple pairs
+        if ((unsigned long long)dtot + 16ull > (unsigned long long)cap_tuples) { atomicExch(&t.status[0], 1u); s_over = 1u; }
+    }
+    __syncthreads();
+    const bool over = s_over != 0u;       // some destination overflows: nothing is sent, every receiver sees an empty relation
     if (c < n1) {
-        t.cur[c] = src; t.src_start[c] = src; t.dst_start[c] = dst; t.cnt[c] = mine;
-        const bool last_of_dest = ((c + 1u) & ((1u << bl) - 1u)) == 0u;
-        if (last_of_dest) {
-            const uint32_t dtot = ex_tot + tot - dbase;
-            const bool over = (unsigned long long)dtot + 16ull > (unsigned long long)cap_tuples;
-            if (over) atomicExch(&t.status[0], 1u);
-            if (d == rank) t.status[1] = over ? 0u : dtot;     // nothing will arrive: the receiver sees an empty relation
+        t.cur[c] = mine_stays ? dst : src;
+        t.dig_base[c] = mine_stays ? own : stage;
+        t.src_start[c] = src; t.dst_start[c] = dst; t.cnt[c] = mine;
+        if (mine_stays) {
+            t.recv_off[c & ((1u << bl) - 1u)] = over ? 0u : ex_tot - dbase;
+            if (last_of_dest) { t.recv_off[1u << bl] = over ? 0u : dtot; t.status[1] = over ? 0u : dtot; }
         }
     }
-    s_ph[c] = src & 1u; s_cn[c] = mine;
+    s_ph[c] = src & 1u; s_cn[c] = (c < n1 && !mine_stays) ? mine : 0u;
     __syncthreads();
     // pieces in COPY order: position k takes chunk tile_perm(k)
     const uint32_t ck = tile_perm(c, perm);
@@ -660,17 +677,19 @@ pcp_layout_kernel(const uint32_t* __restrict__ all_hist, uint32_t n_gpus, uint32
 }
 
 struct PcpCopyArgs {
-    const tup_t* stage;                  // first-pass output of this shard
-    tup_t* const* peer_bases;            // [n_gpus] receive buffers (local or mapped over NVLink)
+    const tup_t* stage;                  // first-pass output of this shard (remote chunks)
+    tup_t* const* peer_bases;            // [n_gpus] receive buffers (mapped over NVLink)
     PcpTables t;
     uint32_t b1, bl, perm;
-    uint32_t l2_hint;                    // 1: loads and stores carry an L2 evict-first policy
+    uint32_t pos_lo, pos_hi;             // this launch moves the chunks at copy positions [pos_lo, pos_hi)
 };
 
 // One warp per CTA, NS ring slots of PCP_PIECE tuples.  Lane 0 walks this CTA's pieces (static
 // round robin): it issues the bulk load of piece i and, LAG pieces behind, the bulk store of piece
 // i - LAG, so LAG loads are in flight per CTA and a slot is reloaded only after its previous store
 // has read it (bulk async-group accounting: one group per piece, empty groups included).
+// NS = 4 on every SM, or NS = 12 (10 loads in flight per CTA, 196 KB of shared memory) on a few SMs
+// that then run nothing else, so the radix passes and the join next to it keep the other SMs whole.
 template <int NS>
 __global__ void __launch_bounds__(32)
 pcp_copy_kernel(PcpCopyArgs a) {
@@ -691,11 +710,11 @@ pcp_copy_kernel(PcpCopyArgs a) {
     }
     __syncwarp();
     if (threadIdx.x != 0) return;
-    const uint32_t total = s_prefix[n1];
+    const uint32_t k0 = s_prefix[a.pos_lo], total = s_prefix[min(a.pos_hi, n1)];
     uint32_t issued = 0, stored = 0;
-    for (uint32_t k = blockIdx.x; k < total || stored < issued; k += gridDim.x) {
+    for (uint32_t k = k0 + blockIdx.x; k < total || stored < issued; k += gridDim.x) {
         if (k < total) {
-            uint32_t lo = 0, hi = n1;             // largest position whose prefix is <= k
+            uint32_t lo = a.pos_lo, hi = n1;      // largest position whose prefix is <= k
             while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (s_prefix[m] <= k) lo = m; else hi = m; }
             const uint32_t c = tile_perm(lo, a.perm), slice = k - s_prefix[lo];
             const uint32_t src0 = a.t.src_start[c], dst0 = a.t.dst_start[c], cnt = a.t.cnt[c];
@@ -724,7 +743,41 @@ pcp_copy_kernel(PcpCopyArgs a) {
             ++stored;
         }
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the stores have completed, not just been read
+    __threadfence_system();
+}
+
+// After a copy stage: tell every peer that this source's chunks of the stage have landed.  Runs on the
+// copy's stream, i.e. after the copy kernel (and all its bulk stores) completed.  A flag word holds
+// the epoch (join number) of the last completed stage; flags of one GPU: [relation][stage][source].
+__global__ void pcp_signal_kernel(uint32_t* const* __restrict__ peer_flags, uint32_t n_gpus, uint32_t rank,
+                                  uint32_t slot, uint32_t epoch) {
+    const uint32_t d = threadIdx.x;
+    if (d >= n_gpus) return;
+    __threadfence_system();
+    volatile uint32_t* f = peer_flags[d] + (size_t)slot * n_gpus + rank;
+    *f = epoch;
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Receiver side: spin until every source has signalled `slot` for this epoch (bounded: after
+// timeout_ns the kernel gives up and raises status[3], so a lost peer becomes an error, not a hang).
+__global__ void pcp_wait_kernel(const uint32_t* __restrict__ flags, uint32_t n_gpus, uint32_t rank, uint32_t slot,
+                                uint32_t epoch, unsigned long long timeout_ns, uint32_t* __restrict__ status) {
+    const uint32_t s = threadIdx.x;
+    if (s >= n_gpus || s == rank) return;      // this GPU's own chunks are ordered by the stream (events)
+    const volatile uint32_t* f = flags + (size_t)slot * n_gpus + s;
+    const unsigned long long t0 = global_timer_ns();
+    while ((int32_t)(*f - epoch) < 0) {
+        if (global_timer_ns() - t0 > timeout_ns) { atomicExch(&status[3], 1u); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -794,7 +847,7 @@ scatter_kernel(ScatterArgs a) {
     const uint32_t first_tile = blockIdx.x;
     if (PUSH) {   // (the tile list is already ordered destination-interleaved, see tile_perm)
         if (blockIdx.x >= ntiles_total || *a.abort_flag) return;
-    }
+    } else if (a.abort_flag != nullptr && *a.abort_flag) return;   // sharded source pass: a destination would overflow
     for (uint32_t tile_id = first_tile; tile_id < ntiles_total; tile_id += gridDim.x) {
     // ---- which slots does this tile cover ----
     uint32_t a0, lo, hi, cbase;

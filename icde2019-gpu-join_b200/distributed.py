@@ -84,17 +84,30 @@ def pcp_plan_bits(n_gpus: int, local_bits: int, pass1_bits: int = 0):
 def pcp_layout(all_hist: np.ndarray, rank: int, source_local_bits: int):
     """numpy model of pcp_layout_kernel: all_hist[s][c] = tuples of source s in chunk c = (dest <<
     bl) | j (j = first-pass partition at the destination).  Returns (dst_start[c] of `rank`'s
-    shares, src_start[c] in `rank`'s stage buffer, tuples every destination receives)."""
+    shares, src_start[c] in `rank`'s stage buffer -- remote chunks only: the chunks a GPU keeps are
+    written straight into its receive buffer, there src_start[c] = dst_start[c] --, tuples every
+    destination receives)."""
     H = np.asarray(all_hist).astype(np.int64)
     G, n1 = H.shape
     bl = source_local_bits
     tot = H.sum(axis=0)
     ex = np.concatenate(([0], np.cumsum(tot)[:-1]))
-    dbase = ex[(np.arange(n1) >> bl) << bl]
+    dest = np.arange(n1) >> bl
+    dbase = ex[dest << bl]
     dst = ex - dbase + H[:rank].sum(axis=0)
-    region = np.concatenate(([0], np.cumsum(H[rank] + 1)[:-1]))
-    src = region + ((region ^ dst) & 1)
+    stays = dest == rank
+    region_sz = np.where(stays, 0, H[rank] + 1)
+    region = np.concatenate(([0], np.cumsum(region_sz)[:-1]))
+    src = np.where(stays, dst, region + ((region ^ dst) & 1))
     return dst, src, tot.reshape(-1, 1 << bl).sum(axis=1)
+
+
+def pcp_stage_positions(n_stages: int, gpu_bits: int, source_local_bits: int):
+    """Copy positions [lo, hi) of every stage (mirror of gj_pcp_copy): positions are (first-pass
+    partition j, destination d) with d fastest; stage k covers partitions [k nj / K, (k+1) nj / K)."""
+    nj = 1 << source_local_bits
+    K = min(n_stages, nj)
+    return [(((k * nj) // K) << gpu_bits, (((k + 1) * nj) // K) << gpu_bits) for k in range(K)]
 
 
 @dataclass
@@ -296,14 +309,24 @@ class GpuOps:
         ph = dict(ph, shuffle_scatter_ms=ph["push_R_ms"] + ph["push_S_ms"], pass1_bits=b1, pass2_bits=b2, radix_bits=B)
         return m, c, (n_r, n_s), ph
 
-    def pcp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob):
-        """Mode "pcp": coarse histograms -> all-gather -> first radix pass at the source -> TMA bulk
-        copies of whole first-pass partitions -> last radix pass + join at the receiver.  R's copy
-        runs under S's first pass, S's copy under R's last pass."""
+    def pcp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob, flags=None, stages=(2, 4)):
+        """Mode "pcp": coarse histograms -> all-gather -> first radix pass at the source (own chunks
+        straight into the receive buffer) -> staged TMA bulk copies of whole first-pass partitions, a
+        flag store into every peer after each stage -> per stage at the receiver: wait, histogram, last
+        radix pass and (probing relation) join.  Four streams: source side and receiver side of each
+        relation; all source-side work is enqueued before any receiver-side wait.  No collective
+        after the histogram all-gathers: arrival is signalled through the peers' flag words."""
         import os
         torch, eng = self.torch, self.engine
-        sR, sS = self.stream_shuffle, self.stream_local           # S on the high-priority stream
-        streams = (sR, sS)
+        if not hasattr(self, "_pcp_streams"):
+            # receiver side of the second (probing) relation on the high-priority stream: it ends the step
+            self._pcp_streams = (self.stream_shuffle, torch.cuda.Stream(self.device),
+                                 self.stream_local, torch.cuda.Stream(self.device, priority=-1))
+        first = 1 if n_glob[0] > n_glob[1] else 0           # the building (smaller) relation travels first
+        order = (first, 1 - first)
+        src = {order[0]: self._pcp_streams[0], order[1]: self._pcp_streams[2]}
+        rcv = {order[0]: self._pcp_streams[1], order[1]: self._pcp_streams[3]}
+        nst = {order[0]: stages[0], order[1]: stages[1]}
         trace = [] if os.environ.get("GJ_TRACE") else None        # optional GPU timeline (ms since the start mark)
 
         def mark(name, stream):
@@ -311,50 +334,47 @@ class GpuOps:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record(stream)
                 trace.append((name, e))
-        eng.pcp_begin(n_glob[0], n_glob[1], G, rank, B, sR)
+        cur = torch.cuda.current_stream(self.device)
+        for s in self._pcp_streams:
+            s.wait_stream(cur)
+        eng.pcp_begin(n_glob[0], n_glob[1], G, rank, B, src[first])
         g, bl, _ = eng.pcp_plan()
         n1 = 1 << (g + bl)                                        # chunks = first-pass partitions of all destinations
         if getattr(self, "_pcp_key", None) != (G, n1):
             self._pcp_hist = [torch.empty(n1, dtype=torch.int32, device=self.dev) for _ in range(2)]
             self._pcp_all = [torch.empty(G * n1, dtype=torch.int32, device=self.dev) for _ in range(2)]
-            self._pcp_tok = [torch.zeros(1, dtype=torch.int32, device=self.dev) for _ in range(2)]
             self._pcp_key = (G, n1)
-        cur = torch.cuda.current_stream(self.device)
-        for s in streams:
-            s.wait_stream(cur)
         caps = (self.cap_R, self.cap_S)
-        mark("start", sR)
         names = ("R", "S")
-        for which, (k, p) in enumerate(rels):
-            eng.pcp_hist(which, k, self._pcp_hist[which], streams[which])
-            with torch.cuda.stream(streams[which]):
-                dist.all_gather_into_tensor(self._pcp_all[which], self._pcp_hist[which], group=group)
-            mark(f"{names[which]} histograms gathered", streams[which])
+        mark("start", src[first])
+        for w in order:
+            k, p = rels[w]
+            eng.pcp_hist(w, k, self._pcp_hist[w], src[w])
+            with torch.cuda.stream(src[w]):
+                dist.all_gather_into_tensor(self._pcp_all[w], self._pcp_hist[w], group=group)
+            mark(f"{names[w]} histograms gathered", src[w])
         ev = {}
-        for which, (k, p) in enumerate(rels):
-            s = streams[which]
-            if which == 1:
-                s.wait_event(ev["part0"])                         # S's first pass runs under R's copy ...
-            eng.pcp_part(which, k, p, self._pcp_all[which], caps[which], s)
-            ev[f"part{which}"] = torch.cuda.Event(); ev[f"part{which}"].record(s)
-            mark(f"{names[which]} source pass done", s)
-            if which == 1:
-                s.wait_event(ev["copy0"])                         # ... and one relation crosses NVLink at a time
-            eng.pcp_copy(which, peers[which], s)
-            ev[f"copy{which}"] = torch.cuda.Event(); ev[f"copy{which}"].record(s)
-            mark(f"{names[which]} copy kernel done (local)", s)
-            with torch.cuda.stream(s):
-                dist.all_reduce(self._pcp_tok[which], group=group)   # every rank's copies have landed
-            mark(f"{names[which]} landed everywhere", s)
-        for which in range(2):
-            eng.pcp_recv(which, own_ptrs[which], caps[which], streams[which])
-            mark(f"{names[which]} receiver pass done", streams[which])
-        sS.wait_stream(sR)
-        eng.pcp_join(caps[0], caps[1], sS)
-        mark("joined", sS)
+        for i, w in enumerate(order):
+            k, p = rels[w]
+            s = src[w]
+            if i == 1:
+                s.wait_event(ev["part"])                          # the second source pass runs under the first copy ...
+            eng.pcp_part(w, k, p, self._pcp_all[w], own_ptrs[w], caps[w], s)
+            ev["part"] = torch.cuda.Event(); ev["part"].record(s)
+            mark(f"{names[w]} source pass done", s)
+            if i == 1:
+                s.wait_event(ev["copy"])                          # ... and one relation crosses NVLink at a time
+            eng.pcp_copy(w, peers[w], flags, nst[w], s)
+            ev["copy"] = torch.cuda.Event(); ev["copy"].record(s)
+            mark(f"{names[w]} copied (local kernels done)", s)
+        for w in order:                                           # receiver side: only now, behind all source-side work
+            eng.pcp_recv(w, own_ptrs[w], flags[rank], caps[w], rcv[w])
+            mark(f"{names[w]} received" + (" and joined" if w != first else ""), rcv[w])
         m, c, n_r, n_s, ph, bits = eng.pcp_finish()
-        sR.synchronize()
-        ph = dict(ph, shuffle_scatter_ms=ph["copy_R_ms"] + ph["copy_S_ms"], radix_bits=B, pass1_bits=bits[0] + bits[1], pass2_bits=bits[2])
+        for s in self._pcp_streams:
+            s.synchronize()
+        ph = dict(ph, shuffle_scatter_ms=ph["copy_R_ms"] + ph["copy_S_ms"], radix_bits=B, pass1_bits=bits[0] + bits[1],
+                  pass2_bits=bits[2], stages=[nst[0], nst[1]])
         if trace is not None:
             torch.cuda.synchronize(self.device)
             ph["trace_ms"] = {n: round(trace[0][1].elapsed_time(e), 3) for n, e in trace[1:]}
@@ -387,7 +407,7 @@ class ShardedJoin:
     with its local shard (device int32 columns) and all ranks get the global result."""
 
     def __init__(self, max_local_R: int, max_local_S: int, device: int | None = None, group=None,
-                 mode: str = "auto", ops=None, part_target: int = 4096, overlap: bool = True):
+                 mode: str = "auto", ops=None, part_target: int = 4096, overlap: bool = True, pcp_stages=(2, 4)):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -400,6 +420,7 @@ class ShardedJoin:
             mode = "pcp"       # partitions cross NVLink, at the bulk-copy rate (684 GB/s out per GPU at 8 GPUs)
         self.mode = mode
         self.overlap = overlap
+        self.pcp_stages = tuple(pcp_stages)     # copy / receive stages of the building and of the probing relation
         self.part_target = part_target
         self.ops = ops if ops is not None else GpuOps(max_local_R, max_local_S, device,
                                                       with_send_buffers=(mode in ("nccl", "dma")))
@@ -410,7 +431,8 @@ class ShardedJoin:
             if ops is None:
                 self._setup_peers()
             else:                      # test stand-in: no device buffers to map
-                self._peers = [[0] * self.world, [0] * self.world]
+                self._peers = [[0] * self.world, [0] * self.world, [0] * self.world]
+                self._own = [0, 0, 0]
                 self._opened = []
         elif mode != "nccl":
             raise ValueError("mode must be 'auto', 'nccl', 'p2p', 'dma', 'pp' or 'pcp'")
@@ -426,19 +448,23 @@ class ShardedJoin:
         # receive buffers must be plain cudaMalloc allocations to be exportable
         self._own = []
         handles = []
-        for which, cap in enumerate((ops.cap_R, ops.cap_S)):
+        flag_bytes = 2 * 64 * self.world * 4     # pcp stage flags: [relation][stage][source] uint32
+        for which, nbytes in enumerate(((ops.cap_R + 16) * 8, (ops.cap_S + 16) * 8, flag_bytes)):
             p = C.c_void_p()
-            _check(L.gj_malloc_device(C.byref(p), cap * 8))
+            _check(L.gj_malloc_device(C.byref(p), nbytes))
+            if which == 2:
+                L.gj_memset_device.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+                _check(L.gj_memset_device(p, 0, nbytes))
             h = C.create_string_buffer(64)
             _check(L.gj_ipc_export(p, h))
             self._own.append(p.value)
             handles.append(h.raw)
         gathered = [None] * self.world
         self.dist.all_gather_object(gathered, handles, group=self.group)
-        self._peers = [[0] * self.world, [0] * self.world]
+        self._peers = [[0] * self.world, [0] * self.world, [0] * self.world]    # R buffers, S buffers, flag buffers
         self._opened = []
         for r in range(self.world):
-            for which in range(2):
+            for which in range(3):
                 if r == self.rank:
                     self._peers[which][r] = self._own[which]
                 else:
@@ -480,8 +506,11 @@ class ShardedJoin:
         rels = ((Rk, Rp), (Sk, Sp))
         local_n = [0, 0]
         if self.mode in ("pp", "pcp"):
-            run = {"pp": ops.pp_join, "pcp": ops.pcp_join}[self.mode]
-            m, c, local_n, tm = run(dist, self.group, rank, rels, G, B, self._peers, self._own, (n_R_global, n_S_global))
+            if self.mode == "pp":
+                m, c, local_n, tm = ops.pp_join(dist, self.group, rank, rels, G, B, self._peers, self._own, (n_R_global, n_S_global))
+            else:
+                m, c, local_n, tm = ops.pcp_join(dist, self.group, rank, rels, G, B, self._peers, self._own, (n_R_global, n_S_global),
+                                                 flags=self._peers[2], stages=self.pcp_stages)
             lap()
         elif self.mode == "nccl":
             import torch

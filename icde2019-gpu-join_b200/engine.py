@@ -23,10 +23,10 @@ C_ABI_SYMBOLS = [
     "gj_join_materialize", "gj_join_aggregate_late", "gj_join_aggregate_nopart", "gj_join_aggregate_perfect", "gj_join_aggregate_stream_host", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
     "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_stage_pass_ms", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
-    "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv", "gj_pcp_join",
+    "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv",
     "gj_pcp_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
-    "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_device_synchronize", "gj_flush_l2",
+    "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_memset_device", "gj_device_synchronize", "gj_flush_l2",
     "gj_kernel_launch_count",
 ]
 
@@ -117,10 +117,9 @@ def lib() -> C.CDLL:
     L.gj_pcp_begin.argtypes = [vp, u64, u64, u32, u32, u32, vp]
     L.gj_pcp_plan.argtypes = [vp, C.POINTER(u32)]
     L.gj_pcp_hist.argtypes = [vp, C.c_int, i32p, u64, vp, vp]
-    L.gj_pcp_part.argtypes = [vp, C.c_int, i32p, i32p, vp, u64, vp]
-    L.gj_pcp_copy.argtypes = [vp, C.c_int, C.POINTER(vp), vp]
-    L.gj_pcp_recv.argtypes = [vp, C.c_int, vp, u64, vp]
-    L.gj_pcp_join.argtypes = [vp, u64, u64, vp]
+    L.gj_pcp_part.argtypes = [vp, C.c_int, i32p, i32p, vp, vp, u64, vp]
+    L.gj_pcp_copy.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), u32, vp]
+    L.gj_pcp_recv.argtypes = [vp, C.c_int, vp, vp, u64, vp]
     L.gj_pcp_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(u32)]
     L.gj_generate_unique.argtypes = [vp, i32p, i32p, u64, u64, u64, u32, u32]
     L.gj_bijection.argtypes = [u64, u64, u32]
@@ -134,6 +133,7 @@ def lib() -> C.CDLL:
     L.gj_free_pinned.argtypes = [vp]
     L.gj_memcpy_h2d.argtypes = [vp, vp, u64]
     L.gj_memcpy_d2h.argtypes = [vp, vp, u64]
+    L.gj_memset_device.argtypes = [vp, C.c_int, u64]
     L.gj_flush_l2.argtypes = [vp]
     L.gj_kernel_launch_count.restype = u64
     _lib = L
@@ -460,27 +460,25 @@ class JoinEngine:
         n = keys.numel()
         _check(self._L.gj_pcp_hist(self._ctx, which, _dev_ptr(keys, n, "keys"), n, C.c_void_p(coarse_hist.data_ptr()), self._sptr(stream)))
 
-    def pcp_part(self, which: int, keys, pays, all_hist, cap_tuples: int, stream=None):
+    def pcp_part(self, which: int, keys, pays, all_hist, own_ptr: int, cap_tuples: int, stream=None):
         n = keys.numel()
         _check(self._L.gj_pcp_part(self._ctx, which, _dev_ptr(keys, n, "keys"), _dev_ptr(pays, n, "pays"),
-                                   C.c_void_p(all_hist.data_ptr()), cap_tuples, self._sptr(stream)))
+                                   C.c_void_p(all_hist.data_ptr()), C.c_void_p(own_ptr), cap_tuples, self._sptr(stream)))
 
-    def pcp_copy(self, which: int, peer_ptrs, stream=None):
+    def pcp_copy(self, which: int, peer_ptrs, peer_flag_ptrs, n_stages: int = 1, stream=None):
         bases = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
-        _check(self._L.gj_pcp_copy(self._ctx, which, bases, self._sptr(stream)))
+        flags = (C.c_void_p * len(peer_flag_ptrs))(*[C.c_void_p(int(p)) for p in peer_flag_ptrs])
+        _check(self._L.gj_pcp_copy(self._ctx, which, bases, flags, n_stages, self._sptr(stream)))
 
-    def pcp_recv(self, which: int, own_ptr: int, cap_tuples: int, stream=None):
-        _check(self._L.gj_pcp_recv(self._ctx, which, C.c_void_p(own_ptr), cap_tuples, self._sptr(stream)))
-
-    def pcp_join(self, cap_R: int, cap_S: int, stream=None):
-        _check(self._L.gj_pcp_join(self._ctx, cap_R, cap_S, self._sptr(stream)))
+    def pcp_recv(self, which: int, own_ptr: int, own_flags_ptr: int, cap_tuples: int, stream=None):
+        _check(self._L.gj_pcp_recv(self._ctx, which, C.c_void_p(own_ptr), C.c_void_p(own_flags_ptr), cap_tuples, self._sptr(stream)))
 
     def pcp_finish(self, phases: bool = True):
         """Returns (matches, checksum, tuples received of R, of S, phase_ms dict, (gpu bits, source bits, receiver bits))."""
         m, c, a, b = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         ph, bits = (C.c_float * 7)(), (C.c_uint32 * 3)()
         _check(self._L.gj_pcp_finish(self._ctx, C.byref(m), C.byref(c), C.byref(a), C.byref(b), ph if phases else None, bits))
-        names = ("part_R_ms", "copy_R_ms", "recv_R_ms", "part_S_ms", "copy_S_ms", "recv_S_ms", "join_ms")
+        names = ("part_R_ms", "copy_R_ms", "recv_R_ms", "part_S_ms", "copy_S_ms", "recv_S_ms", "tail_ms")
         return (int(m.value), int(c.value), int(a.value), int(b.value), dict(zip(names, (float(x) for x in ph))),
                 tuple(int(x) for x in bits))
 

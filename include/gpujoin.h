@@ -82,6 +82,7 @@ int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
  *   "pp_out", "pp_tile16k"  sharded pipeline, see gj_pp_begin
  *   "pcp_ring"     1: the pcp copy kernel uses a 12-slot ring (10 bulk loads in flight per CTA) -- for running it on
  *                  few SMs ("shuffle_grid" = 16..32) so the passes next to it keep their occupancy (default 0)
+ *   "pcp_timeout_ms" bound of the receiver's wait for a peer's stage flag (default 5000)
  *   "nopart_max"   gj_join_aggregate takes the non-partitioned path (gj_join_aggregate_nopart) when the
  *                  smaller relation has at most this many tuples (default 0 = never; to be set from the
  *                  measured crossover, tools/nopart_crossover.py) */
@@ -258,16 +259,32 @@ int gj_pp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n
                  uint64_t* n_local_S, float* phase_ms);
 int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bits);
 
-/* ---- sharded "partition, copy, partition" pipeline (multi-GPU, experimental) -------------------
+/* ---- sharded "partition, copy, partition" pipeline (multi-GPU, the default exchange) ---------
  * NVLink moves long runs far better than short ones, so here only WHOLE first-pass partitions
- * cross it.  Per relation: gj_pcp_hist = this shard's histogram on [gpu bits | top local bits]
- * (2^(g + bl) uint32 into d_coarse_hist); the caller all-gathers those into d_all_hist
- * ([n_gpus][2^(g + bl)]); gj_pcp_part = layout + first radix pass into the context's stage buffer;
- * gj_pcp_copy = a TMA bulk-copy kernel moves every chunk to its slot in the destination's receive
- * buffer (peer_bases[g], 16-byte aligned, cap_tuples + 16 tuples); after the caller's "all copies
- * have landed" point gj_pcp_recv runs histogram + LAST radix pass over d_own (this GPU's receive
- * buffer); gj_pcp_join + gj_pcp_finish as for gj_pp_*.  phase_ms[7] = part R, copy R, recv R,
- * part S, copy S, recv S, join; plan_bits[3] = gpu bits, source-side local bits, receiver-side bits.
+ * cross it, and they cross it as a STREAM: in ascending first-pass partition on every GPU, in
+ * n_stages groups, each followed by a flag store into every peer; the receiver partitions and joins a
+ * group while the later ones are still in flight.  The relation that builds (the globally smaller one,
+ * R when equal) goes first.  Per relation (`which` 0 = R, 1 = S), each on streams of the caller's:
+ *   gj_pcp_hist  this shard's histogram on [gpu bits | top local bits] (2^(g + bl) uint32 into
+ *                d_coarse_hist); the caller all-gathers those into d_all_hist ([n_gpus][2^(g + bl)]);
+ *   gj_pcp_part  layout + first radix pass: remote chunks into the context's stage buffer, this GPU's
+ *                own chunks straight into its receive buffer d_own (never copied);
+ *   gj_pcp_copy  n_stages x (TMA bulk-copy kernel: every remote chunk of the group to its slot in the
+ *                destination's receive buffer peer_bases[g] (16-byte aligned, cap_tuples + 16 tuples);
+ *                then this source's flag word in every peer's flag buffer peer_flags[g]);
+ *   gj_pcp_recv  per stage: wait until every source's flag arrived (bounded by option
+ *                "pcp_timeout_ms", default 5000: then GJ_ERR_STATE from gj_pcp_finish, never a hang),
+ *                histogram + LAST radix pass over the group in d_own; for the probing relation also the
+ *                join of the group.  Call it on a stream other than gj_pcp_copy's so that receiving
+ *                overlaps this GPU's own sending; the building relation must be received first.
+ *   gj_pcp_finish synchronises; local aggregate, tuples received, phase_ms[7] = part R, copy R,
+ *                recv R, part S, copy S, recv S, tail (last byte of the probing relation landed ->
+ *                last join done); plan_bits[3] = gpu bits, source-side local bits, receiver-side bits.
+ * Flag buffers: 2 * 64 * n_gpus uint32 per GPU, zeroed once (gj_malloc_device + gj_memset_device), laid out
+ * [relation][stage][source]; a flag holds the join number (epoch) of the last completed stage, so it
+ * never needs resetting.  Options: "shuffle_grid" = CTAs of the copy kernel (0 = one per SM), "pcp_ring"
+ * = 1: 12-slot ring (10 bulk loads in flight per CTA) for running the copy on few SMs, which then host
+ * nothing else -- the kernels next to it size their grids to the remaining SMs.
  * n + 2^(g + bl) must not exceed the context capacity (one spare stage slot per chunk). */
 int gj_pcp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
                  uint32_t local_bits, void* cuda_stream);
@@ -275,12 +292,14 @@ int gj_pcp_plan(gj_ctx* ctx, uint32_t plan_bits[3]);
 int gj_pcp_hist(gj_ctx* ctx, int which, const int32_t* d_keys, uint64_t n, uint32_t* d_coarse_hist,
                 void* cuda_stream);
 int gj_pcp_part(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays,
-                const uint32_t* d_all_hist, uint64_t cap_tuples, void* cuda_stream);
-int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* cuda_stream);
-int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, uint64_t cap_tuples, void* cuda_stream);
-int gj_pcp_join(gj_ctx* ctx, uint64_t cap_R, uint64_t cap_S, void* cuda_stream);
+                const uint32_t* d_all_hist, void* d_own, uint64_t cap_tuples, void* cuda_stream);
+int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* const* peer_flags, uint32_t n_stages,
+                void* cuda_stream);
+int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, const void* d_flags, uint64_t cap_tuples,
+                void* cuda_stream);
 int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
                   uint64_t* n_local_S, float* phase_ms, uint32_t* plan_bits);
+
 /* CUDA IPC plumbing for the peer-store variant when every GPU is driven by its own process:
  * export a gj_malloc_device allocation as a 64-byte handle, open a peer's handle (peer access is
  * enabled lazily), close it again. */
@@ -311,6 +330,7 @@ int gj_malloc_pinned(void** p, uint64_t bytes);
 int gj_free_pinned(void* p);
 int gj_memcpy_h2d(void* d, const void* h, uint64_t bytes);
 int gj_memcpy_d2h(void* h, const void* d, uint64_t bytes);
+int gj_memset_device(void* d, int value, uint64_t bytes);
 int gj_device_synchronize(void);
 /* L2 flush helper for benchmarks: writes a scratch buffer larger than L2. */
 int gj_flush_l2(gj_ctx* ctx);

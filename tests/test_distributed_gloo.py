@@ -98,7 +98,7 @@ class NumpyOps:
         res = oracle.join_check(cols[0][0], cols[0][1], cols[1][0], cols[1][1], 1)
         return res.matches, res.checksum, local_n, {}
 
-    def pcp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob):
+    def pcp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob, flags=None, stages=(2, 4)):
         """Mode "pcp" without a GPU: coarse histograms with numpy, the real all-gather, the layout of
         distributed.pcp_layout (numpy model of pcp_layout_kernel), the chunk copies emulated by an
         all-to-all of (slot, tuple) pairs.  The receiver checks that the slots tile [0, total) exactly,
@@ -253,7 +253,10 @@ def test_pcp_layout_and_plan(gj):
             at += H[r, c]
     for r in range(G):
         dst, src, tots = d.pcp_layout(H, r, bl)
-        assert np.all(src[1:] >= (src + H[r])[:-1]) and src[-1] + H[r, -1] <= H[r].sum() + (1 << (g + bl))
+        remote = (np.arange(1 << (g + bl)) >> bl) != r      # the chunks a GPU keeps are never staged
+        rs, rc = src[remote], H[r][remote]
+        assert np.all(rs[1:] >= (rs + rc)[:-1]) and rs[-1] + rc[-1] <= rc.sum() + remote.sum()
+        assert np.array_equal(src[~remote], dst[~remote])
         assert np.array_equal(tots, tot.reshape(G, -1).sum(axis=1))
     for G2 in (2, 4, 8, 16, 64):
         for B in range(1, 17):
@@ -265,6 +268,37 @@ def test_pcp_layout_and_plan(gj):
                 gg, b_l, b2 = d.pcp_plan_bits(G2, B, p1)
                 assert gg + b_l <= 10 and 0 <= b_l <= 8 and b_l <= B - 1 and b2 == B - b_l and 1 <= b2 <= 10, (G2, B, p1)
     assert d.pcp_plan_bits(8, 15) == (3, 6, 9) and d.pcp_plan_bits(2, 15) == (1, 7, 8) and d.pcp_plan_bits(8, 16) == (3, 7, 9)
+
+
+def test_pcp_stage_positions_cover_every_chunk_once(gj):
+    """Staged copy: the position ranges of the stages tile [0, 2^(g+bl)) in order, every stage holds whole
+    first-pass partitions for all destinations, more stages than partitions collapse; and the copy kernel's
+    piece lookup (binary search from the stage's first position, own chunks have no pieces) visits exactly
+    the remote chunks of the stage."""
+    d = gj.distributed
+    for g, bl, K in ((1, 7, 4), (3, 6, 5), (3, 6, 64), (3, 6, 200), (2, 0, 3), (3, 7, 1)):
+        pos = d.pcp_stage_positions(K, g, bl)
+        assert len(pos) == min(K, 1 << bl) and pos[0][0] == 0 and pos[-1][1] == 1 << (g + bl)
+        assert all(a[1] == b[0] for a, b in zip(pos, pos[1:])) and all(lo < hi and lo % (1 << g) == 0 for lo, hi in pos)
+    rng = np.random.default_rng(3)
+    g, bl, rank = 2, 3, 1
+    n1 = 1 << (g + bl)
+    perm = lambda k: ((k & ((1 << g) - 1)) << bl) | (k >> g)          # tile_perm: position -> chunk  # noqa: E731
+    pieces = np.array([0 if (perm(k) >> bl) == rank else int(rng.integers(0, 4)) for k in range(n1)])
+    prefix = np.concatenate(([0], np.cumsum(pieces)))
+    seen = []
+    for lo, hi in d.pcp_stage_positions(3, g, bl):
+        for k in range(int(prefix[lo]), int(prefix[hi])):
+            a, b = lo, n1
+            while b - a > 1:
+                m = (a + b) // 2
+                if prefix[m] <= k:
+                    a = m
+                else:
+                    b = m
+            assert lo <= a < hi and pieces[a] > 0 and (perm(a) >> bl) != rank
+            seen.append((a, k - int(prefix[a])))
+    assert sorted(seen) == [(k, s) for k in range(n1) for s in range(pieces[k])]
 
 
 def test_pcp_copy_piece_arithmetic_model():

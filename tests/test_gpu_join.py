@@ -535,9 +535,10 @@ def test_pp_destination_overflow_is_reported(gj, orc, torch_cuda):
 
 
 # ------------------------------------------------------------------------------- sharded "partition, copy, partition"
-def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, opts=None, check_layout=True):
-    """gj_pcp_* with G virtual ranks on ONE GPU (one engine context per rank, every 'peer' buffer
-    local; the all-gather is a torch.stack)."""
+def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, opts=None, check_layout=True, stages=(1, 1)):
+    """gj_pcp_* with G virtual ranks on ONE GPU (one engine context per rank, every 'peer' buffer and
+    flag word local; the all-gather is a torch.stack).  stages = copy / receive stages of the building
+    and of the probing relation."""
     rels = [(Rk, Rp), (Sk, Sp)]
     n = [len(Rk), len(Sk)]
     if splits is None:
@@ -552,8 +553,11 @@ def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, o
     engs = [gj.JoinEngine(mx[0], mx[1], 0, **(opts or {})) for _ in range(G)]
     try:
         own = [[torch.zeros(caps[w] + 16, dtype=torch.int64, device="cuda") for _ in range(G)] for w in range(2)]
+        flags = [torch.zeros(2 * 64 * G, dtype=torch.int32, device="cuda") for _ in range(G)]
         cols = [[dev(torch, rels[w][0][splits[w][r]:splits[w][r + 1]], rels[w][1][splits[w][r]:splits[w][r + 1]])
                  for r in range(G)] for w in range(2)]
+        order = (1, 0) if n[0] > n[1] else (0, 1)          # the building (smaller) relation travels first
+        nst = {order[0]: stages[0], order[1]: stages[1]}
         torch.cuda.synchronize()
         for r in range(G):
             engs[r].pcp_begin(n[0], n[1], G, r, B)
@@ -572,9 +576,9 @@ def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, o
                 k = rels[w][0][splits[w][r]:splits[w][r + 1]].view(np.uint32)
                 assert np.array_equal(hist[w][r].cpu().numpy(), np.bincount((k >> (B - bl)) & (n1 - 1), minlength=n1))
         for r in range(G):
-            for w in range(2):
-                engs[r].pcp_part(w, cols[w][r][0], cols[w][r][1], allh[w], caps[w])
-                engs[r].pcp_copy(w, [t.data_ptr() for t in own[w]])
+            for w in order:
+                engs[r].pcp_part(w, cols[w][r][0], cols[w][r][1], allh[w], own[w][r].data_ptr(), caps[w])
+                engs[r].pcp_copy(w, [t.data_ptr() for t in own[w]], [f.data_ptr() for f in flags], nst[w])
         torch.cuda.synchronize()
         # every receive buffer is first-pass partitioned: partition j of destination d holds exactly the
         # tuples with (key >> (B - bl)) & (2^(g+bl) - 1) == (d << bl) | j, nothing beyond the total
@@ -600,9 +604,8 @@ def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, o
         m = c = 0
         got_n = [0, 0]
         for r in range(G):
-            for w in range(2):
-                engs[r].pcp_recv(w, own[w][r].data_ptr(), caps[w])
-            engs[r].pcp_join(caps[0], caps[1])
+            for w in order:
+                engs[r].pcp_recv(w, own[w][r].data_ptr(), flags[r].data_ptr(), caps[w])
             mm, cc, a, b, ph, bits = engs[r].pcp_finish()
             m += mm
             c = (c + cc) % 2**64
@@ -633,8 +636,14 @@ def test_pcp_virtual_shards(gj, orc, torch_cuda, G, B, p1):
         if G > 2:
             cuts[1] = cuts[0]                   # an empty shard
         splits.append(np.concatenate(([0], cuts, [n])).astype(np.int64))
-    m, c, bits = _pcp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, splits=splits, opts={"pass1_bits": p1} if p1 else None)
+    stages = [(1, 1), (2, 4), (3, 5), (64, 64), (1, 7)][(G + B + p1) % 5]
+    m, c, bits = _pcp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, splits=splits, opts={"pass1_bits": p1} if p1 else None,
+                              stages=stages)
     assert (m, c) == (want.matches, want.checksum)
+    # the larger relation first in the argument list: the engine builds on (and ships first) the smaller one
+    m2, c2, _ = _pcp_virtual(gj, orc, torch_cuda, G, B, Sk, Sp, Rk, Rp, splits=splits[::-1], opts={"pass1_bits": p1} if p1 else None,
+                             stages=stages, check_layout=False)
+    assert (m2, c2) == (want.matches, want.checksum)
     g = G.bit_length() - 1
     assert bits[0] == g and bits[0] + bits[1] <= 10 and bits[2] <= 10 and bits[1] <= 8
     if p1:
@@ -650,7 +659,7 @@ def test_pcp_skew_tiny_and_overflow(gj, orc, torch_cuda):
     rng.shuffle(Sk)
     Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
     want = orc.join_check(Rk, Rp, Sk, Sp)
-    assert _pcp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, slack=1.2)[:2] == (want.matches, want.checksum)
+    assert _pcp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, slack=1.2, stages=(2, 4))[:2] == (want.matches, want.checksum)
     # a handful of tuples: most chunks empty, some with a single tuple
     tk = np.array([5, 5, 7, 300, -1, 1 << 20], dtype=np.int32)
     tp = np.arange(6, dtype=np.int32) + 1
