@@ -102,16 +102,17 @@ static const PPCfg kPPPushBig[2][3] = {
       { 1024, 16, 1, 512, scatter_kernel<1024, 16, 1, 1, false, 1, false, 512, true> },
       { 1024, 16, 1, 1024, scatter_kernel<1024, 16, 1, 1, false, 1, false, 1024, true> } },
 };
-// pcp: last radix pass at the receiver (packed input, tiles from plan_kernel, TMA output)
+// pcp: last radix pass at the receiver (packed input, tiles from plan_kernel, TMA output); PERSISTENT grids: the
+// number of tiles of a stage is known on the device only, and the grid is sized to the SMs the copy kernel leaves
 static const PPCfg kPcpLast[4] = {
-    { 256, 16, 1, 256, scatter_kernel<256, 16, 1, 1, false, 4> },                      // <= 7 bits (tile 4096, as scatter_cfg2)
-    { 512, 16, 1, 256, scatter_kernel<512, 16, 1, 1, false, 2> },                      // 8 bits
-    { 512, 16, 1, 512, scatter_kernel<512, 16, 1, 1, false, 2, false, 512> },          // 9 bits
-    { 1024, 8, 1, 1024, scatter_kernel<1024, 8, 1, 1, false, 1, false, 1024> },        // 10 bits
+    { 256, 16, 1, 256, scatter_kernel<256, 16, 1, 1, false, 4, true> },                      // <= 7 bits (tile 4096, as scatter_cfg2)
+    { 512, 16, 1, 256, scatter_kernel<512, 16, 1, 1, false, 2, true> },                      // 8 bits
+    { 512, 16, 1, 512, scatter_kernel<512, 16, 1, 1, false, 2, true, 512> },                 // 9 bits
+    { 1024, 8, 1, 1024, scatter_kernel<1024, 8, 1, 1, false, 1, true, 1024> },               // 10 bits
 };
 constexpr int PCP_NS = 4;        // ring slots of the copy kernel (2 loads in flight per CTA)
 constexpr int PCP_NS_DEEP = 12;  // deep ring (10 loads in flight per CTA): for running the copy on a FEW SMs only, so
-                                 // that the radix passes next to it keep their full occupancy (option "pcp_ring")
+                                 // that the radix passes next to it keep their full occupancy (option "pcp_copy_ctas")
 static size_t pcp_copy_smem(int ns = PCP_NS) { return (size_t)ns * PCP_PIECE * sizeof(tup_t) + (PCP_MAX_CHUNKS + 4) * sizeof(uint32_t); }
 constexpr uint32_t PP_MAX_PASS_BITS = 10;
 constexpr uint32_t PP_MAX_BITS = 2 * PP_MAX_PASS_BITS;
@@ -254,7 +255,7 @@ struct gj_ctx {
     // options
     int64_t opt_radix_bits = 0, opt_pass1_bits = 0, opt_scatter_cfg1 = 255, opt_scatter_cfg2 = 255,
             opt_join_cfg = 0, opt_unit = 0, opt_gpu_bits = 0, opt_part_target = 4096,
-            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_nopart_max = 0, opt_pcp_ring = 0, opt_pcp_timeout_ms = 5000;
+            opt_join_grid = 0, opt_h2d_chunk = 8u << 20, opt_shuffle_grid = 0, opt_pp_out = 1, opt_pp_tile16k = 1, opt_nopart_max = 1 << 21, opt_pcp_copy_ctas = 24, opt_pcp_timeout_ms = 5000;
     bool attrs_set = false;
 };
 
@@ -448,7 +449,7 @@ static int64_t* option_slot(gj_ctx* ctx, const char* name) {
         {"join_cfg", &ctx->opt_join_cfg}, {"unit_tuples", &ctx->opt_unit},
         {"gpu_bits", &ctx->opt_gpu_bits}, {"part_target", &ctx->opt_part_target},
         {"join_grid", &ctx->opt_join_grid}, {"h2d_chunk", &ctx->opt_h2d_chunk},
-        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"nopart_max", &ctx->opt_nopart_max}, {"pcp_ring", &ctx->opt_pcp_ring}, {"pcp_timeout_ms", &ctx->opt_pcp_timeout_ms},
+        {"shuffle_grid", &ctx->opt_shuffle_grid}, {"pp_out", &ctx->opt_pp_out}, {"pp_tile16k", &ctx->opt_pp_tile16k}, {"nopart_max", &ctx->opt_nopart_max}, {"pcp_copy_ctas", &ctx->opt_pcp_copy_ctas}, {"pcp_timeout_ms", &ctx->opt_pcp_timeout_ms},
     };
     for (auto& t : tab) if (!strcmp(t.n, name)) return t.p;
     return nullptr;
@@ -472,7 +473,7 @@ extern "C" int gj_set_option(gj_ctx* ctx, const char* name, int64_t v) {
     if (p == &ctx->opt_pp_out && v > 1) return fail(GJ_ERR_ARG, "pp_out is 0 (8-byte stores) or 1 (TMA bulk stores)");
     if (p == &ctx->opt_pp_tile16k && v > 1) return fail(GJ_ERR_ARG, "pp_tile16k is 0 or 1");
     if (p == &ctx->opt_unit && v && (v < 1024 || v > (1 << 20))) return fail(GJ_ERR_ARG, "unit_tuples must be 0 (default) or in [1024, 2^20]");
-    if ((p == &ctx->opt_join_grid || p == &ctx->opt_shuffle_grid) && v > 65535) return fail(GJ_ERR_ARG, "%s <= 65535 CTAs", name);
+    if ((p == &ctx->opt_join_grid || p == &ctx->opt_shuffle_grid || p == &ctx->opt_pcp_copy_ctas) && v > 65535) return fail(GJ_ERR_ARG, "%s <= 65535 CTAs", name);
     if (p == &ctx->opt_nopart_max && v > (1ll << 31)) return fail(GJ_ERR_ARG, "nopart_max <= 2^31");
     if (p == &ctx->opt_gpu_bits && v > 8) return fail(GJ_ERR_ARG, "gpu_bits <= 8");
     if (p == &ctx->opt_part_target && v < 32) return fail(GJ_ERR_ARG, "part_target >= 32");
@@ -904,8 +905,10 @@ extern "C" int gj_join_aggregate(gj_ctx* ctx, const int32_t* d_Rk, const int32_t
                                  uint64_t* matches, uint64_t* checksum, gj_timings* t) {
     int rc = check_caps(ctx, nR, nS);
     if (rc) return rc;
-    // small build sides: the L2-resident global hash table beats partitioning (option "nopart_max", 0 = never)
-    if (ctx->opt_nopart_max && std::min(nR, nS) && std::min(nR, nS) <= (uint64_t)ctx->opt_nopart_max)
+    // small build sides: the L2-resident global hash table beats partitioning (option "nopart_max", 0 = never; the
+    // default 2^21 comes from the measured crossover, profiles/r2_a/nopart_crossover.log: 2^20 x 2^20 in 41 us against
+    // 68 us partitioned, break-even between 2^22 and 2^23).  A forced radix plan ("radix_bits") keeps the partitioned path.
+    if (ctx->opt_nopart_max && !ctx->opt_radix_bits && std::min(nR, nS) && std::min(nR, nS) <= (uint64_t)ctx->opt_nopart_max)
         return gj_join_aggregate_nopart(ctx, d_Rk, d_Rp, nR, d_Sk, d_Sp, nS, matches, checksum, t);
     if ((nR && (!d_Rk || !d_Rp)) || (nS && (!d_Sk || !d_Sp))) return fail(GJ_ERR_ARG, "NULL input column");
     Rel R, S;
@@ -1855,10 +1858,8 @@ static const PPCfg& pcp_last_cfg(uint32_t bits) { return kPcpLast[bits <= 7u ? 0
 static int pcp_last_ctas_per_sm(uint32_t bits) { return bits <= 7u ? 4 : (bits <= 9u ? 2 : 1); }
 // SMs left to the kernels that run next to the copy kernel: with "shuffle_grid" = k <= half the SMs and
 // the deep ring, k SMs are filled by copy CTAs (196 KB of shared memory each) and host nothing else
-static int pcp_free_sms(const gj_ctx* ctx) {
-    const int64_t k = ctx->opt_shuffle_grid;
-    return (ctx->opt_pcp_ring && k > 0 && k <= ctx->sm_count / 2) ? ctx->sm_count - (int)k : ctx->sm_count;
-}
+static bool pcp_deep_ring(const gj_ctx* ctx) { return ctx->opt_pcp_copy_ctas > 0 && ctx->opt_pcp_copy_ctas <= ctx->sm_count / 2; }
+static int pcp_free_sms(const gj_ctx* ctx) { return pcp_deep_ring(ctx) ? ctx->sm_count - (int)ctx->opt_pcp_copy_ctas : ctx->sm_count; }
 static tup_t* pcp_stage_buf(gj_ctx* ctx, int which) { return which == ctx->pcp.first ? ctx->scratch : ctx->out[which]; }
 static tup_t* pcp_final_buf(gj_ctx* ctx, int which) { return which == ctx->pcp.first ? ctx->out[which] : ctx->scratch; }
 static uint64_t pcp_stage_cap(const gj_ctx* ctx, int which) {
@@ -1988,14 +1989,16 @@ extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void
     a.stage = pcp_stage_buf(ctx, which); a.peer_bases = q.bases[which]; a.t = q.tab[which];
     a.b1 = q.b1; a.bl = q.bl; a.perm = (q.b1 << 8) | q.g;
     const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
-    uint32_t grid = ctx->opt_shuffle_grid ? (uint32_t)ctx->opt_shuffle_grid : (uint32_t)ctx->sm_count;
+    // few CTAs with the deep ring (they fill their SMs: 196 KB of shared memory each), or one shallow-ring CTA per SM
+    const bool deep = pcp_deep_ring(ctx);
+    uint32_t grid = ctx->opt_pcp_copy_ctas ? (uint32_t)ctx->opt_pcp_copy_ctas : (uint32_t)ctx->sm_count;
     grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));
     for (uint32_t k = 0; k < K; ++k) {
         // copy positions are (first-pass partition j, destination d) with d fastest: stage k = partitions [j_lo, j_hi)
         a.pos_lo = (uint32_t)(((uint64_t)k * nj / K) << q.g);
         a.pos_hi = (uint32_t)(((uint64_t)(k + 1) * nj / K) << q.g);
         if (q.n_loc[which]) {
-            if (ctx->opt_pcp_ring) pcp_copy_kernel<PCP_NS_DEEP><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
+            if (deep) pcp_copy_kernel<PCP_NS_DEEP><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
             else pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
             LAUNCHED();
         }

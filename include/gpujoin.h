@@ -80,12 +80,13 @@ int gj_set_stream(gj_ctx* ctx, void* cuda_stream);
  *   "gpu_bits"     number of key bits above the radix field consumed by the multi-GPU shuffle
  *   "shuffle_grid" persistent CTA count of the peer-store scatter (0 = one tile per CTA)
  *   "pp_out", "pp_tile16k"  sharded pipeline, see gj_pp_begin
- *   "pcp_ring"     1: the pcp copy kernel uses a 12-slot ring (10 bulk loads in flight per CTA) -- for running it on
- *                  few SMs ("shuffle_grid" = 16..32) so the passes next to it keep their occupancy (default 0)
+ *   "pcp_copy_ctas" CTAs of the pcp copy kernel (default 24).  Up to half the SMs: deep ring (12 slots, 10 bulk loads in
+ *                  flight per CTA, 196 KB of shared memory), the CTAs fill their SMs and the kernels next to the copy
+ *                  size their grids to the remaining SMs; more, or 0 = one per SM: 4-slot ring sharing the SMs
  *   "pcp_timeout_ms" bound of the receiver's wait for a peer's stage flag (default 5000)
  *   "nopart_max"   gj_join_aggregate takes the non-partitioned path (gj_join_aggregate_nopart) when the
- *                  smaller relation has at most this many tuples (default 0 = never; to be set from the
- *                  measured crossover, tools/nopart_crossover.py) */
+ *                  smaller relation has at most this many tuples and no radix plan is forced (default 2^21, from
+ *                  the measured crossover, tools/nopart_crossover.py / profiles/r2_a; 0 = never) */
 int gj_set_option(gj_ctx* ctx, const char* name, int64_t value);
 int gj_get_option(gj_ctx* ctx, const char* name, int64_t* value);
 
@@ -282,9 +283,7 @@ int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bits);
  *                last join done); plan_bits[3] = gpu bits, source-side local bits, receiver-side bits.
  * Flag buffers: 2 * 64 * n_gpus uint32 per GPU, zeroed once (gj_malloc_device + gj_memset_device), laid out
  * [relation][stage][source]; a flag holds the join number (epoch) of the last completed stage, so it
- * never needs resetting.  Options: "shuffle_grid" = CTAs of the copy kernel (0 = one per SM), "pcp_ring"
- * = 1: 12-slot ring (10 bulk loads in flight per CTA) for running the copy on few SMs, which then host
- * nothing else -- the kernels next to it size their grids to the remaining SMs.
+ * never needs resetting.  Option "pcp_copy_ctas": see gj_set_option.
  * n + 2^(g + bl) must not exceed the context capacity (one spare stage slot per chunk). */
 int gj_pcp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
                  uint32_t local_bits, void* cuda_stream);

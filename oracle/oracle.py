@@ -32,6 +32,9 @@ def build(ref: bool | None = None) -> None:
         ref = os.path.isdir("/root/reference/src")
     if ref:
         targets.append("ref")
+        # the reference's driver objects linked against the product library
+        if os.path.exists(os.path.join(HERE, "..", "icde2019-gpu-join_b200", "lib", "libgpujoin.so")):
+            targets.append("dropin")
     subprocess.run(["make", "-s", "-C", HERE, "-j8"] + targets, check=True)
 
 

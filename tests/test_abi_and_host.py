@@ -152,3 +152,18 @@ def test_new_entry_points_reject_bad_calls_without_a_gpu(gj):
         assert got == want, (i, got, want)
         assert L.gj_last_error()
     assert u64  # (ctypes types referenced above)
+
+
+def test_reference_driver_links_against_the_library():
+    """INTEGRATION.md section 1, checked where the reference sources exist (this container): the reference's driver
+    objects link against libgpujoin.so, which resolves the operator symbol main.cu's algorithm table needs."""
+    import subprocess
+    ref_obj = os.path.join(ROOT, "oracle", "_ref", "obj", "main.o")
+    if not os.path.isdir("/root/reference/src") and not os.path.exists(ref_obj):
+        pytest.skip("reference sources absent")
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "dropin"], check=True)
+    exe = os.path.join(ROOT, "oracle", "_ref", "bench_dropin")
+    undefined = subprocess.run(["nm", "-u", exe], capture_output=True, text=True, check=True).stdout
+    assert "_Z22hashJoinClusteredProbeP4argsP10timingInfo" in undefined          # main.cu:64 takes it from the library
+    needed = subprocess.run(["ldd", exe], capture_output=True, text=True, check=True).stdout
+    assert "libgpujoin.so" in needed and "not found" not in needed.split("libgpujoin.so")[1].split("\n")[0]

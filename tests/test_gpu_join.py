@@ -36,6 +36,7 @@ def reset(eng):
         eng.set_option(k, 0)
     eng.set_option("scatter_cfg", 255)   # auto
     eng.set_option("part_target", 4096)
+    eng.set_option("nopart_max", 0)      # these tests exercise the partitioned path at every size
 
 
 # ------------------------------------------------------------------------------- partitioner
@@ -139,6 +140,27 @@ def test_config1_reference_workload(gj, orc, eng, torch_cuda):
     got = eng.join_aggregate(*dev(torch_cuda, R, rid, S, rid))
     assert (got.matches, got.checksum) == (want.matches, want.checksum)
     assert got.timings.radix_bits == 8 and got.timings.pass2_bits == 0
+
+
+def test_small_build_sides_take_the_nonpartitioned_path_by_default(gj, orc, torch_cuda):
+    """Default dispatch (option "nopart_max" = 2^21, the measured crossover): a small build side joins through the
+    global hash table (2 launches, no radix plan), a larger one or a forced plan through the radix passes --
+    same aggregate either way."""
+    rng = np.random.default_rng(31)
+    with gj.JoinEngine(1 << 22, 1 << 22, 0) as e:
+        assert e.get_option("nopart_max") == 1 << 21
+        for nR, nS, nopart in ((1 << 20, 1 << 20, True), (1000, 3_000_000, True), ((1 << 21) + 1, (1 << 21) + 1, False)):
+            Rk, Sk = rnd(rng, nR, 0, nR), rnd(rng, nS, 0, nR)
+            Rp, Sp = rnd(rng, nR, -2**31, 2**31), rnd(rng, nS, -2**31, 2**31)
+            want = orc.join_check(Rk, Rp, Sk, Sp)
+            d = dev(torch_cuda, Rk, Rp, Sk, Sp)
+            got = e.join_aggregate(*d)
+            assert (got.matches, got.checksum) == (want.matches, want.checksum)
+            assert (got.timings.kernel_launches == 2 and got.timings.radix_bits == 0) == nopart
+            e.set_option("radix_bits", 9)
+            forced = e.join_aggregate(*d)
+            assert (forced.matches, forced.checksum) == (want.matches, want.checksum) and forced.timings.radix_bits == 9
+            e.set_option("radix_bits", 0)
 
 
 def test_fk_pattern_known_answer(gj, orc, eng, torch_cuda):
@@ -648,6 +670,19 @@ def test_pcp_virtual_shards(gj, orc, torch_cuda, G, B, p1):
     assert bits[0] == g and bits[0] + bits[1] <= 10 and bits[2] <= 10 and bits[1] <= 8
     if p1:
         assert bits[1] == max(min(max(p1 - g, 0), 10 - g, B - 1, 8), B - 10)
+
+
+def test_pcp_more_tiles_than_resident_ctas(gj, orc, torch_cuda):
+    """The receiver's last pass runs a persistent grid (the tile count of a stage lives on the device): with
+    ~10 M tuples per receiver a stage has more tiles than CTAs fit the GPU, so every CTA loops."""
+    rng = np.random.default_rng(77)
+    nR, nS, G, B = 4_000_000, 20_000_000, 2, 11
+    Rk = rng.permutation(nR).astype(np.int32)
+    Sk = rng.integers(0, nR, nS).astype(np.int32)
+    Rp, Sp = orc.payload_of_keys(Rk, 40), orc.payload_of_keys(Sk, 50)
+    want = orc.join_check(Rk, Rp, Sk, Sp)
+    for stages in ((1, 1), (2, 3)):
+        assert _pcp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, slack=1.1, stages=stages, check_layout=False)[:2] == (want.matches, want.checksum)
 
 
 def test_pcp_skew_tiny_and_overflow(gj, orc, torch_cuda):
