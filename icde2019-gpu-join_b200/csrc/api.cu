@@ -51,23 +51,13 @@ typedef void (*scatter_fn)(ScatterArgs);
 struct ScatterCfg { int threads, ipt, mode, out; scatter_fn col, packed, col_persist; };
 #define GJ_SC(T, I, M, O, B) { T, I, M, O, scatter_kernel<T, I, M, O, true, B>, scatter_kernel<T, I, M, O, false, B>, \
                                scatter_kernel<T, I, M, O, true, B, true> }
+// The winners of the round-1 sweeps over 16 shapes (profiles/r1_final/sweep.log) plus one structurally different
+// fallback; the losers (8-tuple-per-thread tiles, 1024-thread CTAs, 5-6 CTAs/SM) were 3-25 % slower and are gone.
 static const ScatterCfg kScatter[] = {
-    GJ_SC(256, 16, 1, 0, 4),   // 0 default: two shared atomics, 8-byte stores, 4 CTAs/SM
-    GJ_SC(256, 16, 0, 0, 3),   // 1 rank registers
-    GJ_SC(256, 16, 0, 0, 4),   // 2 rank registers squeezed to 64 registers
-    GJ_SC(512, 16, 1, 0, 2),   // 3
-    GJ_SC(256, 16, 1, 1, 4),   // 4 TMA bulk-copy output
-    GJ_SC(256, 16, 0, 1, 3),   // 5
-    GJ_SC(512, 16, 1, 1, 2),   // 6
-    GJ_SC(256, 8, 1, 0, 6),    // 7
-    GJ_SC(512, 8, 1, 0, 3),    // 8
-    GJ_SC(1024, 8, 1, 0, 1),   // 9
-    GJ_SC(256, 16, 1, 0, 5),   // 10
-    GJ_SC(512, 16, 1, 1, 1),   // 11
-    GJ_SC(512, 8, 1, 1, 3),    // 12 TMA output at 1536 threads/SM
-    GJ_SC(1024, 4, 1, 1, 2),   // 13 TMA output at 2048 threads/SM
-    GJ_SC(1024, 4, 1, 0, 2),   // 14
-    GJ_SC(1024, 8, 1, 1, 1),   // 15
+    GJ_SC(256, 16, 1, 0, 4),   // 0 first pass: two shared atomics, 8-byte stores, 4 CTAs/SM (0.79 of HBM peak at 7 bits)
+    GJ_SC(256, 16, 0, 0, 3),   // 1 fallback: rank kept in registers (one shared atomic per tuple), 3 CTAs/SM
+    GJ_SC(256, 16, 1, 1, 4),   // 2 TMA bulk-copy output, 4 K-tuple tiles: last pass at <= 7 bits, peer-store shuffle
+    GJ_SC(512, 16, 1, 1, 2),   // 3 TMA bulk-copy output, 8 K-tuple tiles: last pass at 8 bits
 };
 static const int kNumScatter = (int)(sizeof(kScatter) / sizeof(kScatter[0]));
 static size_t scatter_smem(const ScatterCfg& c) {
@@ -553,13 +543,13 @@ static const ScatterCfg& scatter_cfg1(const gj_ctx* ctx) {
     return kScatter[ctx->opt_scatter_cfg1 == 255 ? 0 : ctx->opt_scatter_cfg1];
 }
 static const ScatterCfg& scatter_cfg2(const gj_ctx* ctx, uint32_t b2) {
-    return kScatter[ctx->opt_scatter_cfg2 == 255 ? (b2 <= 7 ? 4 : 6) : ctx->opt_scatter_cfg2];
+    return kScatter[ctx->opt_scatter_cfg2 == 255 ? (b2 <= 7 ? 2 : 3) : ctx->opt_scatter_cfg2];
 }
 
 // peer-store shuffle: TMA bulk stores of the (long) per-destination runs -- measured over NVLink on
 // 2 GPUs: 689 GB/s against 581 GB/s with 8-byte stores
 static const ScatterCfg& scatter_cfg_shuffle(const gj_ctx* ctx) {
-    return kScatter[ctx->opt_scatter_cfg1 == 255 ? 4 : ctx->opt_scatter_cfg1];
+    return kScatter[ctx->opt_scatter_cfg1 == 255 ? 2 : ctx->opt_scatter_cfg1];
 }
 
 static uint32_t unit_tuples(const gj_ctx* ctx) { return ctx->opt_unit ? (uint32_t)ctx->opt_unit : 8192u; }

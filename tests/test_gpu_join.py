@@ -62,7 +62,7 @@ def test_partition_matches_oracle(gj, orc, eng, torch_cuda, n, bits):
     assert np.array_equal(c1, c2) and np.array_equal(h1, h2)
 
 
-@pytest.mark.parametrize("cfg", range(16))
+@pytest.mark.parametrize("cfg", range(4))
 def test_partition_every_scatter_variant(gj, orc, eng, torch_cuda, cfg):
     reset(eng)
     eng.set_option("scatter_cfg", cfg)

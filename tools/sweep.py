@@ -81,7 +81,7 @@ def main():
                 if b - p1 <= 8:
                     run("bits", radix_bits=b, pass1_bits=p1)
     if "combo" in what:
-        for p1, c1s, c2s in ((7, (0, 14), (4, 6, 12, 13, 15)), (8, (0,), (4, 12, 13))):
+        for p1, c1s, c2s in ((7, (0, 1), (2, 3)), (8, (0,), (2, 3))):
             for c1 in c1s:
                 for c2 in c2s:
                     run("combo", radix_bits=15, pass1_bits=p1, scatter_cfg1=c1, scatter_cfg2=c2)
