@@ -10,9 +10,9 @@ The directory name contains hyphens, so import it through `__graft_entry__.load_
 (registered in sys.modules as `icde2019_gpu_join_b200`).
 """
 from .engine import (GJError, JoinEngine, JoinResult, Timings, lib, lib_path, C_ABI_SYMBOLS,  # noqa: F401
-                     kernel_launch_count, bijection, payload_of_key)
+                     kernel_launch_count, bijection, payload_of_key, pcp_ctrl_bytes)
 from . import generator  # noqa: F401
 from . import distributed  # noqa: F401
 
 __all__ = ["GJError", "JoinEngine", "JoinResult", "Timings", "lib", "lib_path", "generator",
-           "distributed", "C_ABI_SYMBOLS", "kernel_launch_count", "bijection", "payload_of_key"]
+           "distributed", "C_ABI_SYMBOLS", "kernel_launch_count", "bijection", "payload_of_key", "pcp_ctrl_bytes"]

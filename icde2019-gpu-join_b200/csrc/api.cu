@@ -100,8 +100,8 @@ static const PPCfg kPcpLast[4] = {
     { 512, 16, 1, 512, scatter_kernel<512, 16, 1, 1, false, 2, true, 512> },                 // 9 bits
     { 1024, 8, 1, 1024, scatter_kernel<1024, 8, 1, 1, false, 1, true, 1024> },               // 10 bits
 };
-constexpr int PCP_NS = 4;        // ring slots of the copy kernel (2 loads in flight per CTA)
-constexpr int PCP_NS_DEEP = 12;  // deep ring (10 loads in flight per CTA): for running the copy on a FEW SMs only, so
+constexpr int PCP_NS = 3;        // ring slots of 32 KB of the copy kernel (1 load in flight per CTA)
+constexpr int PCP_NS_DEEP = 6;   // deep ring (4 loads of 32 KB in flight per CTA): for running the copy on a FEW SMs only, so
                                  // that the radix passes next to it keep their full occupancy (option "pcp_copy_ctas")
 static size_t pcp_copy_smem(int ns = PCP_NS) { return (size_t)ns * PCP_PIECE * sizeof(tup_t) + (PCP_MAX_CHUNKS + 4) * sizeof(uint32_t); }
 constexpr uint32_t PP_MAX_PASS_BITS = 10;
@@ -221,7 +221,8 @@ struct gj_ctx {
         unsigned char* block = nullptr;
         PcpTables tab[2];
         tup_t** bases[2] = {nullptr, nullptr};
-        uint32_t** flag_ptrs[2] = {nullptr, nullptr};   // device: every GPU's flag buffer (local or mapped)
+        unsigned char** ctrl_ptrs[2] = {nullptr, nullptr};   // device: every GPU's control block (flags + fine_in; local or mapped)
+        uint32_t* fine[2] = {nullptr, nullptr};         // this source's fine histograms [2^(g + B)] (zeroed per join)
         int first = 0;                       // the relation that builds (travels first)
         uint32_t epoch = 0;                  // join number: the value the stage flags take
         uint32_t stages[2] = {0, 0};
@@ -1818,12 +1819,13 @@ static int ensure_pcp(gj_ctx* ctx) {
     if (q.block) return GJ_OK;
     const size_t per = (size_t)(PCP_MAX_CHUNKS + 4) * sizeof(uint32_t);
     size_t b = 0;
-    size_t o[2][7], o_db[2], o_bs[2], o_fl[2];
+    size_t o[2][7], o_db[2], o_bs[2], o_fl[2], o_fine[2];
     for (int r = 0; r < 2; ++r) {
         for (int k = 0; k < 7; ++k) { o[r][k] = b; b += per; }
         o_db[r] = b; b += PCP_MAX_CHUNKS * sizeof(tup_t*);
         o_bs[r] = b; b += NB_MAX * sizeof(tup_t*);
         o_fl[r] = b; b += NB_MAX * sizeof(uint32_t*);
+        o_fine[r] = b; b += sizeof(uint32_t) << PP_MAX_BITS;
     }
     if (cudaMalloc(&q.block, b) != cudaSuccess) { cudaGetLastError(); return fail(GJ_ERR_NOMEM, "pcp metadata"); }
     for (int r = 0; r < 2; ++r) {
@@ -1836,7 +1838,8 @@ static int ensure_pcp(gj_ctx* ctx) {
         q.tab[r].recv_off = reinterpret_cast<uint32_t*>(q.block + o[r][6]);
         q.tab[r].dig_base = reinterpret_cast<tup_t**>(q.block + o_db[r]);
         q.bases[r] = reinterpret_cast<tup_t**>(q.block + o_bs[r]);
-        q.flag_ptrs[r] = reinterpret_cast<uint32_t**>(q.block + o_fl[r]);
+        q.ctrl_ptrs[r] = reinterpret_cast<unsigned char**>(q.block + o_fl[r]);
+        q.fine[r] = reinterpret_cast<uint32_t*>(q.block + o_fine[r]);
     }
     CK(cudaHostAlloc(&q.h_pin, 4 * NB_MAX * sizeof(void*) + 64, cudaHostAllocDefault));
     for (auto& r : q.ev) for (auto& e : r) CK(cudaEventCreate(&e));
@@ -1915,6 +1918,7 @@ extern "C" int gj_pcp_hist(gj_ctx* ctx, int which, const int32_t* d_keys, uint64
     q.n_loc[which] = n;
     CK(cudaMemsetAsync(d_coarse_hist, 0, sizeof(uint32_t) << q.b1, s));
     CK(cudaMemsetAsync(q.tab[which].status, 0, 4 * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(q.fine[which], 0, sizeof(uint32_t) << (q.g + q.B), s));
     return enqueue_hist(ctx, s, d_keys, false, n, q.B - q.bl, q.b1, d_coarse_hist);
 }
 
@@ -1947,17 +1951,23 @@ extern "C" int gj_pcp_part(gj_ctx* ctx, int which, const int32_t* d_keys, const 
         a.ntiles = (uint32_t)((n + T1 - 1) / T1);
         c1.fn<<<a.ntiles, c1.threads, pp_smem(c1), s>>>(a);
         LAUNCHED();
+        // fine counts of the chunks this GPU keeps (they never pass through the copy kernel)
+        const uint32_t slices = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(16, (n >> (q.b1 > 0 ? q.b1 : 0)) / PCP_SELF_SLICE + 1));
+        pcp_self_hist_kernel<<<dim3(slices, 1u << q.bl), 256, 0, s>>>((const tup_t*)d_own, q.tab[which], q.rank, q.bl, q.b2, q.fine[which]);
+        LAUNCHED();
     }
     CK(cudaEventRecord(q.ev[which][1], s));
     q.parted[which] = true;
     return GJ_OK;
 }
 
-extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* const* peer_flags, uint32_t n_stages,
+extern "C" uint64_t gj_pcp_ctrl_bytes(uint32_t n_gpus) { return pcp_ctrl_bytes(n_gpus, MAX_RADIX_BITS); }
+
+extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* const* peer_ctrl, uint32_t n_stages,
                            void* cuda_stream) {
     if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
     if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
-    if (!peer_bases || !peer_flags) return fail(GJ_ERR_ARG, "NULL argument");
+    if (!peer_bases || !peer_ctrl) return fail(GJ_ERR_ARG, "NULL argument");
     if (n_stages < 1 || n_stages > (uint32_t)PCP_MAX_STAGES) return fail(GJ_ERR_ARG, "n_stages must be in [1, %d]", PCP_MAX_STAGES);
     gj_ctx::PCP& q = ctx->pcp;
     if (!q.parted[which]) return fail(GJ_ERR_STATE, "gj_pcp_part first");
@@ -1966,18 +1976,19 @@ extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void
     void** hb = reinterpret_cast<void**>(q.h_pin) + (size_t)which * 2 * NB_MAX;
     for (uint32_t g = 0; g < q.G; ++g) {
         if (!peer_bases[g] || ((size_t)peer_bases[g] & 15u)) return fail(GJ_ERR_ARG, "destination buffer %u must be non-NULL and 16-byte aligned", g);
-        if (!peer_flags[g]) return fail(GJ_ERR_ARG, "flag buffer %u is NULL", g);
+        if (!peer_ctrl[g] || ((size_t)peer_ctrl[g] & 15u)) return fail(GJ_ERR_ARG, "control block %u must be non-NULL and 16-byte aligned", g);
         hb[g] = peer_bases[g];
-        hb[NB_MAX + g] = peer_flags[g];
+        hb[NB_MAX + g] = peer_ctrl[g];
     }
     CK(cudaMemcpyAsync(q.bases[which], hb, q.G * sizeof(void*), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(q.flag_ptrs[which], hb + NB_MAX, q.G * sizeof(void*), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(q.ctrl_ptrs[which], hb + NB_MAX, q.G * sizeof(void*), cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(q.ev[which][2], s));
     const uint32_t nj = 1u << q.bl, K = std::min(n_stages, nj);
     q.stages[which] = K;
     PcpCopyArgs a;
     a.stage = pcp_stage_buf(ctx, which); a.peer_bases = q.bases[which]; a.t = q.tab[which];
     a.b1 = q.b1; a.bl = q.bl; a.perm = (q.b1 << 8) | q.g;
+    a.b2 = q.b2; a.fine = q.fine[which];
     const uint64_t pieces_max = q.n_loc[which] / PCP_PIECE + (1ull << q.b1) + 1;
     // few CTAs with the deep ring (they fill their SMs: 196 KB of shared memory each), or one shallow-ring CTA per SM
     const bool deep = pcp_deep_ring(ctx);
@@ -1985,26 +1996,29 @@ extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void
     grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(grid, pieces_max));
     for (uint32_t k = 0; k < K; ++k) {
         // copy positions are (first-pass partition j, destination d) with d fastest: stage k = partitions [j_lo, j_hi)
-        a.pos_lo = (uint32_t)(((uint64_t)k * nj / K) << q.g);
-        a.pos_hi = (uint32_t)(((uint64_t)(k + 1) * nj / K) << q.g);
+        const uint32_t j_lo = (uint32_t)((uint64_t)k * nj / K), j_hi = (uint32_t)((uint64_t)(k + 1) * nj / K);
+        a.pos_lo = j_lo << q.g;
+        a.pos_hi = j_hi << q.g;
         if (q.n_loc[which]) {
-            if (deep) pcp_copy_kernel<PCP_NS_DEEP><<<grid, 32, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
-            else pcp_copy_kernel<PCP_NS><<<grid, 32, pcp_copy_smem(), s>>>(a);
+            if (deep) pcp_copy_kernel<PCP_NS_DEEP><<<grid, PCP_COPY_THREADS, pcp_copy_smem(PCP_NS_DEEP), s>>>(a);
+            else pcp_copy_kernel<PCP_NS><<<grid, PCP_COPY_THREADS, pcp_copy_smem(), s>>>(a);
             LAUNCHED();
         }
-        pcp_signal_kernel<<<1, std::max(32u, q.G), 0, s>>>(q.flag_ptrs[which], q.G, q.rank, (uint32_t)which * PCP_MAX_STAGES + k, q.epoch);
+        // the stage's fine counts + the flag, into every GPU's control block (this one's included)
+        pcp_push_kernel<<<q.G, 256, 0, s>>>(q.fine[which], q.ctrl_ptrs[which], q.G, q.rank, (uint32_t)which, k, q.epoch, q.B,
+                                            j_lo << q.b2, j_hi << q.b2, q.tab[which].status);
         LAUNCHED();
     }
     CK(cudaEventRecord(q.ev[which][3], s));
     return GJ_OK;
 }
 
-extern "C" int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, const void* d_flags, uint64_t cap_tuples,
-                           void* cuda_stream) {
+extern "C" int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, const void* d_ctrl, uint64_t cap_tuples,
+                           void* d_result_out, void* cuda_stream) {
     if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
     if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
     if (!d_own || ((size_t)d_own & 15u)) return fail(GJ_ERR_ARG, "receive buffer must be non-NULL and 16-byte aligned");
-    if (!d_flags) return fail(GJ_ERR_ARG, "flag buffer is NULL");
+    if (!d_ctrl) return fail(GJ_ERR_ARG, "control block is NULL");
     gj_ctx::PCP& q = ctx->pcp;
     if (cap_tuples > pcp_final_cap(ctx, which)) return fail(GJ_ERR_ARG, "receive capacity exceeds the context capacity");
     if (!q.stages[which] || !q.parted[which]) return fail(GJ_ERR_STATE, "gj_pcp_part and gj_pcp_copy first");
@@ -2030,14 +2044,18 @@ extern "C" int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, const void
     bool waited_build = false;
     for (uint32_t k = 0; k < K && !empty; ++k) {
         const uint32_t j_lo = (uint32_t)((uint64_t)k * nj / K), j_hi = (uint32_t)((uint64_t)(k + 1) * nj / K);
-        pcp_wait_kernel<<<1, std::max(32u, q.G), 0, s>>>((const uint32_t*)d_flags, q.G, q.rank, (uint32_t)which * PCP_MAX_STAGES + k,
+        pcp_wait_kernel<<<1, std::max(32u, q.G), 0, s>>>((const uint32_t*)d_ctrl, q.G, q.rank, (uint32_t)which * PCP_MAX_STAGES + k,
                                                          q.epoch, (unsigned long long)ctx->opt_pcp_timeout_ms * 1000000ull, tb.status);
         LAUNCHED();
         if (k + 1 == K) CK(cudaEventRecord(q.jev[0], s));      // the last byte of this relation has landed
-        // fine histogram of what arrived for [j_lo, j_hi); the counters of earlier stages stay, so the
-        // full-range scan below yields the same offsets for them again and the new ones behind them
+        // fine histogram of what arrived for [j_lo, j_hi) = the sum of the counts the sources delivered with
+        // their flags (taken by their copy kernels: the receiver does not read the data to count it).  The
+        // counters of earlier stages stay, so the full-range scan below yields the same offsets for them
+        // again and the new ones behind them.
         if (k) CK(cudaMemsetAsync(ctx->zero_role[role] + desc_off, 0, ctx->zero_role_bytes - desc_off, s));
-        if ((rc = enqueue_hist(ctx, s, d_own, true, cap_tuples, 0, q.B, m.ghist, 1024, tb.recv_off + j_lo, tb.recv_off + j_hi, free_sms))) return rc;
+        pcp_sum_hist_kernel<<<std::max(1u, std::min(64u, ((j_hi - j_lo) << q.b2) / 256u)), 256, 0, s>>>(
+            (const unsigned char*)d_ctrl, q.G, (uint32_t)which, q.B, j_lo << q.b2, j_hi << q.b2, m.ghist);
+        LAUNCHED();
         {
             ScanSeq so;
             so.in = m.ghist; so.in2 = nullptr; so.out = m.off; so.desc = m.desc; so.ticket = m.ticket;
@@ -2101,6 +2119,8 @@ extern "C" int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, const void
     q.recv_done[which] = true;
     if (joins) {
         CK(cudaEventRecord(q.jev[1], s));
+        // the local aggregate {matches, checksum} also into a device buffer of the caller's (input of its all-reduce)
+        if (d_result_out) CK(cudaMemcpyAsync(d_result_out, ctx->result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(ctx->h_result, ctx->result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         uint32_t* hs = reinterpret_cast<uint32_t*>(q.h_pin + 4 * NB_MAX * sizeof(void*));
         for (int w = 0; w < 2; ++w) CK(cudaMemcpyAsync(hs + 4 * w, q.tab[w].status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -588,15 +588,21 @@ pp_cursor_kernel(const uint32_t* __restrict__ all_hist, uint32_t n_gpus, uint32_
 //     never staged or copied: the source pass stores them straight into this GPU's receive buffer.
 //     The exchange is a STREAM: chunks travel in ascending first-pass partition j on every GPU
 //     (tile_perm), the copy is issued in stages (groups of j), each followed by a flag store into
-//     every peer (pcp_signal_kernel); the receiver waits per stage (pcp_wait_kernel) and runs
-//     histogram + last radix pass + join over the partitions of that stage while the later
-//     stages are still crossing NVLink.
+//     every peer (pcp_push_kernel); the receiver waits per stage (pcp_wait_kernel) and runs the last
+//     radix pass + join over the partitions of that stage while the later stages are still crossing
+//     NVLink.  The receiver never re-reads what arrived to count it: the copy kernel's histogram
+//     warps count every piece by the receiver-side radix bits while it sits in shared memory, and
+//     pcp_push_kernel delivers those counts with the flag.
 //     status: [0] abort (a destination would overflow) [1] tuples this GPU receives [2] pieces
 //             [3] a wait timed out
 // ------------------------------------------------------------------------------------------
 constexpr int PCP_MAX_CHUNKS = 1024;
 constexpr int PCP_MAX_STAGES = 64;
-constexpr uint32_t PCP_PIECE = 2048;     // tuples per bulk copy (16 KB), even
+constexpr uint32_t PCP_PIECE = 4096;     // tuples per bulk copy (32 KB), even
+// per-GPU control block (peer-mapped): stage flags [relation][stage][source] uint32, then the fine
+// histograms the sources deliver, fine_in [relation][source][2^B] uint32
+__host__ __device__ __forceinline__ size_t pcp_ctrl_flag_bytes(uint32_t n_gpus) { return (size_t)2 * PCP_MAX_STAGES * n_gpus * sizeof(uint32_t); }
+__host__ __device__ __forceinline__ size_t pcp_ctrl_bytes(uint32_t n_gpus, uint32_t B) { return pcp_ctrl_flag_bytes(n_gpus) + (((size_t)2 * n_gpus) << B) * sizeof(uint32_t); }
 struct PcpTables {                       // device arrays of n1 (+1) entries
     uint32_t* cur;                       // pass-1 cursors (consumed by the scatter), relative to dig_base[c]
     tup_t** dig_base;                    // pass-1 output base of chunk c: the stage buffer, or this GPU's receive buffer
@@ -682,81 +688,213 @@ struct PcpCopyArgs {
     PcpTables t;
     uint32_t b1, bl, perm;
     uint32_t pos_lo, pos_hi;             // this launch moves the chunks at copy positions [pos_lo, pos_hi)
+    uint32_t b2;                         // receiver-side radix bits
+    uint32_t* fine;                      // this source's fine histogram [2^(b1 + b2)], index (chunk << b2) | low key bits
 };
 
-// One warp per CTA, NS ring slots of PCP_PIECE tuples.  Lane 0 walks this CTA's pieces (static
-// round robin): it issues the bulk load of piece i and, LAG pieces behind, the bulk store of piece
-// i - LAG, so LAG loads are in flight per CTA and a slot is reloaded only after its previous store
-// has read it (bulk async-group accounting: one group per piece, empty groups included).
-// NS = 4 on every SM, or NS = 12 (10 loads in flight per CTA, 196 KB of shared memory) on a few SMs
-// that then run nothing else, so the radix passes and the join next to it keep the other SMs whole.
+constexpr int PCP_HIST_WARPS = 4;
+constexpr int PCP_COPY_THREADS = 32 * (2 + PCP_HIST_WARPS);
+constexpr uint32_t PCP_BAR_HIST = 2;     // named barrier of the histogram warps
+
+// Warp-specialised copy pipeline over a ring of NS slots of PCP_PIECE tuples; this CTA's pieces are those
+// of the stage taken round robin.
+//   warp 0 (one lane)  LOADER: per piece, address arithmetic (the chunk's table entries stay in registers
+//                      while consecutive pieces belong to the same chunk), wait for the slot to be free,
+//                      bulk load global -> shared (completion on the slot's "full" mbarrier).  Never waits
+//                      for a load: up to NS loads are in flight per CTA.
+//   warp 1 (one lane)  STORER: waits for "full", issues the bulk store shared -> peer global, and frees a
+//                      slot once the store has READ it (bulk async-group accounting, one group per piece).
+//   warps 2..5         HISTOGRAM: while a piece sits in shared memory they count its tuples by the
+//                      receiver-side radix bits -- the FINE histogram the receiver needs for its last pass,
+//                      taken here for free (no HBM traffic) instead of by a second read of everything that
+//                      arrived (8 B/tuple at the receiver).  Counts gather per chunk in shared memory and go
+//                      to `fine` when the CTA moves to another chunk.
+// A slot is free again when the storer and the four histogram warps have arrived on its "free" mbarrier.
+// NS = 3 on every SM, or NS = 6 (192 KB of shared memory) on a few SMs that then run nothing else, so the
+// radix passes and the join next to it keep the other SMs whole.
 template <int NS>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(PCP_COPY_THREADS)
 pcp_copy_kernel(PcpCopyArgs a) {
-    constexpr uint32_t LAG = NS - 2;
-    static_assert(NS >= 3, "ring too small");
+    static_assert(NS >= 2, "ring too small");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tup_t* ring = reinterpret_cast<tup_t*>(smem_raw);                                   // [NS][PCP_PIECE]
     uint32_t* s_prefix = reinterpret_cast<uint32_t*>(smem_raw + (size_t)NS * PCP_PIECE * sizeof(tup_t));   // [n1 + 1]
-    __shared__ uint64_t s_full[NS];
+    __shared__ uint64_t s_full[NS], s_free[NS];
     __shared__ tup_t* s_dst[NS];
-    __shared__ uint32_t s_bytes[NS];
-    const uint32_t n1 = 1u << a.b1;
+    __shared__ uint32_t s_bytes[NS], s_chunk[NS];
+    __shared__ uint32_t s_hist[1u << 10];       // receiver-side pass: <= 10 bits
+    const uint32_t n1 = 1u << a.b1, tid = threadIdx.x, wid = tid >> 5;
     if (a.t.status[0]) return;
-    for (uint32_t i = threadIdx.x; i <= n1; i += 32) s_prefix[i] = a.t.piece_prefix[i];
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) mbar_init(&s_full[s], 1);
+    for (uint32_t i = tid; i <= n1; i += PCP_COPY_THREADS) s_prefix[i] = a.t.piece_prefix[i];
+    for (uint32_t i = tid; i < (1u << a.b2); i += PCP_COPY_THREADS) s_hist[i] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 1 + PCP_HIST_WARPS); }
         fence_mbar_init();
     }
-    __syncwarp();
-    if (threadIdx.x != 0) return;
+    __syncthreads();
     const uint32_t k0 = s_prefix[a.pos_lo], total = s_prefix[min(a.pos_hi, n1)];
-    uint32_t issued = 0, stored = 0;
-    for (uint32_t k = k0 + blockIdx.x; k < total || stored < issued; k += gridDim.x) {
-        if (k < total) {
-            uint32_t lo = a.pos_lo, hi = n1;      // largest position whose prefix is <= k
-            while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (s_prefix[m] <= k) lo = m; else hi = m; }
-            const uint32_t c = tile_perm(lo, a.perm), slice = k - s_prefix[lo];
-            const uint32_t src0 = a.t.src_start[c], dst0 = a.t.dst_start[c], cnt = a.t.cnt[c];
-            const uint32_t phase = src0 & 1u;     // == dst0 & 1 by construction
-            const tup_t* src = a.stage + src0;
-            tup_t* dst = a.peer_bases[c >> a.bl] + dst0;
-            if (slice == 0 && phase) *dst = *src;                     // odd first slot: plain 8-byte copy
-            const uint32_t body0 = phase + slice * PCP_PIECE;         // even slot on both sides
-            uint32_t m = (cnt > body0) ? min(PCP_PIECE, cnt - body0) : 0u;
-            if (m & 1u) { dst[body0 + m - 1u] = src[body0 + m - 1u]; --m; }   // odd tail (last piece only)
-            const uint32_t slot = issued % NS;
-            // the slot's previous tenant (piece issued - NS) was stored at least NS - 1 - LAG groups ago
-            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NS - 1 - LAG) : "memory");
-            s_dst[slot] = dst + body0;
-            s_bytes[slot] = m * (uint32_t)sizeof(tup_t);
-            mbar_arrive_expect_tx(&s_full[slot], m * (uint32_t)sizeof(tup_t));
-            if (m) bulk_g2s(ring + (size_t)slot * PCP_PIECE, src + body0, m * (uint32_t)sizeof(tup_t), &s_full[slot]);
-            ++issued;
+    const uint32_t first = k0 + blockIdx.x;
+    const uint32_t mine = first < total ? (total - first + gridDim.x - 1) / gridDim.x : 0u;   // pieces of this CTA
+    const uint32_t mask2 = (1u << a.b2) - 1u;
+    if (wid >= 2) {
+        // ---------------- histogram warps
+        const uint32_t ht = tid - 64, HT = 32 * PCP_HIST_WARPS;
+        uint32_t cur = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i < mine; ++i) {
+            const uint32_t slot = i % NS;
+            if ((tid & 31u) == 0) mbar_wait(&s_full[slot], (i / NS) & 1u);     // one poller per warp
+            __syncwarp();
+            const uint32_t c = s_chunk[slot], m = s_bytes[slot] / (uint32_t)sizeof(tup_t);
+            if (c != cur) {
+                if (cur != 0xFFFFFFFFu) {
+                    named_bar_sync(PCP_BAR_HIST, HT);          // every count of the previous chunk is in
+                    for (uint32_t x = ht; x <= mask2; x += HT) {
+                        const uint32_t v = s_hist[x];
+                        if (v) { atomicAdd(&a.fine[((size_t)cur << a.b2) + x], v); s_hist[x] = 0; }
+                    }
+                    named_bar_sync(PCP_BAR_HIST, HT);          // zeroed before anybody counts again
+                }
+                cur = c;
+            }
+            const tup_t* p = ring + (size_t)slot * PCP_PIECE;
+#pragma unroll 4
+            for (uint32_t x = ht; x < m; x += HT) atomicAdd(&s_hist[p[x].x & mask2], 1u);
+            __syncwarp();
+            if ((tid & 31u) == 0) mbar_arrive(&s_free[slot]);
         }
-        // keep at most LAG loads ahead of the stores; drain once the pieces are exhausted
-        while (stored < issued && (k >= total || issued - stored > LAG)) {
-            const uint32_t slot = stored % NS;
-            mbar_wait(&s_full[slot], (stored / NS) & 1u);
+        if (cur != 0xFFFFFFFFu) {
+            named_bar_sync(PCP_BAR_HIST, HT);
+            for (uint32_t x = ht; x <= mask2; x += HT) {
+                const uint32_t v = s_hist[x];
+                if (v) atomicAdd(&a.fine[((size_t)cur << a.b2) + x], v);
+            }
+        }
+        return;
+    }
+    if ((tid & 31u) != 0) return;
+    if (wid == 1) {
+        // ---------------- storer lane
+        for (uint32_t i = 0; i < mine; ++i) {
+            const uint32_t slot = i % NS;
+            mbar_wait(&s_full[slot], (i / NS) & 1u);
             if (s_bytes[slot]) bulk_s2g(s_dst[slot], ring + (size_t)slot * PCP_PIECE, s_bytes[slot]);
             bulk_commit();
-            ++stored;
+            if (i) {   // all groups but the newest have been read: piece i - 1 has left its slot
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                mbar_arrive(&s_free[(i - 1) % NS]);
+            }
         }
+        if (mine) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(&s_free[(mine - 1) % NS]);
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the stores have completed, not just been read
+        __threadfence_system();
+        return;
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the stores have completed, not just been read
-    __threadfence_system();
+    // ---------------- loader lane
+    uint32_t pos = a.pos_lo, c = 0, src0 = 0, dst0 = 0, cnt = 0, cached = 0xFFFFFFFFu;
+    tup_t* dbase = nullptr;
+    uint32_t i = 0;
+    for (uint32_t k = first; k < total; k += gridDim.x, ++i) {
+        while (s_prefix[pos + 1] <= k) ++pos;           // the position holding piece k (k < total <= prefix of the stage's end)
+        if (pos != cached) {
+            cached = pos;
+            c = tile_perm(pos, a.perm);
+            src0 = a.t.src_start[c]; dst0 = a.t.dst_start[c]; cnt = a.t.cnt[c];
+            dbase = a.peer_bases[c >> a.bl];
+        }
+        const uint32_t slice = k - s_prefix[pos];
+        const uint32_t phase = src0 & 1u;     // == dst0 & 1 by construction
+        const tup_t* src = a.stage + src0;
+        tup_t* dst = dbase + dst0;
+        if (slice == 0 && phase) {            // odd first slot: plain 8-byte copy, counted here
+            const tup_t t = *src;
+            *dst = t;
+            atomicAdd(&a.fine[((size_t)c << a.b2) + (t.x & mask2)], 1u);
+        }
+        const uint32_t body0 = phase + slice * PCP_PIECE;         // even slot on both sides
+        uint32_t m = (cnt > body0) ? min(PCP_PIECE, cnt - body0) : 0u;
+        if (m & 1u) {                         // odd tail (last piece only)
+            const tup_t t = src[body0 + m - 1u];
+            dst[body0 + m - 1u] = t;
+            atomicAdd(&a.fine[((size_t)c << a.b2) + (t.x & mask2)], 1u);
+            --m;
+        }
+        const uint32_t slot = i % NS;
+        if (i >= (uint32_t)NS) mbar_wait(&s_free[slot], ((i / NS) - 1u) & 1u);   // stored and counted
+        s_dst[slot] = dst + body0;
+        s_bytes[slot] = m * (uint32_t)sizeof(tup_t);
+        s_chunk[slot] = c;
+        mbar_arrive_expect_tx(&s_full[slot], m * (uint32_t)sizeof(tup_t));
+        if (m) bulk_g2s(ring + (size_t)slot * PCP_PIECE, src + body0, m * (uint32_t)sizeof(tup_t), &s_full[slot]);
+    }
+    __threadfence_system();                   // the plain head / tail stores
 }
 
-// After a copy stage: tell every peer that this source's chunks of the stage have landed.  Runs on the
-// copy's stream, i.e. after the copy kernel (and all its bulk stores) completed.  A flag word holds
-// the epoch (join number) of the last completed stage; flags of one GPU: [relation][stage][source].
-__global__ void pcp_signal_kernel(uint32_t* const* __restrict__ peer_flags, uint32_t n_gpus, uint32_t rank,
-                                  uint32_t slot, uint32_t epoch) {
-    const uint32_t d = threadIdx.x;
-    if (d >= n_gpus) return;
+// Fine histogram of the chunks this GPU KEEPS (its source pass stored them straight into its receive
+// buffer; they never pass through the copy kernel): one CTA per (first-pass partition j, slice of
+// PCP_SELF_SLICE tuples), counts by the receiver-side radix bits into `fine`.  8 B/tuple over 1/G of the shard.
+constexpr uint32_t PCP_SELF_SLICE = 16384;
+__global__ void __launch_bounds__(256)
+pcp_self_hist_kernel(const tup_t* __restrict__ own, PcpTables t, uint32_t rank, uint32_t bl, uint32_t b2,
+                     uint32_t* __restrict__ fine) {
+    __shared__ uint32_t s_hist[1u << 10];
+    if (t.status[0]) return;
+    const uint32_t mask2 = (1u << b2) - 1u;
+    const uint32_t c = (rank << bl) | blockIdx.y;
+    const uint32_t cnt = t.cnt[c], base = t.dst_start[c];
+    for (uint32_t s0 = blockIdx.x * PCP_SELF_SLICE; s0 < cnt; s0 += gridDim.x * PCP_SELF_SLICE) {
+        for (uint32_t x = threadIdx.x; x <= mask2; x += 256) s_hist[x] = 0;
+        __syncthreads();
+        const uint32_t hi = min(cnt, s0 + PCP_SELF_SLICE);
+        for (uint32_t i = s0 + threadIdx.x; i < hi; i += 256) atomicAdd(&s_hist[__ldg(&own[base + i].x) & mask2], 1u);
+        __syncthreads();
+        for (uint32_t x = threadIdx.x; x <= mask2; x += 256) {
+            const uint32_t v = s_hist[x];
+            if (v) atomicAdd(&fine[((size_t)c << b2) + x], v);
+        }
+        __syncthreads();
+    }
+}
+
+// After a copy stage: hand every destination d the fine counts of what this source sent it in the stage
+// (fine[(d << B) + p] for the stage's partitions p, into d's table fine_in[source = rank]) and then tell it
+// that the stage has landed.  Runs on the copy's stream, i.e. after the copy kernel (and all its bulk
+// stores) completed.  A flag word holds the epoch (join number) of the last completed stage; control
+// block of one GPU: flags [relation][stage][source], then fine_in [relation][source][2^B].
+// One CTA per destination (this GPU included: its own chunks' counts come from pcp_self_hist_kernel).
+__global__ void __launch_bounds__(256)
+pcp_push_kernel(const uint32_t* __restrict__ fine, unsigned char* const* __restrict__ peer_ctrl, uint32_t n_gpus,
+                uint32_t rank, uint32_t which, uint32_t stage, uint32_t epoch, uint32_t B, uint32_t p_lo, uint32_t p_hi,
+                const uint32_t* __restrict__ status) {
+    const uint32_t d = blockIdx.x;
+    unsigned char* ctrl = peer_ctrl[d];
+    uint32_t* flags = reinterpret_cast<uint32_t*>(ctrl);
+    uint32_t* fine_in = reinterpret_cast<uint32_t*>(ctrl + pcp_ctrl_flag_bytes(n_gpus)) + (((size_t)which * n_gpus + rank) << B);
+    if (!status[0]) {
+        const uint32_t* src = fine + ((size_t)d << B);
+        for (uint32_t p = p_lo + threadIdx.x; p < p_hi; p += 256) fine_in[p] = src[p];
+    }
     __threadfence_system();
-    volatile uint32_t* f = peer_flags[d] + (size_t)slot * n_gpus + rank;
-    *f = epoch;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        volatile uint32_t* f = flags + ((size_t)which * PCP_MAX_STAGES + stage) * n_gpus + rank;
+        *f = epoch;
+    }
+}
+
+// Receiver: counts of the stage's partitions = sum over the sources' tables.
+__global__ void __launch_bounds__(256)
+pcp_sum_hist_kernel(const unsigned char* __restrict__ ctrl, uint32_t n_gpus, uint32_t which, uint32_t B, uint32_t p_lo,
+                    uint32_t p_hi, uint32_t* __restrict__ ghist) {
+    const uint32_t* fine_in = reinterpret_cast<const uint32_t*>(ctrl + pcp_ctrl_flag_bytes(n_gpus)) + (((size_t)which * n_gpus) << B);
+    for (uint32_t p = p_lo + blockIdx.x * 256 + threadIdx.x; p < p_hi; p += gridDim.x * 256) {
+        uint32_t v = 0;
+        for (uint32_t s = 0; s < n_gpus; ++s) v += fine_in[((size_t)s << B) + p];
+        ghist[p] = v;
+    }
 }
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -770,7 +908,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __global__ void pcp_wait_kernel(const uint32_t* __restrict__ flags, uint32_t n_gpus, uint32_t rank, uint32_t slot,
                                 uint32_t epoch, unsigned long long timeout_ns, uint32_t* __restrict__ status) {
     const uint32_t s = threadIdx.x;
-    if (s >= n_gpus || s == rank) return;      // this GPU's own chunks are ordered by the stream (events)
+    (void)rank;                                 // this GPU's own counts arrive through its own push kernel: wait for it too
+    if (s >= n_gpus) return;
     const volatile uint32_t* f = flags + (size_t)slot * n_gpus + s;
     const unsigned long long t0 = global_timer_ns();
     while ((int32_t)(*f - epoch) < 0) {

@@ -367,14 +367,22 @@ class GpuOps:
             eng.pcp_copy(w, peers[w], flags, nst[w], s)
             ev["copy"] = torch.cuda.Event(); ev["copy"].record(s)
             mark(f"{names[w]} copied (local kernels done)", s)
+        if not hasattr(self, "_pcp_result"):
+            self._pcp_result = torch.zeros(2, dtype=torch.int64, device=self.dev)
         for w in order:                                           # receiver side: only now, behind all source-side work
-            eng.pcp_recv(w, own_ptrs[w], flags[rank], caps[w], rcv[w])
+            eng.pcp_recv(w, own_ptrs[w], flags[rank], caps[w], rcv[w], result_out=self._pcp_result if w != first else None)
             mark(f"{names[w]} received" + (" and joined" if w != first else ""), rcv[w])
+        # the global aggregate: all-reduce of the local {matches, checksum} right behind the last join, on its
+        # stream (int64 two's-complement add = addition mod 2^64); the host blocks once, in pcp_finish
+        with torch.cuda.stream(rcv[order[1]]):
+            dist.all_reduce(self._pcp_result, group=group)
+            self._pcp_global = self._pcp_result.to("cpu", non_blocking=True)
         m, c, n_r, n_s, ph, bits = eng.pcp_finish()
         for s in self._pcp_streams:
             s.synchronize()
         ph = dict(ph, shuffle_scatter_ms=ph["copy_R_ms"] + ph["copy_S_ms"], radix_bits=B, pass1_bits=bits[0] + bits[1],
-                  pass2_bits=bits[2], stages=[nst[0], nst[1]])
+                  pass2_bits=bits[2], stages=[nst[0], nst[1]],
+                  global_result=[int(x) & 0xFFFFFFFFFFFFFFFF for x in self._pcp_global.tolist()])
         if trace is not None:
             torch.cuda.synchronize(self.device)
             ph["trace_ms"] = {n: round(trace[0][1].elapsed_time(e), 3) for n, e in trace[1:]}
@@ -448,8 +456,9 @@ class ShardedJoin:
         # receive buffers must be plain cudaMalloc allocations to be exportable
         self._own = []
         handles = []
-        flag_bytes = 2 * 64 * self.world * 4     # pcp stage flags: [relation][stage][source] uint32
-        for which, nbytes in enumerate(((ops.cap_R + 16) * 8, (ops.cap_S + 16) * 8, flag_bytes)):
+        from .engine import pcp_ctrl_bytes
+        ctrl_bytes = pcp_ctrl_bytes(self.world)   # pcp control block: stage flags + the fine histograms the sources deliver
+        for which, nbytes in enumerate(((ops.cap_R + 16) * 8, (ops.cap_S + 16) * 8, ctrl_bytes)):
             p = C.c_void_p()
             _check(L.gj_malloc_device(C.byref(p), nbytes))
             if which == 2:
@@ -461,7 +470,7 @@ class ShardedJoin:
             handles.append(h.raw)
         gathered = [None] * self.world
         self.dist.all_gather_object(gathered, handles, group=self.group)
-        self._peers = [[0] * self.world, [0] * self.world, [0] * self.world]    # R buffers, S buffers, flag buffers
+        self._peers = [[0] * self.world, [0] * self.world, [0] * self.world]    # R buffers, S buffers, control blocks
         self._opened = []
         for r in range(self.world):
             for which in range(3):
@@ -501,7 +510,9 @@ class ShardedJoin:
         t_host = [time.perf_counter()]
         lap = lambda: t_host.append(time.perf_counter())  # noqa: E731
         B = self.plan_bits(min(n_R_global, n_S_global))
-        ops.configure(B, self.gpu_bits)
+        if getattr(self, "_configured", None) != (B, self.gpu_bits):
+            ops.configure(B, self.gpu_bits)
+            self._configured = (B, self.gpu_bits)
         shift = B
         rels = ((Rk, Rp), (Sk, Sp))
         local_n = [0, 0]
@@ -562,9 +573,12 @@ class ShardedJoin:
             m, c, tm = ops.local_join(local_n[0], local_n[1])
         if self.mode not in ("pp", "pcp"):
             lap()
-        res = ops.result_tensor(m, c)
-        dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
-        vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
+        if isinstance(tm, dict) and "global_result" in tm:      # pcp: already all-reduced on the device, behind the last join
+            vals = tm.pop("global_result")
+        else:
+            res = ops.result_tensor(m, c)
+            dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
+            vals = [int(x) & 0xFFFFFFFFFFFFFFFF for x in res.tolist()]
         lap()
         if self.mode in ("pp", "pcp"):
             d = [1e3 * (b - a) for a, b in zip(t_host, t_host[1:])]

@@ -23,7 +23,7 @@ C_ABI_SYMBOLS = [
     "gj_join_materialize", "gj_join_aggregate_late", "gj_join_aggregate_nopart", "gj_join_aggregate_perfect", "gj_join_aggregate_stream_host", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
     "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_stage_pass_ms", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
-    "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv",
+    "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv", "gj_pcp_ctrl_bytes",
     "gj_pcp_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
     "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_memset_device", "gj_device_synchronize", "gj_flush_l2",
@@ -119,7 +119,9 @@ def lib() -> C.CDLL:
     L.gj_pcp_hist.argtypes = [vp, C.c_int, i32p, u64, vp, vp]
     L.gj_pcp_part.argtypes = [vp, C.c_int, i32p, i32p, vp, vp, u64, vp]
     L.gj_pcp_copy.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), u32, vp]
-    L.gj_pcp_recv.argtypes = [vp, C.c_int, vp, vp, u64, vp]
+    L.gj_pcp_recv.argtypes = [vp, C.c_int, vp, vp, u64, vp, vp]
+    L.gj_pcp_ctrl_bytes.argtypes = [u32]
+    L.gj_pcp_ctrl_bytes.restype = u64
     L.gj_pcp_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(u32)]
     L.gj_generate_unique.argtypes = [vp, i32p, i32p, u64, u64, u64, u32, u32]
     L.gj_bijection.argtypes = [u64, u64, u32]
@@ -143,6 +145,11 @@ def lib() -> C.CDLL:
 def _check(rc: int):
     if rc != 0:
         raise GJError(rc, lib().gj_last_error().decode(errors="replace"))
+
+
+def pcp_ctrl_bytes(n_gpus: int) -> int:
+    """Size of one GPU's pcp control block (stage flags + delivered fine histograms)."""
+    return int(lib().gj_pcp_ctrl_bytes(n_gpus))
 
 
 def kernel_launch_count() -> int:
@@ -465,13 +472,15 @@ class JoinEngine:
         _check(self._L.gj_pcp_part(self._ctx, which, _dev_ptr(keys, n, "keys"), _dev_ptr(pays, n, "pays"),
                                    C.c_void_p(all_hist.data_ptr()), C.c_void_p(own_ptr), cap_tuples, self._sptr(stream)))
 
-    def pcp_copy(self, which: int, peer_ptrs, peer_flag_ptrs, n_stages: int = 1, stream=None):
+    def pcp_copy(self, which: int, peer_ptrs, peer_ctrl_ptrs, n_stages: int = 1, stream=None):
         bases = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
-        flags = (C.c_void_p * len(peer_flag_ptrs))(*[C.c_void_p(int(p)) for p in peer_flag_ptrs])
-        _check(self._L.gj_pcp_copy(self._ctx, which, bases, flags, n_stages, self._sptr(stream)))
+        ctrl = (C.c_void_p * len(peer_ctrl_ptrs))(*[C.c_void_p(int(p)) for p in peer_ctrl_ptrs])
+        _check(self._L.gj_pcp_copy(self._ctx, which, bases, ctrl, n_stages, self._sptr(stream)))
 
-    def pcp_recv(self, which: int, own_ptr: int, own_flags_ptr: int, cap_tuples: int, stream=None):
-        _check(self._L.gj_pcp_recv(self._ctx, which, C.c_void_p(own_ptr), C.c_void_p(own_flags_ptr), cap_tuples, self._sptr(stream)))
+    def pcp_recv(self, which: int, own_ptr: int, own_ctrl_ptr: int, cap_tuples: int, stream=None, result_out=None):
+        """result_out: optional int64 CUDA tensor of >= 2 elements receiving the local {matches, checksum}."""
+        _check(self._L.gj_pcp_recv(self._ctx, which, C.c_void_p(own_ptr), C.c_void_p(own_ctrl_ptr), cap_tuples,
+                                   C.c_void_p(result_out.data_ptr() if result_out is not None else 0), self._sptr(stream)))
 
     def pcp_finish(self, phases: bool = True):
         """Returns (matches, checksum, tuples received of R, of S, phase_ms dict, (gpu bits, source bits, receiver bits))."""

@@ -271,19 +271,25 @@ int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bits);
  *   gj_pcp_part  layout + first radix pass: remote chunks into the context's stage buffer, this GPU's
  *                own chunks straight into its receive buffer d_own (never copied);
  *   gj_pcp_copy  n_stages x (TMA bulk-copy kernel: every remote chunk of the group to its slot in the
- *                destination's receive buffer peer_bases[g] (16-byte aligned, cap_tuples + 16 tuples);
- *                then this source's flag word in every peer's flag buffer peer_flags[g]);
+ *                destination's receive buffer peer_bases[g] (16-byte aligned, cap_tuples + 16 tuples),
+ *                its histogram warps counting every piece by the receiver-side radix bits while it sits
+ *                in shared memory; then those counts and this source's flag word into every GPU's
+ *                control block peer_ctrl[g]);
  *   gj_pcp_recv  per stage: wait until every source's flag arrived (bounded by option
  *                "pcp_timeout_ms", default 5000: then GJ_ERR_STATE from gj_pcp_finish, never a hang),
- *                histogram + LAST radix pass over the group in d_own; for the probing relation also the
- *                join of the group.  Call it on a stream other than gj_pcp_copy's so that receiving
- *                overlaps this GPU's own sending; the building relation must be received first.
+ *                sum the delivered counts (the receiver never re-reads the data to count it), LAST
+ *                radix pass over the group in d_own; for the probing relation also the join of the
+ *                group, and at the end the local {matches, checksum} into d_result_out (2 x uint64 on
+ *                the device, optional: the input of the caller's all-reduce).  Call it on a stream other
+ *                than gj_pcp_copy's so that receiving overlaps this GPU's own sending; the building
+ *                relation must be received first.
  *   gj_pcp_finish synchronises; local aggregate, tuples received, phase_ms[7] = part R, copy R,
  *                recv R, part S, copy S, recv S, tail (last byte of the probing relation landed ->
  *                last join done); plan_bits[3] = gpu bits, source-side local bits, receiver-side bits.
- * Flag buffers: 2 * 64 * n_gpus uint32 per GPU, zeroed once (gj_malloc_device + gj_memset_device), laid out
- * [relation][stage][source]; a flag holds the join number (epoch) of the last completed stage, so it
- * never needs resetting.  Option "pcp_copy_ctas": see gj_set_option.
+ * Control block: gj_pcp_ctrl_bytes(n_gpus) bytes per GPU, 16-byte aligned, zeroed once (gj_malloc_device +
+ * gj_memset_device): stage flags [relation][stage][source] uint32 -- a flag holds the join number (epoch)
+ * of the last completed stage, so it never needs resetting -- followed by the delivered fine histograms
+ * [relation][source][2^local_bits] uint32.  Option "pcp_copy_ctas": see gj_set_option.
  * n + 2^(g + bl) must not exceed the context capacity (one spare stage slot per chunk). */
 int gj_pcp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
                  uint32_t local_bits, void* cuda_stream);
@@ -292,10 +298,11 @@ int gj_pcp_hist(gj_ctx* ctx, int which, const int32_t* d_keys, uint64_t n, uint3
                 void* cuda_stream);
 int gj_pcp_part(gj_ctx* ctx, int which, const int32_t* d_keys, const int32_t* d_pays,
                 const uint32_t* d_all_hist, void* d_own, uint64_t cap_tuples, void* cuda_stream);
-int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* const* peer_flags, uint32_t n_stages,
+int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* const* peer_ctrl, uint32_t n_stages,
                 void* cuda_stream);
-int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, const void* d_flags, uint64_t cap_tuples,
-                void* cuda_stream);
+int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, const void* d_ctrl, uint64_t cap_tuples,
+                void* d_result_out, void* cuda_stream);
+uint64_t gj_pcp_ctrl_bytes(uint32_t n_gpus);
 int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
                   uint64_t* n_local_S, float* phase_ms, uint32_t* plan_bits);
 

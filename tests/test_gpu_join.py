@@ -575,7 +575,7 @@ def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, o
     engs = [gj.JoinEngine(mx[0], mx[1], 0, **(opts or {})) for _ in range(G)]
     try:
         own = [[torch.zeros(caps[w] + 16, dtype=torch.int64, device="cuda") for _ in range(G)] for w in range(2)]
-        flags = [torch.zeros(2 * 64 * G, dtype=torch.int32, device="cuda") for _ in range(G)]
+        flags = [torch.zeros(gj.pcp_ctrl_bytes(G) // 4, dtype=torch.int32, device="cuda") for _ in range(G)]   # control blocks
         cols = [[dev(torch, rels[w][0][splits[w][r]:splits[w][r + 1]], rels[w][1][splits[w][r]:splits[w][r + 1]])
                  for r in range(G)] for w in range(2)]
         order = (1, 0) if n[0] > n[1] else (0, 1)          # the building (smaller) relation travels first
