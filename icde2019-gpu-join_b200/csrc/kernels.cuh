@@ -1423,12 +1423,35 @@ join_kernel(JoinArgs a) {
                     const bool live = (w[q] & HEAD_VER_MASK) == ver;
                     r[q] = rbuf[live ? (w[q] & 0xFFFFu) : 0u];
                 }
+                if (LATE) {
+                    // the head-of-bucket hits of all KP tuples gather together: per side-table column the
+                    // thread issues its (up to KP) independent loads back to back before it adds them up, so
+                    // KP random HBM accesses are in flight per thread instead of one (the gathers, not the
+                    // join, are this kernel's cost: 4 x 32-byte sectors per result pair with 2 + 2 columns)
+                    bool hit[KP];
+#pragma unroll
+                    for (int q = 0; q < KP; ++q) hit[q] = (w[q] & HEAD_VER_MASK) == ver && r[q].x == t[q].x;
+                    for (uint32_t z = 0; z < a.ncols_bld; ++z) {
+                        int32_t v[KP];
+#pragma unroll
+                        for (int q = 0; q < KP; ++q) v[q] = hit[q] ? __ldg(a.bld_cols + (size_t)z * a.stride_bld + r[q].y) : 0;
+#pragma unroll
+                        for (int q = 0; q < KP; ++q) sum += (unsigned long long)(long long)v[q];
+                    }
+                    for (uint32_t z = 0; z < a.ncols_prb; ++z) {
+                        int32_t v[KP];
+#pragma unroll
+                        for (int q = 0; q < KP; ++q) v[q] = hit[q] ? __ldg(a.prb_cols + (size_t)z * a.stride_prb + t[q].y) : 0;
+#pragma unroll
+                        for (int q = 0; q < KP; ++q) sum += (unsigned long long)(long long)v[q];
+                    }
+                }
 #pragma unroll
                 for (int q = 0; q < KP; ++q) {
                     if ((w[q] & HEAD_VER_MASK) == ver) {
                         if (r[q].x == t[q].x) {
                             ++m32;
-                            sum += pair_value<LATE>(a, r[q].y, t[q].y);
+                            if (!LATE) sum += pair_value<false>(a, r[q].y, t[q].y);
                         }
                         if (w[q] & HEAD_MULTI) {
                             for (uint32_t i = next[w[q] & 0xFFFFu]; i != 0xFFFFu; i = next[i]) {

@@ -415,7 +415,8 @@ class ShardedJoin:
     with its local shard (device int32 columns) and all ranks get the global result."""
 
     def __init__(self, max_local_R: int, max_local_S: int, device: int | None = None, group=None,
-                 mode: str = "auto", ops=None, part_target: int = 4096, overlap: bool = True, pcp_stages=(2, 4)):
+                 mode: str = "auto", ops=None, part_target: int = 4096, overlap: bool = True, pcp_stages=(2, 4),
+                 slack: float = 1.3):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -430,7 +431,10 @@ class ShardedJoin:
         self.overlap = overlap
         self.pcp_stages = tuple(pcp_stages)     # copy / receive stages of the building and of the probing relation
         self.part_target = part_target
-        self.ops = ops if ops is not None else GpuOps(max_local_R, max_local_S, device,
+        # slack = capacity of a GPU's receive buffers relative to an even split.  A skewed probe side sends one
+        # GPU more than its share (Zipf z = 1 at 8 GPUs: 1/8 + 5.2 % of S = 1.42x): the exchange refuses up front
+        # (every rank sees the same histograms) when a destination would overflow -- size the slack for the skew.
+        self.ops = ops if ops is not None else GpuOps(max_local_R, max_local_S, device, slack=slack,
                                                       with_send_buffers=(mode in ("nccl", "dma")))
         self.max_local = (max_local_R, max_local_S)
         self._peers = None
