@@ -748,7 +748,7 @@ def multi_gpu(args):
                             "receiver_pass_bits": tm.get("pass2_bits"), "stages_build_probe": list(stages)}
             line["shuffle"].update({"copy_kernels_ms": copy_ms, "nvlink_out_GBs_per_gpu": 8.0 * sent / (copy_ms * 1e-3) / 1e9,
                                     "nvlink_busy_frac_of_step": copy_ms / ms_step,
-                                    "hbm_bytes_per_tuple": 4 + 16 + 16.0 * (world - 1) / world + 8 + 16 + 8,
+                                    "hbm_bytes_per_tuple": 4 + 16 + 8.0 / world + 16.0 * (world - 1) / world + 16 + 8,   # coarse hist, source pass, own-chunk counts, copy out + landing, receiver pass, join
                                     "note": "partition-copy-partition, streamed: first radix pass at the source on [gpu | top local bits] (own chunks "
                                             "straight into the receive buffer), whole first-pass partitions bulk-copied in stages (TMA, global->shared->"
                                             "peer global) with a flag store into every peer after each stage; the receiver partitions and joins a stage "

@@ -2197,6 +2197,18 @@ extern "C" int gj_generate_unique(gj_ctx* ctx, int32_t* d_keys, int32_t* d_pays,
 extern "C" uint32_t gj_bijection(uint64_t row, uint64_t n_total, uint32_t seed) { return bijection(row, n_total, seed); }
 extern "C" int32_t gj_payload_of_key(uint32_t key, uint32_t pay_seed) { return payload_of_key(key, pay_seed); }
 
+// One process driving several GPUs (tests, profiling with ncu): let kernels on `device` dereference `peer`'s memory.
+extern "C" int gj_enable_peer_access(int device, int peer) {
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return fail(GJ_ERR_CUDA, "device %d cannot access device %d", device, peer);
+    CK(cudaSetDevice(device));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(GJ_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer, cudaGetErrorString(e));
+    cudaGetLastError();
+    return GJ_OK;
+}
+
 extern "C" int gj_device_count(int* n) {
     if (!n) return fail(GJ_ERR_ARG, "NULL argument");
     CK(cudaGetDeviceCount(n));

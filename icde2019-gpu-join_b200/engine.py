@@ -24,7 +24,7 @@ C_ABI_SYMBOLS = [
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
     "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_stage_pass_ms", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
     "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv", "gj_pcp_ctrl_bytes",
-    "gj_pcp_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
+    "gj_pcp_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_enable_peer_access", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
     "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_memset_device", "gj_device_synchronize", "gj_flush_l2",
     "gj_kernel_launch_count",
@@ -128,6 +128,7 @@ def lib() -> C.CDLL:
     L.gj_bijection.restype = u32
     L.gj_payload_of_key.argtypes = [u32, u32]
     L.gj_payload_of_key.restype = C.c_int32
+    L.gj_enable_peer_access.argtypes = [C.c_int, C.c_int]
     L.gj_device_count.argtypes = [C.POINTER(C.c_int)]
     L.gj_malloc_device.argtypes = [C.POINTER(vp), u64]
     L.gj_free_device.argtypes = [vp]

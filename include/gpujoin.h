@@ -312,6 +312,8 @@ int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* 
 int gj_ipc_export(void* d_ptr, char handle[64]);
 int gj_ipc_open(const char handle[64], void** d_ptr);
 int gj_ipc_close(void* d_ptr);
+/* One process driving several GPUs (tests, ncu): let kernels on `device` dereference `peer`'s memory. */
+int gj_enable_peer_access(int device, int peer);
 
 /* Per-destination histogram only (what ranks exchange before gj_shuffle_scatter_peers). */
 int gj_shuffle_count(gj_ctx* ctx, const int32_t* d_keys, uint64_t n, uint32_t n_gpus,
