@@ -349,7 +349,9 @@ struct PlanArgs {
 
 __global__ void __launch_bounds__(PLAN_THREADS)
 plan_kernel(PlanArgs a) {
-    __shared__ uint32_t s_tp[NB_MAX + 1], s_a0[NB_MAX], s_warp[PLAN_THREADS / 32];
+    // 16-byte aligned and padded: the compiler reads s_warp with 128-bit loads, which otherwise also touch the
+    // neighbouring array's last word (harmless, but racecheck reports it)
+    __shared__ __align__(16) uint32_t s_tp[NB_MAX + 4], s_a0[NB_MAX], s_warp[PLAN_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t gtid = blockIdx.x * PLAN_THREADS + tid, gsz = gridDim.x * PLAN_THREADS;
     const uint32_t B = a.b1 + a.b2, nb = 1u << B, n1 = 1u << a.b1;
