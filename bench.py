@@ -641,7 +641,8 @@ def multi_gpu(args):
     n5 = WORKLOADS["cfg5"][0] // world
     with_cfg5 = (w == "B" and not args.no_cfg5)
     capn = max(nR, n5) if with_cfg5 else nR
-    sj = gj.distributed.ShardedJoin(capn, capn, device=local, mode=args.shuffle, overlap=not args.no_overlap, pcp_stages=stages)
+    sj = gj.distributed.ShardedJoin(capn, capn, device=local, mode=args.shuffle, overlap=not args.no_overlap, pcp_stages=stages,
+                                    pcp_peer_hist=args.pcp_peer_hist)
     for kv in args.opt:
         k, v = kv.split("=")
         sj.ops.engine.set_option(k, int(v))
@@ -781,6 +782,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
+    ap.add_argument("--pcp-peer-hist", action="store_true", help="pcp: coarse histograms through the peers' control blocks instead of an NCCL all-gather")
     ap.add_argument("--pcp-stages", default="2,4", help="pcp: copy/receive stages of the building and of the probing relation")
     ap.add_argument("--shuffle", default="auto", choices=["auto", "p2p", "nccl", "dma", "pp", "pcp"],
                     help="multi-GPU exchange: pp = partition locally, last radix pass pushes into the peers; p2p = peer-store "

@@ -665,7 +665,9 @@ static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup
     uint64_t grid = (uint64_t)ctx->sm_count;   // persistent: one CTA per SM owns the whole shared memory
     if (ctx->opt_join_grid) grid = (uint64_t)ctx->opt_join_grid;
     const uint64_t max_units = n_prb / unit_tuples(ctx) + (1ull << pl.B);
-    grid = std::max<uint64_t>(1, std::min(grid, max_units));
+    // probe partitions of several units (measured on workload A: 8 units each): blocks of consecutive units per CTA
+    a.unit_block = (n_prb / unit_tuples(ctx)) > (3ull << pl.B) / 2 ? JOIN_UNIT_BLOCK : 1u;
+    grid = std::max<uint64_t>(1, std::min(grid, (max_units + a.unit_block - 1) / a.unit_block));
     (late ? kJoinLate : (mat ? jc.mat : jc.agg))<<<(uint32_t)grid, jc.threads, smem, s>>>(a);
     LAUNCHED();
     return GJ_OK;
@@ -1961,7 +1963,33 @@ extern "C" int gj_pcp_part(gj_ctx* ctx, int which, const int32_t* d_keys, const 
     return GJ_OK;
 }
 
-extern "C" uint64_t gj_pcp_ctrl_bytes(uint32_t n_gpus) { return pcp_ctrl_bytes(n_gpus, MAX_RADIX_BITS); }
+extern "C" uint64_t gj_pcp_ctrl_bytes(uint32_t n_gpus) { return pcp_ctrl_bytes(n_gpus); }
+
+// Exchange of the coarse histograms through the peers' control blocks instead of a collective: push this shard's
+// histogram (gj_pcp_hist's output) into every GPU's block, wait (bounded) for every source's, compact them into
+// d_all_hist ([n_gpus][2^(g + bl)], the input of gj_pcp_part).  Stream-ordered; replaces the caller's all-gather.
+extern "C" int gj_pcp_hist_exchange(gj_ctx* ctx, int which, const uint32_t* d_coarse_hist, void* const* peer_ctrl,
+                                    const void* d_ctrl, uint32_t* d_all_hist, void* cuda_stream) {
+    if (!ctx || !ctx->pcp.active) return fail(GJ_ERR_STATE, "gj_pcp_begin first");
+    if (which != 0 && which != 1) return fail(GJ_ERR_ARG, "which must be 0 (R) or 1 (S)");
+    if (!d_coarse_hist || !peer_ctrl || !d_ctrl || !d_all_hist) return fail(GJ_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    gj_ctx::PCP& q = ctx->pcp;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    void** hb = reinterpret_cast<void**>(q.h_pin) + (size_t)which * 2 * NB_MAX;
+    for (uint32_t g = 0; g < q.G; ++g) {
+        if (!peer_ctrl[g] || ((size_t)peer_ctrl[g] & 15u)) return fail(GJ_ERR_ARG, "control block %u must be non-NULL and 16-byte aligned", g);
+        hb[NB_MAX + g] = peer_ctrl[g];
+    }
+    CK(cudaMemcpyAsync(q.ctrl_ptrs[which], hb + NB_MAX, q.G * sizeof(void*), cudaMemcpyHostToDevice, s));
+    const uint32_t n1 = 1u << q.b1;
+    pcp_hist_push_kernel<<<q.G, 256, 0, s>>>(d_coarse_hist, q.ctrl_ptrs[which], q.G, q.rank, (uint32_t)which, n1, q.epoch);
+    LAUNCHED();
+    pcp_hist_gather_kernel<<<q.G, 256, 0, s>>>((const unsigned char*)d_ctrl, q.G, (uint32_t)which, n1, q.epoch,
+                                               (unsigned long long)ctx->opt_pcp_timeout_ms * 1000000ull, d_all_hist, q.tab[which].status);
+    LAUNCHED();
+    return GJ_OK;
+}
 
 extern "C" int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* const* peer_ctrl, uint32_t n_stages,
                            void* cuda_stream) {

@@ -600,11 +600,17 @@ pp_cursor_kernel(const uint32_t* __restrict__ all_hist, uint32_t n_gpus, uint32_
 // ------------------------------------------------------------------------------------------
 constexpr int PCP_MAX_CHUNKS = 1024;
 constexpr int PCP_MAX_STAGES = 64;
+constexpr int MAX_RADIX_BITS_CTRL = 16;
 constexpr uint32_t PCP_PIECE = 4096;     // tuples per bulk copy (32 KB), even
 // per-GPU control block (peer-mapped): stage flags [relation][stage][source] uint32, then the fine
 // histograms the sources deliver, fine_in [relation][source][2^B] uint32
 __host__ __device__ __forceinline__ size_t pcp_ctrl_flag_bytes(uint32_t n_gpus) { return (size_t)2 * PCP_MAX_STAGES * n_gpus * sizeof(uint32_t); }
-__host__ __device__ __forceinline__ size_t pcp_ctrl_bytes(uint32_t n_gpus, uint32_t B) { return pcp_ctrl_flag_bytes(n_gpus) + (((size_t)2 * n_gpus) << B) * sizeof(uint32_t); }
+__host__ __device__ __forceinline__ size_t pcp_ctrl_fine_bytes(uint32_t n_gpus, uint32_t B) { return (((size_t)2 * n_gpus) << B) * sizeof(uint32_t); }
+// ... then (at the offset for the largest B) the coarse histograms the sources deliver before the source pass,
+// coarse_in [relation][source][PCP_MAX_CHUNKS] uint32, and their flags [relation][source]
+__host__ __device__ __forceinline__ size_t pcp_ctrl_coarse_off(uint32_t n_gpus) { return pcp_ctrl_flag_bytes(n_gpus) + pcp_ctrl_fine_bytes(n_gpus, MAX_RADIX_BITS_CTRL); }
+__host__ __device__ __forceinline__ size_t pcp_ctrl_hflag_off(uint32_t n_gpus) { return pcp_ctrl_coarse_off(n_gpus) + (size_t)2 * n_gpus * PCP_MAX_CHUNKS * sizeof(uint32_t); }
+__host__ __device__ __forceinline__ size_t pcp_ctrl_bytes(uint32_t n_gpus) { return pcp_ctrl_hflag_off(n_gpus) + (size_t)2 * n_gpus * sizeof(uint32_t) + 64; }
 struct PcpTables {                       // device arrays of n1 (+1) entries
     uint32_t* cur;                       // pass-1 cursors (consumed by the scatter), relative to dig_base[c]
     tup_t** dig_base;                    // pass-1 output base of chunk c: the stage buffer, or this GPU's receive buffer
@@ -899,6 +905,25 @@ pcp_sum_hist_kernel(const unsigned char* __restrict__ ctrl, uint32_t n_gpus, uin
     }
 }
 
+// Exchange of the coarse histograms WITHOUT a collective (option "pcp_peer_hist"): every source writes its 2^b1
+// counters into every GPU's control block and raises a flag; pcp_hist_gather_kernel waits for all sources (bounded)
+// and compacts them into the dense [n_gpus][2^b1] array the layout kernel reads.  ~15 us against ~110 us for an
+// 8-rank NCCL all-gather of 2 KB -- on the critical path of the building relation.
+__global__ void __launch_bounds__(256)
+pcp_hist_push_kernel(const uint32_t* __restrict__ coarse, unsigned char* const* __restrict__ peer_ctrl, uint32_t n_gpus,
+                     uint32_t rank, uint32_t which, uint32_t n1, uint32_t epoch) {
+    unsigned char* ctrl = peer_ctrl[blockIdx.x];
+    uint32_t* dst = reinterpret_cast<uint32_t*>(ctrl + pcp_ctrl_coarse_off(n_gpus)) + ((size_t)which * n_gpus + rank) * PCP_MAX_CHUNKS;
+    for (uint32_t c = threadIdx.x; c < n1; c += 256) dst[c] = coarse[c];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        volatile uint32_t* f = reinterpret_cast<uint32_t*>(ctrl + pcp_ctrl_hflag_off(n_gpus)) + (size_t)which * n_gpus + rank;
+        *f = epoch;
+    }
+}
+
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -919,6 +944,24 @@ __global__ void pcp_wait_kernel(const uint32_t* __restrict__ flags, uint32_t n_g
         __nanosleep(200);
     }
     __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256)
+pcp_hist_gather_kernel(const unsigned char* __restrict__ ctrl, uint32_t n_gpus, uint32_t which, uint32_t n1, uint32_t epoch,
+                       unsigned long long timeout_ns, uint32_t* __restrict__ all_hist, uint32_t* __restrict__ status) {
+    const uint32_t s = blockIdx.x;       // one CTA per source
+    const volatile uint32_t* f = reinterpret_cast<const uint32_t*>(ctrl + pcp_ctrl_hflag_off(n_gpus)) + (size_t)which * n_gpus + s;
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = global_timer_ns();
+        while ((int32_t)(*f - epoch) < 0) {
+            if (global_timer_ns() - t0 > timeout_ns) { atomicExch(&status[3], 1u); break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const volatile uint32_t* src = reinterpret_cast<const uint32_t*>(ctrl + pcp_ctrl_coarse_off(n_gpus)) + ((size_t)which * n_gpus + s) * PCP_MAX_CHUNKS;
+    for (uint32_t c = threadIdx.x; c < n1; c += 256) all_hist[(size_t)s * n1 + c] = src[c];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1147,8 +1190,8 @@ scatter_kernel(ScatterArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// 5. Per-partition hash join: persistent CTAs (one per SM), static round-robin over the unit
-//    list, fed by TMA bulk copies into two shared-memory rings.
+// 5. Per-partition hash join: persistent CTAs (one per SM), blocks of 8 consecutive units dealt round
+//    robin, fed by TMA bulk copies into two shared-memory rings.
 //    A unit {probe range, build partition} is processed in steps of (build chunk <= CAP tuples)
 //    x (probe chunk <= U tuples).  A dedicated LOADER WARP (one lane) runs an iterator ahead of
 //    the consumer warps and issues bulk async copies (cp.async.bulk, completion on "full"
@@ -1180,6 +1223,7 @@ struct JoinArgs {
     const tup_t* bld; const tup_t* prb;     // partitioned tuples (16-byte aligned, +2 slack)
     const uint4* units; const uint32_t* num_units;
     uint32_t hash_shift;
+    uint32_t unit_block;          // consecutive units a CTA takes at a time (1 or JOIN_UNIT_BLOCK)
     unsigned long long* result;   // [0] matches [1] checksum [2] pairs reserved (materialise)
     int32_t* out_bld_pay; int32_t* out_prb_pay; unsigned long long cap;
     // LATE (late materialisation, join_partitioned_varpayload, join-primitives.cu:1420-1557): payloads are row
@@ -1202,6 +1246,7 @@ __device__ __forceinline__ unsigned long long pair_value(const JoinArgs& a, uint
 
 constexpr int JOIN_STAGE_PAIRS = 4096;   // staged result pairs per CTA (materialise): 32 KB
 constexpr uint32_t STEP_DONE = 0xFFFFFFFFu;
+constexpr uint32_t JOIN_UNIT_BLOCK = 8;   // consecutive units a CTA takes at a time when probe partitions span several units
 // head word = MULTI(1) | version(15) | entry index(16).  A head is live only if its version equals
 // the current build chunk's, so the table is never cleared between chunks.
 constexpr uint32_t HEAD_MULTI = 0x80000000u;   // bucket holds more than one entry
@@ -1262,12 +1307,24 @@ join_kernel(JoinArgs a) {
         // ================= loader warp: one lane walks (unit, build chunk, probe chunk) ahead of
         // the consumers and feeds the rings; it never touches a tuple =================
         if (tid == NC) {
-            uint32_t it_u = blockIdx.x;
-            bool it_valid = it_u < nunits;
+            // This CTA's units: blocks of a.unit_block consecutive units, dealt round robin.  With probe partitions
+            // of several units (workload A: 8) the host picks blocks of 8: further units of the same partition
+            // then share ONE load + build of its build chunk (unit-by-unit striding rebuilt it in every CTA), while
+            // a hot partition's hundreds of units still spread over all CTAs (whole contiguous ranges per CTA
+            // left the hot ranges to a few: measured slower under Zipf).  With one unit per partition (workload B)
+            // blocks of 1 = plain striding: all CTAs stream one contiguous window of both relations.
+            const uint32_t ub = a.unit_block;
+            auto next_unit = [&](uint32_t u) -> uint32_t {
+                const uint32_t v = u + 1u;
+                return (v % ub) ? v : (u / ub + gridDim.x) * ub;
+            };
+            uint32_t it_u = blockIdx.x * ub;
+            const uint32_t it_end = nunits;
+            bool it_valid = it_u < it_end;
             uint4 it_d = make_uint4(0, 0, 0, 0), it_dn = make_uint4(0, 0, 0, 0);
             if (it_valid) {
                 it_d = __ldg(a.units + it_u);
-                if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
+                if (next_unit(it_u) < it_end) it_dn = __ldg(a.units + next_unit(it_u));
             }
             uint32_t it_rc = it_d.z, it_sc = it_d.x;
             uint32_t chunks = 0;          // build chunks issued so far
@@ -1293,12 +1350,12 @@ join_kernel(JoinArgs a) {
                     it_rc += CAP;
                     lastc = true;
                     if (it_rc >= it_d.w) {
-                        it_u += gridDim.x;
-                        it_valid = it_u < nunits;
+                        it_u = next_unit(it_u);
+                        it_valid = it_u < it_end;
                         const uint4 prev = it_d;
                         it_d = it_dn;                               // prefetched one unit ahead
                         it_rc = it_d.z; it_sc = it_d.x;
-                        if (it_u + gridDim.x < nunits) it_dn = __ldg(a.units + it_u + gridDim.x);
+                        if (it_valid && next_unit(it_u) < it_end) it_dn = __ldg(a.units + next_unit(it_u));
                         // consecutive units of one (hot) partition share a single-chunk build side
                         if (it_valid && it_d.z == prev.z && it_d.w == prev.w && prev.w - prev.z <= (uint32_t)CAP) lastc = false;
                     }

@@ -23,7 +23,7 @@ C_ABI_SYMBOLS = [
     "gj_join_materialize", "gj_join_aggregate_late", "gj_join_aggregate_nopart", "gj_join_aggregate_perfect", "gj_join_aggregate_stream_host", "gj_partition", "gj_shuffle_split", "gj_shuffle_scatter_peers",
     "gj_shuffle_count", "gj_shuffle_scatter_peers_async", "gj_shuffle_scatter_ms", "gj_memcpy_d2d_async", "gj_stage_begin",
     "gj_stage_partition", "gj_stage_join", "gj_stage_finish", "gj_stage_pass_ms", "gj_pp_begin", "gj_pp_local", "gj_pp_push", "gj_pp_join",
-    "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv", "gj_pcp_ctrl_bytes",
+    "gj_pp_finish", "gj_pp_plan", "gj_pcp_begin", "gj_pcp_plan", "gj_pcp_hist", "gj_pcp_part", "gj_pcp_copy", "gj_pcp_recv", "gj_pcp_ctrl_bytes", "gj_pcp_hist_exchange",
     "gj_pcp_finish", "gj_ipc_export", "gj_ipc_open", "gj_ipc_close", "gj_enable_peer_access", "gj_generate_unique", "gj_bijection", "gj_payload_of_key",
     "gj_device_count", "gj_malloc_device", "gj_free_device", "gj_malloc_pinned", "gj_free_pinned",
     "gj_memcpy_h2d", "gj_memcpy_d2h", "gj_memset_device", "gj_device_synchronize", "gj_flush_l2",
@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.gj_pcp_part.argtypes = [vp, C.c_int, i32p, i32p, vp, vp, u64, vp]
     L.gj_pcp_copy.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), u32, vp]
     L.gj_pcp_recv.argtypes = [vp, C.c_int, vp, vp, u64, vp, vp]
+    L.gj_pcp_hist_exchange.argtypes = [vp, C.c_int, vp, C.POINTER(vp), vp, vp, vp]
     L.gj_pcp_ctrl_bytes.argtypes = [u32]
     L.gj_pcp_ctrl_bytes.restype = u64
     L.gj_pcp_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(u32)]
@@ -467,6 +468,12 @@ class JoinEngine:
     def pcp_hist(self, which: int, keys, coarse_hist, stream=None):
         n = keys.numel()
         _check(self._L.gj_pcp_hist(self._ctx, which, _dev_ptr(keys, n, "keys"), n, C.c_void_p(coarse_hist.data_ptr()), self._sptr(stream)))
+
+    def pcp_hist_exchange(self, which: int, coarse_hist, peer_ctrl_ptrs, own_ctrl_ptr: int, all_hist, stream=None):
+        """Coarse histograms through the peers' control blocks (no collective): fills all_hist [G][2^(g+bl)]."""
+        ctrl = (C.c_void_p * len(peer_ctrl_ptrs))(*[C.c_void_p(int(p)) for p in peer_ctrl_ptrs])
+        _check(self._L.gj_pcp_hist_exchange(self._ctx, which, C.c_void_p(coarse_hist.data_ptr()), ctrl, C.c_void_p(own_ctrl_ptr),
+                                            C.c_void_p(all_hist.data_ptr()), self._sptr(stream)))
 
     def pcp_part(self, which: int, keys, pays, all_hist, own_ptr: int, cap_tuples: int, stream=None):
         n = keys.numel()

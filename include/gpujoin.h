@@ -289,7 +289,7 @@ int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bits);
  * Control block: gj_pcp_ctrl_bytes(n_gpus) bytes per GPU, 16-byte aligned, zeroed once (gj_malloc_device +
  * gj_memset_device): stage flags [relation][stage][source] uint32 -- a flag holds the join number (epoch)
  * of the last completed stage, so it never needs resetting -- followed by the delivered fine histograms
- * [relation][source][2^local_bits] uint32.  Option "pcp_copy_ctas": see gj_set_option.
+ * [relation][source][2^local_bits] uint32 and the coarse histograms + flags of gj_pcp_hist_exchange.  Option "pcp_copy_ctas": see gj_set_option.
  * n + 2^(g + bl) must not exceed the context capacity (one spare stage slot per chunk). */
 int gj_pcp_begin(gj_ctx* ctx, uint64_t n_R_global, uint64_t n_S_global, uint32_t n_gpus, uint32_t rank,
                  uint32_t local_bits, void* cuda_stream);
@@ -303,6 +303,11 @@ int gj_pcp_copy(gj_ctx* ctx, int which, void* const* peer_bases, void* const* pe
 int gj_pcp_recv(gj_ctx* ctx, int which, const void* d_own, const void* d_ctrl, uint64_t cap_tuples,
                 void* d_result_out, void* cuda_stream);
 uint64_t gj_pcp_ctrl_bytes(uint32_t n_gpus);
+/* Optional replacement of the caller's all-gather between gj_pcp_hist and gj_pcp_part: pushes this shard's coarse
+ * histogram into every GPU's control block, waits (bounded, "pcp_timeout_ms") for every source's, and compacts them
+ * into d_all_hist ([n_gpus][2^(g + bl)] uint32).  Stream-ordered, no collective library involved. */
+int gj_pcp_hist_exchange(gj_ctx* ctx, int which, const uint32_t* d_coarse_hist, void* const* peer_ctrl,
+                         const void* d_ctrl, uint32_t* d_all_hist, void* cuda_stream);
 int gj_pcp_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum, uint64_t* n_local_R,
                   uint64_t* n_local_S, float* phase_ms, uint32_t* plan_bits);
 

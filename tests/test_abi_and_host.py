@@ -141,6 +141,7 @@ def test_new_entry_points_reject_bad_calls_without_a_gpu(gj):
         (L.gj_pcp_part(null, 0, null, null, null, null, 0, null), GJ_ERR_STATE),
         (L.gj_pcp_copy(null, 0, None, None, 1, null), GJ_ERR_STATE),
         (L.gj_pcp_recv(null, 0, null, null, 0, null, null), GJ_ERR_STATE),
+        (L.gj_pcp_hist_exchange(null, 0, null, None, null, null, null), GJ_ERR_STATE),
         (L.gj_pcp_finish(null, None, None, None, None, None, None), GJ_ERR_STATE),
         (L.gj_join_aggregate_late(null, null, null, 0, null, null, 0, null, 0, 0, null, 0, 0, None, None, None), GJ_ERR_ARG),
         (L.gj_join_aggregate_nopart(null, null, null, 0, null, null, 0, None, None, None), GJ_ERR_ARG),

@@ -98,7 +98,7 @@ class NumpyOps:
         res = oracle.join_check(cols[0][0], cols[0][1], cols[1][0], cols[1][1], 1)
         return res.matches, res.checksum, local_n, {}
 
-    def pcp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob, flags=None, stages=(2, 4)):
+    def pcp_join(self, dist, group, rank, rels, G, B, peers, own_ptrs, n_glob, flags=None, stages=(2, 4), peer_hist=False):
         """Mode "pcp" without a GPU: coarse histograms with numpy, the real all-gather, the layout of
         distributed.pcp_layout (numpy model of pcp_layout_kernel), the chunk copies emulated by an
         all-to-all of (slot, tuple) pairs.  The receiver checks that the slots tile [0, total) exactly,

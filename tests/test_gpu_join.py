@@ -557,7 +557,8 @@ def test_pp_destination_overflow_is_reported(gj, orc, torch_cuda):
 
 
 # ------------------------------------------------------------------------------- sharded "partition, copy, partition"
-def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, opts=None, check_layout=True, stages=(1, 1)):
+def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, opts=None, check_layout=True, stages=(1, 1),
+                 peer_hist=False):
     """gj_pcp_* with G virtual ranks on ONE GPU (one engine context per rank, every 'peer' buffer and
     flag word local; the all-gather is a torch.stack).  stages = copy / receive stages of the building
     and of the probing relation."""
@@ -591,15 +592,24 @@ def _pcp_virtual(gj, orc, torch, G, B, Rk, Rp, Sk, Sp, splits=None, slack=1.6, o
         for r in range(G):
             for w in range(2):
                 engs[r].pcp_hist(w, cols[w][r][0], hist[w][r])
+        if peer_hist:      # gj_pcp_hist_exchange instead of a collective: every rank pushes, waits, compacts
+            allr = [[torch.full((G, n1), -1, dtype=torch.int32, device="cuda") for _ in range(G)] for w in range(2)]
+            for r in range(G):
+                for w in range(2):
+                    engs[r].pcp_hist_exchange(w, hist[w][r], [f.data_ptr() for f in flags], flags[r].data_ptr(), allr[w][r])
         torch.cuda.synchronize()
         allh = [torch.stack(hist[w]).contiguous() for w in range(2)]
+        if peer_hist:
+            for w in range(2):
+                for r in range(G):
+                    assert torch.equal(allr[w][r], allh[w])
         for w in range(2):
             for r in range(G):
                 k = rels[w][0][splits[w][r]:splits[w][r + 1]].view(np.uint32)
                 assert np.array_equal(hist[w][r].cpu().numpy(), np.bincount((k >> (B - bl)) & (n1 - 1), minlength=n1))
         for r in range(G):
             for w in order:
-                engs[r].pcp_part(w, cols[w][r][0], cols[w][r][1], allh[w], own[w][r].data_ptr(), caps[w])
+                engs[r].pcp_part(w, cols[w][r][0], cols[w][r][1], allr[w][r] if peer_hist else allh[w], own[w][r].data_ptr(), caps[w])
                 engs[r].pcp_copy(w, [t.data_ptr() for t in own[w]], [f.data_ptr() for f in flags], nst[w])
         torch.cuda.synchronize()
         # every receive buffer is first-pass partitioned: partition j of destination d holds exactly the
@@ -660,7 +670,8 @@ def test_pcp_virtual_shards(gj, orc, torch_cuda, G, B, p1):
         splits.append(np.concatenate(([0], cuts, [n])).astype(np.int64))
     stages = [(1, 1), (2, 4), (3, 5), (64, 64), (1, 7)][(G + B + p1) % 5]
     m, c, bits = _pcp_virtual(gj, orc, torch_cuda, G, B, Rk, Rp, Sk, Sp, splits=splits, opts={"pass1_bits": p1} if p1 else None,
-                              stages=stages)
+                              stages=stages, peer_hist=(G + B) % 2 == 0 and G <= 8)   # (one stream per virtual rank: beyond the 8 hardware
+                                                                                     # queues a spinning gather would block another rank's push)
     assert (m, c) == (want.matches, want.checksum)
     # the larger relation first in the argument list: the engine builds on (and ships first) the smaller one
     m2, c2, _ = _pcp_virtual(gj, orc, torch_cuda, G, B, Sk, Sp, Rk, Rp, splits=splits[::-1], opts={"pass1_bits": p1} if p1 else None,

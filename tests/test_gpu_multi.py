@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_local, mode, overlap, q):
+def _worker(rank, world, port, n_local, mode, overlap, q, peer_hist=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch
@@ -30,7 +30,7 @@ def _worker(rank, world, port, n_local, mode, overlap, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         N = n_local * world
-        sj = gj.distributed.ShardedJoin(n_local, n_local, device=rank, mode=mode, overlap=overlap)
+        sj = gj.distributed.ShardedJoin(n_local, n_local, device=rank, mode=mode, overlap=overlap, pcp_peer_hist=peer_hist)
         eng = sj.ops.engine
         mk = lambda: torch.empty(n_local, dtype=torch.int32, device=f"cuda:{rank}")  # noqa: E731
         Rk, Rp, Sk, Sp = mk(), mk(), mk(), mk()
@@ -49,7 +49,8 @@ def _worker(rank, world, port, n_local, mode, overlap, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,overlap", [("nccl", False), ("p2p", False), ("p2p", True), ("dma", True), ("pp", True), ("pcp", True)])
+@pytest.mark.parametrize("mode,overlap", [("nccl", False), ("p2p", False), ("p2p", True), ("dma", True), ("pp", True), ("pcp", True),
+                                          ("pcp-peer-hist", True)])
 def test_sharded_join_on_real_gpus(mode, overlap):
     import torch
     import torch.multiprocessing as mp
@@ -60,7 +61,9 @@ def test_sharded_join_on_real_gpus(mode, overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 6_000_000, mode, overlap, q)) for r in range(world)]
+    peer_hist = mode == "pcp-peer-hist"      # coarse histograms through the peers' control blocks, no all-gather
+    mode = "pcp" if peer_hist else mode
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 6_000_000, mode, overlap, q, peer_hist)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=600) for _ in range(world)]
