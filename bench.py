@@ -340,8 +340,8 @@ def reference_arm(args):
 
 
 CFG5_CACHE = os.path.join(tempfile.gettempdir(), "gj_cfg5_1gpu.json")
-CFG5_1GPU_MEASURED = {"value": 75.8e9, "ms_per_step": 52.8,
-                      "source": "profiles/r1_final/bench_1gpu_cfg5.log (round 1, same kernels)"}
+CFG5_1GPU_MEASURED = {"value": 75.28e9, "ms_per_step": 53.1,
+                      "source": "profiles/r2_final/bench.log, key config5 (round 2, same kernels; no 1-GPU run of this bench found on this box)"}
 
 
 def run_cfg5_share(torch, gj, n_gpus, rank, dev_index, sharded=None, steps=3, warm=1, opts=()):
@@ -741,8 +741,10 @@ def multi_gpu(args):
         if args.shuffle == "pcp" and tm.get("part_R_ms"):
             ph = {k: med(k) for k in ("part_R_ms", "copy_R_ms", "recv_R_ms", "part_S_ms", "copy_S_ms", "recv_S_ms", "tail_ms")}
             copy_ms = ph["copy_R_ms"] + ph["copy_S_ms"]
-            # dominant HBM kernel that runs ALONE: the source pass of the first relation (layout + first pass, 16 B/tuple)
-            line["roofline"].update({"kernel": "pcp source-side radix pass of R (layout + first pass, 16 B/tuple), rank 0",
+            # dominant HBM phase that runs ALONE: the source pass of the first relation (layout + first radix pass 16 B/tuple;
+            # the phase also holds the counting pass over the chunks this GPU keeps, 8 B/tuple over 1/N of them -- not
+            # credited, so the fraction is a lower bound)
+            line["roofline"].update({"kernel": "pcp source-side radix pass of R (layout + first pass 16 B/tuple [+ own-chunk counts, not credited]), rank 0",
                                      "achieved": 16.0 * nR / (ph["part_R_ms"] * 1e-3) / 1e9, "algorithmic_bytes_per_launch": 16.0 * nR,
                                      "local_phases_ms": ph})
             line["plan"] = {"gpu_bits": world.bit_length() - 1, "local_bits": tm.get("radix_bits"), "source_pass_bits": tm.get("pass1_bits"),

@@ -1804,13 +1804,15 @@ extern "C" int gj_pp_plan(gj_ctx* ctx, uint32_t* pass1_bits, uint32_t* pass2_bit
 // that builds (the globally smaller one) goes first.  Per relation:
 //   gj_pcp_hist : this shard's first-pass histogram on [gpu bits | top local bits] (2^b1 counters)
 //   [caller: all-gather of those histograms]
+//   [or gj_pcp_hist_exchange: the same exchange through the peers' control blocks, no collective]
 //   gj_pcp_part : layout (pcp_layout_kernel) + first radix pass: remote chunks into the stage buffer,
-//                 this GPU's own chunks straight into its receive buffer
-//   gj_pcp_copy : n_stages x (TMA bulk-copy kernel over a group of first-pass partitions, then a flag
-//                 store into every peer): every remote chunk to its slot in the destination's buffer
-//   gj_pcp_recv : per stage: wait for every source's flag, histogram + scan + plan + LAST radix pass
-//                 over the first-pass partitions of the stage; for the probing relation also unit
-//                 planning + join of those partitions -- while later stages still cross NVLink
+//                 this GPU's own chunks straight into its receive buffer (+ their fine counts)
+//   gj_pcp_copy : n_stages x (TMA bulk-copy kernel over a group of first-pass partitions, whose histogram
+//                 warps count every piece for the receiver's last pass; then those counts and a flag into
+//                 every peer's control block): every remote chunk to its slot in the destination's buffer
+//   gj_pcp_recv : per stage: wait for every source's flag, sum the delivered counts, scan + plan + LAST
+//                 radix pass over the first-pass partitions of the stage; for the probing relation also
+//                 unit planning + join of those partitions -- while later stages still cross NVLink
 //   gj_pcp_finish
 // Buffers: the first relation stages in ctx->scratch and ends in ctx->out[first]; the second stages
 // in ctx->out[second] and ends in ctx->scratch (free again once the first relation's copy is done,
@@ -1851,8 +1853,8 @@ static int ensure_pcp(gj_ctx* ctx) {
 
 static const PPCfg& pcp_last_cfg(uint32_t bits) { return kPcpLast[bits <= 7u ? 0u : bits - 7u]; }
 static int pcp_last_ctas_per_sm(uint32_t bits) { return bits <= 7u ? 4 : (bits <= 9u ? 2 : 1); }
-// SMs left to the kernels that run next to the copy kernel: with "shuffle_grid" = k <= half the SMs and
-// the deep ring, k SMs are filled by copy CTAs (196 KB of shared memory each) and host nothing else
+// SMs left to the kernels that run next to the copy kernel: with "pcp_copy_ctas" = k <= half the SMs (deep
+// ring), k SMs are filled by copy CTAs (196 KB of shared memory each) and host nothing else
 static bool pcp_deep_ring(const gj_ctx* ctx) { return ctx->opt_pcp_copy_ctas > 0 && ctx->opt_pcp_copy_ctas <= ctx->sm_count / 2; }
 static int pcp_free_sms(const gj_ctx* ctx) { return pcp_deep_ring(ctx) ? ctx->sm_count - (int)ctx->opt_pcp_copy_ctas : ctx->sm_count; }
 static tup_t* pcp_stage_buf(gj_ctx* ctx, int which) { return which == ctx->pcp.first ? ctx->scratch : ctx->out[which]; }

@@ -38,3 +38,23 @@ def test_config_is_a_function_of_workload_and_n():
     assert a == b and a["global_R"] == 8 * 128_000_000 and "8 GPUs" in a["parallelism"]
     assert bench.config_of("cfg5", 8)["per_gpu_R"] == 250_000_000
     assert bench.config_of("B", 1)["parallelism"] == "1 GPU"
+
+
+def test_cpu_sample_is_the_whole_workload_b_and_a_bounded_sample_beyond(monkeypatch):
+    monkeypatch.setitem(bench.WORKLOADS, "tinyB", (4096, 4096, "unique", 0.0))
+    Rk, Sk, what = bench.cpu_join_sample("tinyB", 1)
+    assert Rk.size == Sk.size == 4096 and "whole workload" in what and sorted(Rk.tolist()) == list(range(4096))
+    monkeypatch.setattr(bench, "CPU_SAMPLE_MAX", 5000)
+    Rk, Sk, what = bench.cpu_join_sample("tinyB", 8)          # 8 GPUs, weak scaling: 32768 tuples per side in total
+    assert Rk.size == Sk.size == 5000 and "sample" in what
+
+
+def test_config5_record_speedup_uses_the_cached_one_gpu_value(tmp_path, monkeypatch):
+    monkeypatch.setattr(bench, "CFG5_CACHE", str(tmp_path / "cfg5.json"))
+    one = bench.cfg5_record(50.0, 1)
+    assert one["speedup_vs_1gpu"] == 1.0 and abs(one["value"] - 4e9 / 0.05) < 1
+    eight = bench.cfg5_record(8.0, 8, shuffle="pcp")
+    assert abs(eight["speedup_vs_1gpu"] - 50.0 / 8.0) < 1e-9 and "this box" in eight["one_gpu_source"] and eight["per_gpu_R"] == 250_000_000
+    monkeypatch.setattr(bench, "CFG5_CACHE", str(tmp_path / "missing.json"))
+    fallback = bench.cfg5_record(8.0, 8)
+    assert fallback["one_gpu_value"] == bench.CFG5_1GPU_MEASURED["value"] and "profiles/" in fallback["one_gpu_source"]
