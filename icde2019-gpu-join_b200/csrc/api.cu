@@ -112,14 +112,13 @@ struct JoinCfg { int threads, cap, u; join_fn agg, mat; size_t smem_agg, smem_ma
 // <threads, build chunk, probe chunk, R ring slots, S ring slots>
 #define GJ_JC(T, C, U, NR, NS, OPT) { T, C, U, join_kernel<T, C, U, NR, NS, false, OPT>, join_kernel<T, C, U, NR, NS, true, OPT>, \
                                  JoinSmem<C, U, NR, NS, false>::total, JoinSmem<C, U, NR, NS, true>::total }
+// The winner of round 1's sweep over seven shapes (rings of 3 + 3 slots, atomic build) plus the small-ring shape
+// the materialising join needs (its 32 KB of pair staging does not fit next to 3 + 3 rings) and, as a structurally
+// different fallback, the optimistic (store-then-verify) build, measured 3 % slower on B200.
 static const JoinCfg kJoin[] = {
     GJ_JC(1024, 4096, 4096, 3, 3, false),  // 0 default: two whole steps (build + probe chunk) in flight
-    GJ_JC(1024, 4096, 4096, 3, 3, true),   // 1 optimistic (atomic-free when collision-free) build
-    GJ_JC(1024, 4096, 4096, 2, 2, false),  // 2 small rings (fits the 16 KB pair staging when materialising)
-    GJ_JC(1024, 4096, 4096, 2, 2, true),   // 3
-    GJ_JC(768, 4096, 4096, 3, 3, true),    // 4
-    GJ_JC(512, 4096, 4096, 3, 3, true),    // 5
-    GJ_JC(1024, 4096, 2048, 3, 4, true),   // 6
+    GJ_JC(1024, 4096, 4096, 2, 2, false),  // 1 small rings: the materialising join
+    GJ_JC(1024, 4096, 4096, 3, 3, true),   // 2 optimistic (atomic-free when collision-free) build
 };
 static const int kNumJoin = (int)(sizeof(kJoin) / sizeof(kJoin[0]));
 // late-materialisation aggregate (payload = row id, side-table gathers on a match): the default shape
@@ -647,7 +646,7 @@ static int enqueue_join(gj_ctx* ctx, cudaStream_t s, const tup_t* bld, const tup
                         bool bld_is_S = false) {
     (void)n_bld;
     int cfg = late ? 0 : (int)ctx->opt_join_cfg;
-    if (mat && kJoin[cfg].smem_mat > (size_t)227 * 1024) cfg = 2;   // pair staging needs 16 KB: smaller rings
+    if (mat && kJoin[cfg].smem_mat > (size_t)227 * 1024) cfg = 1;   // pair staging needs 32 KB: smaller rings
     const JoinCfg& jc = kJoin[cfg];
     JoinArgs a;
     a.bld = bld; a.prb = prb;

@@ -197,7 +197,7 @@ def test_build_partition_larger_than_shared_memory(gj, orc, eng, torch_cuda):
     Sk = np.where(rng.random(nS) < 0.01, 42, rng.integers(0, 1000, nS)).astype(np.int32)
     Rp, Sp = rnd(rng, nR, -1000, 1000), rnd(rng, nS, -1000, 1000)
     want = orc.join_check(Rk, Rp, Sk, Sp)
-    for jc in (0, 2, 6):
+    for jc in (0, 1, 2):
         eng.set_option("join_cfg", jc)
         got = eng.join_aggregate(*dev(torch_cuda, Rk, Rp, Sk, Sp))
         assert (got.matches, got.checksum) == (want.matches, want.checksum), jc
