@@ -226,7 +226,7 @@ int gj_stage_finish(gj_ctx* ctx, uint64_t* matches, uint64_t* checksum);
  * S pass 2 (CUDA events on the streams they ran on; 0 where a pass did not run). */
 int gj_stage_pass_ms(gj_ctx* ctx, float pass_ms[4]);
 
-/* ---- sharded "partition, then push" pipeline (multi-GPU, default) -------
+/* ---- sharded "partition, then push" pipeline (multi-GPU, alternative to gj_pcp_*)
  * Radix field = [gpu bits | local bits] (destination = (key >> local_bits) & (n_gpus-1), as above).
  * Every GPU partitions its OWN shard on all gpu+local bits in two passes; the second pass stores
  * its runs straight into the destination GPU's final partition buffer (local or peer-mapped over
