@@ -13,9 +13,14 @@
 //   join_kernel
 //        -> decompose_chains (:843-874, probe-side splitting becomes the unit list written by
 //           plan_kernel), join_partitioned_aggregate (:885-1095) and join_partitioned_results
-//           (:1107-1416); fed by a TMA bulk-copy ring (cp.async.bulk + mbarrier).
+//           (:1107-1416); <..., LATE>: join_partitioned_varpayload (:1420-1557); fed by a TMA
+//           bulk-copy ring (cp.async.bulk + mbarrier).
+//   np_build_kernel / np_probe_kernel, np_build_perfect_kernel / np_probe_perfect_kernel
+//        -> build_ht_chains / chains_probing (:681-742), build_perfect_array / probe_perfect_array
+//           (:628-668): the non-partitioned joins.
 //   subhist_tiles_kernel, pp_cursor_kernel, scatter_kernel<..., PUSH>   (section 3c)
-//   pcp_layout_kernel, pcp_copy_kernel                                  (section 3d)
+//   pcp_layout_kernel, pcp_copy_kernel, pcp_self_hist_kernel, pcp_push_kernel, pcp_wait_kernel,
+//   pcp_sum_hist_kernel, pcp_hist_push_kernel, pcp_hist_gather_kernel   (section 3d)
 //        -> no reference counterpart (the reference is single-GPU, hash_join_clustered_probe.cu
 //           :1001,1685 only select a device): the multi-GPU exchange, SURVEY.md section 8e.
 //
