@@ -301,6 +301,31 @@ def test_pcp_stage_positions_cover_every_chunk_once(gj):
     assert sorted(seen) == [(k, s) for k in range(n1) for s in range(pieces[k])]
 
 
+def test_staged_receiver_prefix_property():
+    """What gj_pcp_recv relies on: the receive layout places first-pass partition j at the sum of the counts of all
+    j' < j, fine partitions inside it in order, so when the fine counts arrive stage by stage (ascending j) a scan over
+    ALL 2^B counters -- later stages still zero -- already gives the final offsets of every partition of the stages
+    that have landed, and the final scan leaves them unchanged.  Also: the units of a stage only involve its partitions."""
+    rng = np.random.default_rng(12)
+    bl, b2, K = 4, 5, 3
+    nj, nb = 1 << bl, 1 << (bl + b2)
+    fine = rng.integers(0, 40, nb)
+    fine[rng.integers(0, nb, 30)] = 0
+    final = np.concatenate(([0], np.cumsum(fine)))
+    seen = np.zeros(nb, dtype=np.int64)
+    for k in range(K):
+        j_lo, j_hi = k * nj // K, (k + 1) * nj // K
+        p_lo, p_hi = j_lo << b2, j_hi << b2
+        seen[p_lo:p_hi] = fine[p_lo:p_hi]                       # pcp_sum_hist_kernel of stage k
+        off = np.concatenate(([0], np.cumsum(seen)))            # full-range scan, later stages still zero
+        assert np.array_equal(off[:p_hi + 1], final[:p_hi + 1])
+        # first-pass partition j of the receive buffer = [off[j << b2], off[(j + 1) << b2]): the tiles of the stage
+        coarse = fine.reshape(nj, -1).sum(axis=1)
+        recv_off = np.concatenate(([0], np.cumsum(coarse)))
+        assert np.array_equal(off[[j << b2 for j in range(j_lo, j_hi + 1)]], recv_off[j_lo:j_hi + 1])
+    assert np.array_equal(off, final)
+
+
 def test_pcp_copy_piece_arithmetic_model():
     """numpy model of pcp_layout_kernel's piece prefix and pcp_copy_kernel's per-piece arithmetic
     (csrc/kernels.cuh section 3d), both piece-to-CTA assignments: every tuple of every chunk is copied
