@@ -22,7 +22,7 @@ the same per-GPU shard sizes (weak scaling), radix-sharded with an all-to-all sh
                 join) on a bounded sample of the same workload
   materialize   the materialising join (exact-size pair output) on the same inputs
   config5       BASELINE config 5 (2e9 x 2e9 tuples in total, strong scaling): the per-GPU share
-                2e9/N, device-generated, 3 timed steps, with the speed-up over the 1-GPU run
+                2e9/N, device-generated, 5 timed steps after 2 warm-ups, with the speed-up over the 1-GPU run
   reference_cuda  the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref/bench_ref),
                 same inputs via .bin files, run on the same GPU in the same run
 
@@ -344,7 +344,7 @@ CFG5_1GPU_MEASURED = {"value": 75.28e9, "ms_per_step": 53.1,
                       "source": "profiles/r2_final/bench.log, key config5 (round 2, same kernels; no 1-GPU run of this bench found on this box)"}
 
 
-def run_cfg5_share(torch, gj, n_gpus, rank, dev_index, sharded=None, steps=3, warm=1, opts=()):
+def run_cfg5_share(torch, gj, n_gpus, rank, dev_index, sharded=None, steps=5, warm=2, opts=()):
     """BASELINE config 5: |R|=|S|=2e9 in total, this GPU generates and joins rows [rank, rank+1) * 2e9/N.
     Returns (ms per step on this rank, matches, checksum of the last step, expected matches, expected checksum)."""
     n_tot = WORKLOADS["cfg5"][0]
@@ -390,10 +390,10 @@ def run_cfg5_share(torch, gj, n_gpus, rank, dev_index, sharded=None, steps=3, wa
     return ms, m, c, want, tm
 
 
-def cfg5_record(ms_step, n_gpus, shuffle=None, tm=None):
+def cfg5_record(ms_step, n_gpus, shuffle=None, tm=None, steps=5, warm=2):
     n_tot = WORKLOADS["cfg5"][0]
     rec = {"workload": workload_name("cfg5"), "scaling": "strong", "n_gpus": n_gpus, "per_gpu_R": n_tot // n_gpus,
-           "per_gpu_S": n_tot // n_gpus, "steps": 3, "warmup": 1, "ms_per_step": ms_step,
+           "per_gpu_S": n_tot // n_gpus, "steps": steps, "warmup": warm, "ms_per_step": ms_step,
            "value": 2 * n_tot / (ms_step * 1e-3), "unit": UNIT}
     if shuffle:
         rec["shuffle"] = shuffle
@@ -593,7 +593,7 @@ def cfg5_single(args):
     gj = ge.load_package()
     torch.cuda.set_device(0)
     launches0 = gj.kernel_launch_count()
-    ms5, m5, c5, want5, t = run_cfg5_share(torch, gj, 1, 0, 0, steps=min(args.steps, 3), opts=args.opt)
+    ms5, m5, c5, want5, t = run_cfg5_share(torch, gj, 1, 0, 0, steps=min(args.steps, 5), opts=args.opt)
     if (m5, c5) != want5:
         raise SystemExit(f"WRONG RESULT: {m5} {c5}, expected {want5}")
     n = WORKLOADS["cfg5"][0]
@@ -602,7 +602,7 @@ def cfg5_single(args):
     # three-pass plan: every pass 16 B/tuple + the third level's sub-histogram (8 B/tuple)
     alg = (16.0 * passes + (8.0 if passes == 3 else 0.0)) * 2 * n
     line = base_line(args, "cfg5", 1)
-    line.update({"steps": min(args.steps, 3), "warmup": 1, "value": 2 * n / (ms5 * 1e-3), "ms_per_step": ms5,
+    line.update({"steps": min(args.steps, 5), "warmup": 2, "value": 2 * n / (ms5 * 1e-3), "ms_per_step": ms5,
                  "e2e": None, "gpu_launches": int(gj.kernel_launch_count() - launches0),
                  "roofline": {"bound": "hbm", "kernel": f"scatter passes ({passes} per relation" + (" + sub-histogram of the third level)" if passes == 3 else ")"),
                               "achieved": alg / (t["part_ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
@@ -611,7 +611,7 @@ def cfg5_single(args):
                  "plan": {"radix_bits": t["radix_bits"], "pass1_bits": t["pass1_bits"], "pass2_bits": t["pass2_bits"], "pass3_bits": t.get("pass3_bits")},
                  "checked": f"matches == {want5[0]} and checksum == {want5[1]}"})
     line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
-    line["config5"] = cfg5_record(ms5, 1)
+    line["config5"] = cfg5_record(ms5, 1, steps=min(args.steps, 5))
     print(json.dumps(line))
 
 
