@@ -159,9 +159,8 @@ def test_reference_driver_links_against_the_library():
     """INTEGRATION.md section 1, checked where the reference sources exist (this container): the reference's driver
     objects link against libgpujoin.so, which resolves the operator symbol main.cu's algorithm table needs."""
     import subprocess
-    ref_obj = os.path.join(ROOT, "oracle", "_ref", "obj", "main.o")
-    if not os.path.isdir("/root/reference/src") and not os.path.exists(ref_obj):
-        pytest.skip("reference sources absent")
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference sources absent (the recipe compiles them from where they lie)")
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "dropin"], check=True)
     exe = os.path.join(ROOT, "oracle", "_ref", "bench_dropin")
     undefined = subprocess.run(["nm", "-u", exe], capture_output=True, text=True, check=True).stdout
