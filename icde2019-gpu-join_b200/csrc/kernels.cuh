@@ -885,7 +885,8 @@ pcp_push_kernel(const uint32_t* __restrict__ fine, unsigned char* const* __restr
     unsigned char* ctrl = peer_ctrl[d];
     uint32_t* flags = reinterpret_cast<uint32_t*>(ctrl);
     uint32_t* fine_in = reinterpret_cast<uint32_t*>(ctrl + pcp_ctrl_flag_bytes(n_gpus)) + (((size_t)which * n_gpus + rank) << B);
-    if (!status[0]) {
+    if (!status[0]) {   // (aborted exchange: the tables keep the previous join's counts -- sums within the same buffers' capacity;
+                        //  whatever the receiver then computes is discarded, gj_pcp_finish returns the overflow error)
         const uint32_t* src = fine + ((size_t)d << B);
         for (uint32_t p = p_lo + threadIdx.x; p < p_hi; p += 256) fine_in[p] = src[p];
     }
